@@ -1,0 +1,722 @@
+// capi.cu -- the extern "C" boundary (include/flate_b200.h) over the CUDA pipelines.
+// No CPU fallback anywhere: without a CUDA device every entry point fails with FB200_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/flate_b200.h"
+#include "common.cuh"
+#include "inflate.cuh"
+#include "pipeline.cuh"
+
+namespace fb {
+static thread_local char g_cuda_err[256] = "";
+void set_last_cuda_error(cudaError_t e, const char* file, int line) {
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s (%s:%d)", cudaGetErrorString(e), file, line);
+}
+
+__global__ void plan_simple_blocks_kernel(uint64_t n, uint32_t nblocks, uint32_t kind, BlockPlan* __restrict__ plans,
+                                          uint32_t* __restrict__ nblocks_dev) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *nblocks_dev = nblocks;
+    if (b >= nblocks) return;
+    BlockPlan pl;
+    pl.tok_begin = 0;
+    pl.tok_count = 0;
+    pl.in_begin = (uint64_t)b * kMaxStore;  // deflate.zig:456: 65535-byte slices
+    const uint64_t rem = n - pl.in_begin;
+    pl.in_len = (uint32_t)(rem < kMaxStore ? rem : kMaxStore);
+    pl.has_input = 1;
+    pl.eof = b + 1 == nblocks;
+    pl.kind = kind;
+    plans[b] = pl;
+}
+
+// zero [0, ceil(total_bits/32)+2) words of the output, total_bits read on the device
+__global__ void zero_output_kernel(uint32_t* __restrict__ out, const uint64_t* __restrict__ total_bits, uint64_t cap_words) {
+    uint64_t words = ((*total_bits + 31) >> 5) + 2;
+    if (words > cap_words) words = cap_words;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint4* o4 = reinterpret_cast<uint4*>(out);
+    const uint64_t n4 = words / 4;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) o4[i] = make_uint4(0, 0, 0, 0);
+    for (uint64_t i = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) out[i] = 0;
+}
+}  // namespace fb
+
+using namespace fb;
+
+namespace {
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+}  // namespace
+
+struct fb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    // LZ77 workspace
+    DevBuf<uint16_t> link, exits, gexits, gentry, entry;
+    DevBuf<uint32_t> r_full, r_quarter, nx, bitmap, chunk_tokens, tok_offset, tokens, cut_rp;
+    // block writer workspace
+    DevBuf<BlockPlan> plans;
+    DevBuf<BlockDesc> descs;
+    DevBuf<uint32_t> lit_freq, dist_freq;
+    // staging
+    DevBuf<uint8_t> d_in, d_out;
+    uint32_t* d_scalars = nullptr;  // [0] total_tokens [1] nblocks ; +8: total_bits (u64)
+    uint64_t* h_scalars = nullptr;  // pinned: [0] total_bits [1] total_tokens | nblocks<<32
+    // inflate workspace
+    DevBuf<uint64_t> m_desc;        // member descriptors / results
+    std::vector<uint64_t> h_members;
+};
+
+static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+int fb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+const char* fb200_last_cuda_error(void) { return g_cuda_err; }
+const char* fb200_strerror(int code) {
+    static const char* names[] = {"Ok", "EndOfStream", "InvalidCode", "InvalidMatch", "InvalidBlockType",
+                                  "WrongStoredBlockNlen", "InvalidDynamicBlockHeader", "OversubscribedHuffmanTree",
+                                  "IncompleteHuffmanTree", "MissingEndOfBlockCode", "BadGzipHeader", "BadZlibHeader",
+                                  "WrongGzipChecksum", "WrongGzipSize", "WrongZlibChecksum", "UnfinishedBits",
+                                  "InvalidState", "NoSpaceLeft", "InvalidArgument", "CudaError", "NoDevice"};
+    if (code < 0 || code > 20) return "Unknown";
+    return names[code];
+}
+uint64_t fb200_kernel_launches(const fb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int fb200_ctx_create(int device, fb200_ctx** out) {
+    if (!out) return FB200_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FB200_NO_DEVICE;
+    if (device < 0 || device >= ndev) return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(device));
+    fb200_ctx* c = new (std::nothrow) fb200_ctx();
+    if (!c) return FB200_INVALID_ARGUMENT;
+    c->device = device;
+    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    FB_CUDA_CHECK(cudaMalloc(&c->d_scalars, 64));
+    FB_CUDA_CHECK(cudaMallocHost(&c->h_scalars, 64));
+    *out = c;
+    return FB200_OK;
+}
+
+void fb200_ctx_destroy(fb200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->link.release(); c->exits.release(); c->gexits.release(); c->gentry.release(); c->entry.release();
+    c->r_full.release(); c->r_quarter.release(); c->nx.release(); c->bitmap.release(); c->chunk_tokens.release();
+    c->tok_offset.release(); c->tokens.release(); c->cut_rp.release(); c->plans.release(); c->descs.release();
+    c->lit_freq.release(); c->dist_freq.release(); c->d_in.release(); c->d_out.release(); c->m_desc.release();
+    if (c->d_scalars) cudaFree(c->d_scalars);
+    if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+size_t fb200_compress_bound(size_t n, int mode) {
+    (void)mode;
+    // stored blocks cost 5 bytes each; an unstorable Huffman block of incompressible bytes < 9/8 n + header
+    return n + (n >> 3) + (n / 32768 + 2) * 640 + 64;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+static int ensure_lz77(fb200_ctx* c, size_t n) {
+    const size_t nchunks = (n + kChunk - 1) / kChunk + 1;
+    const size_t ngroups = (nchunks + kGroup - 1) / kGroup + 1;
+    FB_CUDA_CHECK(c->link.ensure(n + 64));
+    FB_CUDA_CHECK(c->r_full.ensure(n + 64));
+    FB_CUDA_CHECK(c->r_quarter.ensure(n + 64));
+    FB_CUDA_CHECK(c->nx.ensure(n + 64));
+    FB_CUDA_CHECK(c->exits.ensure(nchunks * kEntries));
+    FB_CUDA_CHECK(c->gexits.ensure(ngroups * kEntries));
+    FB_CUDA_CHECK(c->gentry.ensure(ngroups));
+    FB_CUDA_CHECK(c->entry.ensure(nchunks));
+    FB_CUDA_CHECK(c->bitmap.ensure(nchunks * (kChunk / 32)));
+    FB_CUDA_CHECK(c->chunk_tokens.ensure(nchunks));
+    FB_CUDA_CHECK(c->tok_offset.ensure(nchunks));
+    FB_CUDA_CHECK(c->tokens.ensure(n + 64));
+    FB_CUDA_CHECK(c->cut_rp.ensure(n / kTokensPerBlock + 4));
+    return FB200_OK;
+}
+static int ensure_blocks(fb200_ctx* c, size_t max_blocks) {
+    FB_CUDA_CHECK(c->plans.ensure(max_blocks));
+    FB_CUDA_CHECK(c->descs.ensure(max_blocks));
+    FB_CUDA_CHECK(c->lit_freq.ensure(max_blocks * kNumLit));
+    FB_CUDA_CHECK(c->dist_freq.ensure(max_blocks * kNumDist));
+    return FB200_OK;
+}
+static Lz77Buffers lz77_view(fb200_ctx* c) {
+    Lz77Buffers b;
+    b.link = c->link.p; b.r_full = c->r_full.p; b.r_quarter = c->r_quarter.p; b.nx = c->nx.p;
+    b.exits = c->exits.p; b.gexits = c->gexits.p; b.gentry = c->gentry.p; b.entry = c->entry.p;
+    b.bitmap = c->bitmap.p; b.chunk_tokens = c->chunk_tokens.p; b.tok_offset = c->tok_offset.p;
+    b.total_tokens = c->d_scalars; b.tokens = c->tokens.p; b.cut_rp = c->cut_rp.p;
+    return b;
+}
+
+static const uint8_t kGzipHeader[10] = {0x1f, 0x8b, 0x08, 0, 0, 0, 0, 0, 0, 0x03};  // container.zig:64
+static const uint8_t kZlibHeader[2] = {0x78, 0x9c};                                  // container.zig:78
+static inline size_t header_size(int container) { return container == FB200_GZIP ? 10 : container == FB200_ZLIB ? 2 : 0; }
+static inline size_t footer_size(int container) { return container == FB200_GZIP ? 8 : container == FB200_ZLIB ? 4 : 0; }
+
+// Runs the deflate body on the device: d_out[hdr .. hdr+body) ; returns body end (bytes from d_out start)
+static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint8_t* d_in, size_t n, uint8_t* d_out,
+                               size_t cap, size_t* end_bytes, bool final_flush, cudaStream_t st) {
+    if (container < 0 || container > 2) return FB200_INVALID_ARGUMENT;
+    if (((uintptr_t)d_out & 15) != 0) return FB200_INVALID_ARGUMENT;
+    const size_t bound = fb200_compress_bound(n, mode) + header_size(container) + footer_size(container);
+    if (cap < bound) return FB200_NO_SPACE_LEFT;
+    uint32_t* nblocks_dev = c->d_scalars + 1;
+    uint64_t* total_bits_dev = reinterpret_cast<uint64_t*>(c->d_scalars + 2);
+    uint32_t max_blocks;
+    const uint32_t* tokens = nullptr;
+    LevelArgs lv;
+    if (level_args(mode, lv)) {
+        if (n > (1ull << 31)) return FB200_INVALID_ARGUMENT;  // single-stream position space is 32-bit
+        int rc = ensure_lz77(c, n);
+        if (rc) return rc;
+        max_blocks = (uint32_t)(n / kTokensPerBlock + 3);
+        if ((rc = ensure_blocks(c, max_blocks))) return rc;
+        Lz77Buffers b = lz77_view(c);
+        FB_CUDA_CHECK(lz77_tokenize(b, d_in, (uint32_t)n, lv, st));
+        c->launches += n ? 10 : 0;
+        FB_CUDA_CHECK(plan_level_blocks(b.total_tokens, b.cut_rp, (uint32_t)n, max_blocks, final_flush ? 1 : 0, c->plans.p,
+                                        nblocks_dev, st));
+        FB_CUDA_CHECK(histogram_tokens(b.tokens, c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, st));
+        c->launches += 2;
+        tokens = b.tokens;
+    } else if (mode == FB200_MODE_HUFFMAN || mode == FB200_MODE_STORE) {
+        const uint64_t nb64 = n / kMaxStore + 1;
+        if (nb64 > 0x7fffffffull) return FB200_INVALID_ARGUMENT;
+        max_blocks = (uint32_t)nb64;
+        int rc = ensure_blocks(c, max_blocks);
+        if (rc) return rc;
+        plan_simple_blocks_kernel<<<(max_blocks + 255) / 256, 256, 0, st>>>(n, max_blocks,
+                                                                            mode == FB200_MODE_HUFFMAN ? kHuffmanBlock : 3u,
+                                                                            c->plans.p, nblocks_dev);
+        FB_CUDA_CHECK(cudaGetLastError());
+        c->launches += 1;
+        if (mode == FB200_MODE_HUFFMAN) {
+            FB_CUDA_CHECK(histogram_bytes(d_in, c->plans.p, max_blocks, c->lit_freq.p, st));
+            c->launches += 1;
+        }
+    } else {
+        return FB200_INVALID_ARGUMENT;
+    }
+    FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, c->descs.p, st));
+    FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, header_size(container) * 8, total_bits_dev, st));
+    zero_output_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<uint32_t*>(d_out), total_bits_dev, cap / 4);
+    FB_CUDA_CHECK(cudaGetLastError());
+    if (container == FB200_GZIP) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kGzipHeader, 10, cudaMemcpyHostToDevice, st));
+    if (container == FB200_ZLIB) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kZlibHeader, 2, cudaMemcpyHostToDevice, st));
+    FB_CUDA_CHECK(pack_blocks(d_in, tokens, c->descs.p, nblocks_dev, max_blocks, reinterpret_cast<uint32_t*>(d_out), st));
+    c->launches += 4;
+    FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    *end_bytes = (size_t)((c->h_scalars[0] + 7) >> 3);
+    return FB200_OK;
+}
+
+// host-side checksums for the container footer (container.zig:85-109).  The device path for
+// these is SURVEY.md §8(f) rank 1; the footer is 8 bytes of framing outside the hot path.
+static uint32_t crc32_host(const uint8_t* p, size_t n) {
+    static uint32_t table[8][256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; i++)
+            for (int t = 1; t < 8; t++) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xff];
+        ready = true;
+    }
+    uint32_t c = 0xffffffffu;
+    while (n >= 8) {
+        uint32_t a, b;
+        memcpy(&a, p, 4);
+        memcpy(&b, p + 4, 4);
+        a ^= c;
+        c = table[7][a & 0xff] ^ table[6][(a >> 8) & 0xff] ^ table[5][(a >> 16) & 0xff] ^ table[4][a >> 24] ^
+            table[3][b & 0xff] ^ table[2][(b >> 8) & 0xff] ^ table[1][(b >> 16) & 0xff] ^ table[0][b >> 24];
+        p += 8;
+        n -= 8;
+    }
+    while (n--) c = table[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+    return ~c;
+}
+static uint32_t adler32_host(const uint8_t* p, size_t n) {
+    uint32_t a = 1, b = 0;
+    while (n) {
+        size_t k = n < 5552 ? n : 5552;
+        n -= k;
+        while (k--) {
+            a += *p++;
+            b += a;
+        }
+        a %= 65521;
+        b %= 65521;
+    }
+    return (b << 16) | a;
+}
+static size_t make_footer(int container, const uint8_t* plain, size_t n, uint8_t* f) {
+    if (container == FB200_GZIP) {
+        const uint32_t c = crc32_host(plain, n), sz = (uint32_t)n;
+        for (int i = 0; i < 4; i++) f[i] = (uint8_t)(c >> (8 * i)), f[4 + i] = (uint8_t)(sz >> (8 * i));
+        return 8;
+    }
+    if (container == FB200_ZLIB) {
+        const uint32_t c = adler32_host(plain, n);
+        for (int i = 0; i < 4; i++) f[i] = (uint8_t)(c >> (24 - 8 * i));
+        return 4;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int fb200_compress_device(fb200_ctx* c, int container, int mode, const void* d_in, size_t n, void* d_out, size_t cap,
+                          size_t* out_len, void* stream) {
+    if (!c || !out_len || (!d_in && n)) return FB200_INVALID_ARGUMENT;
+    if (container != FB200_RAW) return FB200_INVALID_ARGUMENT;  // footer checksum needs the host copy: use fb200_compress
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    size_t end = 0;
+    int rc = deflate_body_device(c, container, mode, (const uint8_t*)d_in, n, (uint8_t*)d_out, cap, &end, true, st);
+    if (rc) return rc;
+    *out_len = end;
+    return FB200_OK;
+}
+
+int fb200_compress(fb200_ctx* c, int container, int mode, const uint8_t* in, size_t n, uint8_t* out, size_t cap,
+                   size_t* out_len) {
+    if (!c || !out_len || (!in && n) || !out) return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    const size_t bound = fb200_compress_bound(n, mode) + 32;
+    FB_CUDA_CHECK(c->d_in.ensure(n + 512));
+    FB_CUDA_CHECK(c->d_out.ensure(round_up(bound, 16)));
+    cudaStream_t st = c->stream;
+    if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
+    size_t end = 0;
+    int rc = deflate_body_device(c, container, mode, c->d_in.p, n, c->d_out.p, c->d_out.cap, &end, true, st);
+    if (rc) return rc;
+    uint8_t footer[8];
+    const size_t flen = make_footer(container, in, n, footer);
+    if (end + flen > cap) return FB200_NO_SPACE_LEFT;
+    FB_CUDA_CHECK(cudaMemcpyAsync(out, c->d_out.p, end, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    memcpy(out + end, footer, flen);
+    *out_len = end + flen;
+    return FB200_OK;
+}
+
+// ---- test seams ----
+int fb200_debug_tokens(fb200_ctx* c, int level, const uint8_t* in, size_t n, uint32_t* tokens, size_t cap, size_t* ntok) {
+    LevelArgs lv;
+    if (!c || !level_args(level, lv) || !ntok || n > (1ull << 31)) return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    FB_CUDA_CHECK(c->d_in.ensure(n + 512));
+    int rc = ensure_lz77(c, n);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
+    Lz77Buffers b = lz77_view(c);
+    FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, (uint32_t)n, lv, st));
+    c->launches += n ? 10 : 0;
+    uint32_t total = 0;
+    FB_CUDA_CHECK(cudaMemcpyAsync(&total, b.total_tokens, 4, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    *ntok = total;
+    if (total > cap) return FB200_NO_SPACE_LEFT;
+    if (total) FB_CUDA_CHECK(cudaMemcpy(tokens, b.tokens, (size_t)total * 4, cudaMemcpyDeviceToHost));
+    return FB200_OK;
+}
+
+int fb200_debug_match_tables(fb200_ctx* c, int level, const uint8_t* in, size_t n, uint32_t* r_full, uint32_t* r_quarter) {
+    LevelArgs lv;
+    if (!c || !level_args(level, lv) || n > (1ull << 31) || n == 0) return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    FB_CUDA_CHECK(c->d_in.ensure(n + 512));
+    int rc = ensure_lz77(c, n);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
+    Lz77Buffers b = lz77_view(c);
+    FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, (uint32_t)n, lv, st));
+    c->launches += 10;
+    FB_CUDA_CHECK(cudaMemcpyAsync(r_full, b.r_full, n * 4, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaMemcpyAsync(r_quarter, b.r_quarter, n * 4, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return FB200_OK;
+}
+
+int fb200_debug_block_write(fb200_ctx* c, int kind, const uint32_t* tokens, size_t ntok, int eof, const uint8_t* input,
+                            size_t input_len, int has_input, uint8_t* out, size_t cap, size_t* out_len) {
+    if (!c || kind < 0 || kind > 2 || !out_len || ntok > (1u << 20)) return FB200_INVALID_ARGUMENT;
+    if (kind == 2 && !has_input) return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    FB_CUDA_CHECK(c->d_in.ensure(input_len + 512));
+    FB_CUDA_CHECK(c->tokens.ensure(ntok + 64));
+    int rc = ensure_blocks(c, 2);
+    if (rc) return rc;
+    const size_t bound = round_up(ntok * 8 + input_len + input_len / 8 + 8192, 16);
+    FB_CUDA_CHECK(c->d_out.ensure(bound));
+    if (has_input && input_len) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, input, input_len, cudaMemcpyHostToDevice, st));
+    if (ntok) FB_CUDA_CHECK(cudaMemcpyAsync(c->tokens.p, tokens, ntok * 4, cudaMemcpyHostToDevice, st));
+    BlockPlan pl;
+    pl.tok_begin = 0;
+    pl.tok_count = (uint32_t)ntok;
+    pl.in_begin = 0;
+    pl.in_len = has_input ? (uint32_t)input_len : 0;
+    pl.has_input = has_input ? 1 : 0;
+    pl.eof = eof ? 1 : 0;
+    pl.kind = (uint32_t)kind;
+    if (has_input && input_len > kMaxStore) pl.in_len = (uint32_t)input_len;  // not storable; never dereferenced
+    uint32_t one = 1;
+    uint32_t* nblocks_dev = c->d_scalars + 1;
+    uint64_t* total_bits_dev = reinterpret_cast<uint64_t*>(c->d_scalars + 2);
+    FB_CUDA_CHECK(cudaMemcpyAsync(c->plans.p, &pl, sizeof pl, cudaMemcpyHostToDevice, st));
+    FB_CUDA_CHECK(cudaMemcpyAsync(nblocks_dev, &one, 4, cudaMemcpyHostToDevice, st));
+    if (kind == 2) FB_CUDA_CHECK(histogram_bytes(c->d_in.p, c->plans.p, 1, c->lit_freq.p, st));
+    else FB_CUDA_CHECK(histogram_tokens(c->tokens.p, c->plans.p, nblocks_dev, 1, c->lit_freq.p, c->dist_freq.p, st));
+    FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, 1, c->lit_freq.p, c->dist_freq.p, c->descs.p, st));
+    FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, 0, total_bits_dev, st));
+    zero_output_kernel<<<64, 256, 0, st>>>(reinterpret_cast<uint32_t*>(c->d_out.p), total_bits_dev, c->d_out.cap / 4);
+    FB_CUDA_CHECK(cudaGetLastError());
+    FB_CUDA_CHECK(pack_blocks(c->d_in.p, kind == 2 ? nullptr : c->tokens.p, c->descs.p, nblocks_dev, 1,
+                              reinterpret_cast<uint32_t*>(c->d_out.p), st));
+    c->launches += 5;
+    FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    const size_t end = (size_t)((c->h_scalars[0] + 7) >> 3);
+    if (end > cap) return FB200_NO_SPACE_LEFT;
+    if (end) FB_CUDA_CHECK(cudaMemcpy(out, c->d_out.p, end, cudaMemcpyDeviceToHost));
+    *out_len = end;
+    return FB200_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// inflate entry points
+// =============================================================================================
+static int run_members(fb200_ctx* c, int container, const uint8_t* d_in, const MemberDesc* h_desc, size_t k, uint8_t* d_out,
+                       MemberResult* h_res, cudaStream_t st) {
+    const size_t desc_words = k * (sizeof(MemberDesc) / 8), res_words = k * (sizeof(MemberResult) / 8);
+    FB_CUDA_CHECK(c->m_desc.ensure(desc_words + res_words));
+    MemberDesc* d_desc = reinterpret_cast<MemberDesc*>(c->m_desc.p);
+    MemberResult* d_res = reinterpret_cast<MemberResult*>(c->m_desc.p + desc_words);
+    FB_CUDA_CHECK(cudaMemcpyAsync(d_desc, h_desc, k * sizeof(MemberDesc), cudaMemcpyHostToDevice, st));
+    FB_CUDA_CHECK(inflate_members(container, d_in, d_desc, (uint32_t)k, d_out, d_res, st));
+    c->launches += 1;
+    FB_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, k * sizeof(MemberResult), cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return FB200_OK;
+}
+
+extern "C" {
+
+int fb200_decompress_members_device(fb200_ctx* c, int container, const void* d_in, const uint64_t* in_off,
+                                    const uint64_t* in_len, size_t k, void* d_out, const uint64_t* out_off,
+                                    const uint64_t* out_cap, uint64_t* out_len, uint64_t* consumed, int* status,
+                                    void* stream) {
+    if (!c || container < 0 || container > 2 || (k && (!in_off || !in_len || !out_off || !out_cap))) return FB200_INVALID_ARGUMENT;
+    if (k > 0x7fffffffu) return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    std::vector<MemberDesc> desc(k);
+    std::vector<MemberResult> res(k);
+    for (size_t i = 0; i < k; i++) desc[i] = MemberDesc{in_off[i], in_len[i], out_off[i], out_cap[i], 0};
+    int rc = run_members(c, container, (const uint8_t*)d_in, desc.data(), k, (uint8_t*)d_out, res.data(), st);
+    if (rc) return rc;
+    int first = FB200_OK;
+    for (size_t i = 0; i < k; i++) {
+        if (out_len) out_len[i] = res[i].out_len;
+        if (consumed) consumed[i] = res[i].consumed;
+        if (status) status[i] = (int)res[i].status;
+        if (first == FB200_OK && res[i].status) first = (int)res[i].status;
+    }
+    return first;
+}
+
+int fb200_decompress_members(fb200_ctx* c, int container, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len,
+                             size_t k, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                             uint64_t* consumed, int* status) {
+    if (!c || (k && (!in || !out || !in_off || !in_len || !out_off || !out_cap || !out_len))) return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    uint64_t in_end = 0, out_end = 0;
+    for (size_t i = 0; i < k; i++) {
+        if (in_off[i] + in_len[i] > in_end) in_end = in_off[i] + in_len[i];
+        if (out_off[i] + out_cap[i] > out_end) out_end = out_off[i] + out_cap[i];
+    }
+    FB_CUDA_CHECK(c->d_in.ensure(in_end + 512));
+    FB_CUDA_CHECK(c->d_out.ensure(out_end + 512));
+    cudaStream_t st = c->stream;
+    if (in_end) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, in_end, cudaMemcpyHostToDevice, st));
+    int rc = fb200_decompress_members_device(c, container, c->d_in.p, in_off, in_len, k, c->d_out.p, out_off, out_cap,
+                                             out_len, consumed, status, st);
+    // deliver what was produced (also for failed members: the caller decides what to do with it)
+    for (size_t i = 0; i < k; i++)
+        if (out_len[i]) FB_CUDA_CHECK(cudaMemcpyAsync(out + out_off[i], c->d_out.p + out_off[i], out_len[i], cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return rc;
+}
+
+int fb200_decompress(fb200_ctx* c, int container, const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len,
+                     size_t* consumed) {
+    if (!c || (!in && n) || (!out && cap)) return FB200_INVALID_ARGUMENT;
+    uint64_t in_off = 0, in_len = n, out_off = 0, out_cap = cap, olen = 0, used = 0;
+    int status = 0;
+    uint8_t dummy_in = 0, dummy_out = 0;
+    int rc = fb200_decompress_members(c, container, in ? in : &dummy_in, &in_off, &in_len, 1, out ? out : &dummy_out, &out_off,
+                                      &out_cap, &olen, &used, &status);
+    if (out_len) *out_len = (size_t)olen;
+    if (consumed) *consumed = (size_t)used;
+    return rc;
+}
+
+// =============================================================================================
+// streaming compressor: Compressor / SimpleCompressor (deflate.zig:121-373, 449-529).
+// Input is accumulated; finish() runs the device pipeline over the whole stream and hands the
+// bytes to the writer.  Chunking of write() calls is not observable in the reference's output
+// (the slide schedule depends on stream position only), so this is byte-identical for
+// write*/finish.  flush() (sync marker) needs the segmented pipeline and is rejected until then.
+// =============================================================================================
+struct fb200_deflate {
+    fb200_ctx* ctx;
+    int container, mode;
+    fb200_write_fn writer;
+    void* user;
+    std::vector<uint8_t> pending;
+    bool header_written = false, finished = false;
+    int err = 0;
+};
+
+int fb200_deflate_create(fb200_ctx* ctx, int container, int mode, fb200_write_fn writer, void* user, fb200_deflate** out) {
+    LevelArgs lv;
+    if (!ctx || !out || !writer || container < 0 || container > 2) return FB200_INVALID_ARGUMENT;
+    if (mode != FB200_MODE_STORE && mode != FB200_MODE_HUFFMAN && !level_args(mode, lv)) return FB200_INVALID_ARGUMENT;
+    fb200_deflate* d = new (std::nothrow) fb200_deflate();
+    if (!d) return FB200_INVALID_ARGUMENT;
+    d->ctx = ctx;
+    d->container = container;
+    d->mode = mode;
+    d->writer = writer;
+    d->user = user;
+    // the reference writes the container header in init (deflate.zig:144, :470)
+    int rc = 0;
+    if (container == FB200_GZIP) rc = writer(user, kGzipHeader, 10);
+    else if (container == FB200_ZLIB) rc = writer(user, kZlibHeader, 2);
+    d->header_written = true;
+    if (rc) {
+        delete d;
+        return FB200_NO_SPACE_LEFT;
+    }
+    *out = d;
+    return FB200_OK;
+}
+int fb200_deflate_write(fb200_deflate* d, const uint8_t* data, size_t n) {
+    if (!d || (!data && n)) return FB200_INVALID_ARGUMENT;
+    if (d->err) return d->err;
+    if (d->finished) return d->err = FB200_INVALID_STATE;
+    d->pending.insert(d->pending.end(), data, data + n);
+    return FB200_OK;
+}
+int fb200_deflate_flush(fb200_deflate* d) {
+    if (!d) return FB200_INVALID_ARGUMENT;
+    return FB200_INVALID_STATE;  // TODO(segments): sync-flush marker, deflate.zig:335-337
+}
+int fb200_deflate_finish(fb200_deflate* d) {
+    if (!d) return FB200_INVALID_ARGUMENT;
+    if (d->err) return d->err;
+    if (d->finished) return d->err = FB200_INVALID_STATE;
+    const size_t n = d->pending.size();
+    std::vector<uint8_t> out(fb200_compress_bound(n, d->mode) + 64);
+    size_t out_len = 0;
+    int rc = fb200_compress(d->ctx, d->container, d->mode, d->pending.data(), n, out.data(), out.size(), &out_len);
+    if (rc) return d->err = rc;
+    const size_t hs = header_size(d->container);  // already written in create()
+    if (d->writer(d->user, out.data() + hs, out_len - hs)) return d->err = FB200_NO_SPACE_LEFT;
+    d->finished = true;
+    d->pending.clear();
+    return FB200_OK;
+}
+void fb200_deflate_set_writer(fb200_deflate* d, fb200_write_fn writer, void* user) {
+    if (!d) return;
+    d->writer = writer;
+    d->user = user;
+}
+void fb200_deflate_destroy(fb200_deflate* d) { delete d; }
+
+// =============================================================================================
+// streaming decompressor: Decompressor (inflate.zig:43-355).  One member per decompress()/next()
+// sequence; reset() continues with the next member of the same reader, keeping the history
+// (CircularBuffer.wp is not reset, so later members may reach into earlier output).
+// =============================================================================================
+struct fb200_inflate {
+    fb200_ctx* ctx;
+    int container;
+    fb200_read_fn reader;
+    void* user;
+    std::vector<uint8_t> in;     // everything read so far and not yet consumed
+    size_t in_pos = 0;           // start of the current member inside `in`
+    std::vector<uint8_t> hist;   // last <= 32768 bytes of earlier members' output
+    uint64_t total_out = 0;      // bytes produced by earlier members (CircularBuffer.wp)
+    std::vector<uint8_t> out;    // current member's plain bytes
+    size_t out_pos = 0;
+    enum { kHeader, kDecoded, kEnd } state = kHeader;
+    int err = 0;
+};
+
+int fb200_inflate_create(fb200_ctx* ctx, int container, fb200_read_fn reader, void* user, fb200_inflate** out) {
+    if (!ctx || !out || container < 0 || container > 2) return FB200_INVALID_ARGUMENT;
+    fb200_inflate* s = new (std::nothrow) fb200_inflate();
+    if (!s) return FB200_INVALID_ARGUMENT;
+    s->ctx = ctx;
+    s->container = container;
+    s->reader = reader;
+    s->user = user;
+    *out = s;
+    return FB200_OK;
+}
+static void inflate_slurp(fb200_inflate* s) {
+    if (!s->reader) return;
+    uint8_t buf[65536];
+    for (;;) {
+        const size_t got = s->reader(s->user, buf, sizeof buf);
+        if (got == 0) break;
+        s->in.insert(s->in.end(), buf, buf + got);
+    }
+}
+static int inflate_decode_member(fb200_inflate* s) {
+    inflate_slurp(s);
+    fb200_ctx* c = s->ctx;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    const size_t n = s->in.size() - s->in_pos;
+    const size_t hist = s->hist.size();
+    size_t cap = n * 8 + 65536;
+    for (;;) {
+        FB_CUDA_CHECK(c->d_in.ensure(n + 512));
+        FB_CUDA_CHECK(c->d_out.ensure(hist + cap + 512));
+        cudaStream_t st = c->stream;
+        if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, s->in.data() + s->in_pos, n, cudaMemcpyHostToDevice, st));
+        if (hist) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_out.p, s->hist.data(), hist, cudaMemcpyHostToDevice, st));
+        MemberDesc md{0, n, hist, cap, hist};
+        // the reference only checks `wp < distance` (CircularBuffer.zig:45): with more than 32 KiB of
+        // earlier output every distance is reachable
+        if (s->total_out > hist) md.hist = hist;
+        MemberResult res;
+        int rc = run_members(c, s->container, c->d_in.p, &md, 1, c->d_out.p, &res, st);
+        if (rc) return rc;
+        if (res.status == FB200_NO_SPACE_LEFT && cap < (n + 64) * 1100) {
+            cap *= 4;
+            continue;
+        }
+        if (res.status) return (int)res.status;
+        s->out.resize(res.out_len);
+        if (res.out_len) FB_CUDA_CHECK(cudaMemcpy(s->out.data(), c->d_out.p + hist, res.out_len, cudaMemcpyDeviceToHost));
+        s->out_pos = 0;
+        s->in_pos += res.consumed;
+        return FB200_OK;
+    }
+}
+int fb200_inflate_get(fb200_inflate* s, size_t limit, const uint8_t** data, size_t* len) {
+    if (!s || !data || !len) return FB200_INVALID_ARGUMENT;
+    *data = nullptr;
+    *len = 0;
+    if (s->err) return s->err;
+    if (s->state == fb200_inflate::kHeader) {
+        int rc = inflate_decode_member(s);
+        if (rc) return s->err = rc;
+        s->state = fb200_inflate::kDecoded;
+    }
+    if (s->state == fb200_inflate::kDecoded) {
+        size_t avail = s->out.size() - s->out_pos;
+        if (avail == 0) {
+            s->state = fb200_inflate::kEnd;
+            return FB200_OK;
+        }
+        // the reference hands out at most one 64 KiB ring's worth per call (inflate.zig:321-325)
+        size_t take = avail < 65536 ? avail : 65536;
+        if (limit && take > limit) take = limit;
+        *data = s->out.data() + s->out_pos;
+        *len = take;
+        s->out_pos += take;
+    }
+    return FB200_OK;
+}
+int fb200_inflate_next(fb200_inflate* s, const uint8_t** data, size_t* len) { return fb200_inflate_get(s, 0, data, len); }
+int fb200_inflate_read(fb200_inflate* s, uint8_t* buf, size_t cap, size_t* n) {
+    if (!n) return FB200_INVALID_ARGUMENT;
+    *n = 0;
+    if (cap == 0) return FB200_OK;
+    const uint8_t* p;
+    size_t len;
+    int rc = fb200_inflate_get(s, cap, &p, &len);
+    if (rc) return rc;
+    if (len) memcpy(buf, p, len);
+    *n = len;
+    return FB200_OK;
+}
+int fb200_inflate_reset(fb200_inflate* s) {
+    if (!s) return FB200_INVALID_ARGUMENT;
+    // inflate.zig:301-309: only legal once the current member has been fully delivered
+    if (s->err || !(s->state == fb200_inflate::kEnd ||
+                    (s->state == fb200_inflate::kDecoded && s->out_pos == s->out.size())))
+        return FB200_INVALID_STATE;
+    // keep the last 32 KiB as history for the next member
+    s->total_out += s->out.size();
+    s->hist.insert(s->hist.end(), s->out.begin(), s->out.end());
+    if (s->hist.size() > kMaxDist) s->hist.erase(s->hist.begin(), s->hist.end() - kMaxDist);
+    s->out.clear();
+    s->out_pos = 0;
+    s->in.erase(s->in.begin(), s->in.begin() + s->in_pos);
+    s->in_pos = 0;
+    s->state = fb200_inflate::kHeader;
+    return FB200_OK;
+}
+void fb200_inflate_set_reader(fb200_inflate* s, fb200_read_fn reader, void* user) {
+    if (!s) return;
+    s->reader = reader;
+    s->user = user;
+    if (s->state == fb200_inflate::kEnd) s->state = fb200_inflate::kHeader;  // inflate.zig:283-288
+}
+void fb200_inflate_destroy(fb200_inflate* s) { delete s; }
+
+}  // extern "C"

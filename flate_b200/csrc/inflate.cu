@@ -1,0 +1,616 @@
+// inflate.cu -- inflate on sm_100a.  One warp per member (independent gzip/zlib/raw stream).
+//
+// Lane 0 owns the bit cursor and walks the symbol stream; Huffman tables are rebuilt per deflate
+// block by the whole warp into shared memory (10-bit direct table + canonical fallback), and
+// back-references are resolved by the whole warp against the flat output buffer in HBM (the
+// reference's 64 KiB CircularBuffer, CircularBuffer.zig:44-75, becomes a flat buffer with the
+// same InvalidMatch rule).  Error classes and their order follow inflate.zig / huffman_decoder.zig /
+// bit_reader.zig exactly; the bit cursor reproduces bit_reader.zig's
+// "fill fails only when no bit is left, shift fails when fewer than n bits are left" rules on a
+// flat input with zero-padded peeks.
+#include "../../include/flate_b200.h"
+#include "inflate.cuh"
+
+namespace fb {
+
+__constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59,
+                                        67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769,
+                                         1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+
+constexpr uint32_t kLitFast = 10, kDistFast = 8;
+constexpr uint32_t kInflateWarps = 4;
+
+struct WarpTables {
+    uint16_t lit_fast[1 << kLitFast];    // len | sym << 4 ; 0 = use the canonical fallback
+    uint16_t dist_fast[1 << kDistFast];
+    uint16_t lit_count[16], dist_count[16];
+    uint16_t lit_sym[kNumLit + 2], dist_sym[kNumDist + 2];
+    uint8_t lit_lens[kNumLit + 2], dist_lens[kNumDist + 2];
+    uint32_t crc_tab[256];
+};
+
+struct BitCursor {  // lane 0 only
+    const uint8_t* next;
+    const uint8_t* end;
+    uint64_t buf;
+    uint32_t cnt;
+    __device__ __forceinline__ void refill() {
+        while (cnt <= 32 && next < end) {
+            if ((((uintptr_t)next) & 3) == 0 && next + 4 <= end) {
+                buf |= (uint64_t)(*reinterpret_cast<const uint32_t*>(next)) << cnt;
+                next += 4;
+                cnt += 32;
+            } else {
+                buf |= (uint64_t)(*next) << cnt;
+                next += 1;
+                cnt += 8;
+            }
+        }
+    }
+    __device__ __forceinline__ bool empty() { refill(); return cnt == 0; }             // fill(): EndOfStream
+    __device__ __forceinline__ uint32_t peek(uint32_t nb) { return (uint32_t)buf & ((1u << nb) - 1); }
+    __device__ __forceinline__ bool shift(uint32_t nb) {                                 // false => EndOfStream
+        if (nb > cnt) { refill(); if (nb > cnt) return false; }
+        buf >>= nb;
+        cnt -= nb;
+        return true;
+    }
+    // read(U): fill + shift
+    __device__ __forceinline__ int read(uint32_t nb, uint32_t& v) {
+        refill();
+        if (cnt == 0) return FB200_END_OF_STREAM;
+        v = nb >= 32 ? (uint32_t)buf : ((uint32_t)buf & ((1u << nb) - 1));
+        if (nb > cnt) return FB200_END_OF_STREAM;
+        buf >>= nb;
+        cnt -= nb;
+        return FB200_OK;
+    }
+    __device__ __forceinline__ void align_to_byte() {
+        const uint32_t r = cnt & 7;  // whole bytes are buffered, so cnt mod 8 is the stream's bit phase
+        buf >>= r;
+        cnt -= r;
+    }
+    __device__ __forceinline__ const uint8_t* byte_pos() const { return next - (cnt >> 3); }  // when aligned
+};
+
+// canonical decode on a zero-padded LSB-first peek (huffman_decoder.zig:156-175 find semantics)
+__device__ __forceinline__ int slow_find(const uint16_t* count, const uint16_t* symbol, uint32_t max_bits, uint32_t peek,
+                                         uint32_t& sym, uint32_t& nbits) {
+    int code = 0, first = 0, index = 0;
+    for (uint32_t len = 1; len <= max_bits; len++) {
+        code |= (int)(peek & 1);
+        peek >>= 1;
+        const int cnt = count[len];
+        if (code - cnt < first) {
+            sym = symbol[index + (code - first)];
+            nbits = len;
+            return FB200_OK;
+        }
+        index += cnt;
+        first += cnt;
+        first <<= 1;
+        code <<= 1;
+    }
+    return FB200_INVALID_CODE;
+}
+
+// huffman_decoder.zig:126-153 checkCompletnes + canonical tables.  Whole warp; returns status (uniform).
+__device__ int build_decoder(const uint8_t* lens, uint32_t n, bool is_lit, uint32_t max_code_bits, uint16_t* count,
+                             uint16_t* symbol, uint16_t* fast, uint32_t fast_bits) {
+    const uint32_t lane = threadIdx.x & 31;
+    int status = FB200_OK;
+    __shared__ uint16_t offs_all[kInflateWarps][17];
+    uint16_t* offs = offs_all[(threadIdx.x >> 5) % kInflateWarps];
+    if (lane == 0) {
+        if (is_lit && lens[256] == 0) status = FB200_MISSING_END_OF_BLOCK_CODE;  // :127-128
+        if (status == FB200_OK) {
+            for (uint32_t i = 0; i < 16; i++) count[i] = 0;
+            uint32_t mx = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                const uint32_t l = lens[i];
+                if (l == 0) continue;
+                if (l > mx) mx = l;
+                count[l]++;
+            }
+            if (mx != 0) {
+                int left = 1;
+                for (uint32_t len = 1; len <= max_code_bits; len++) {
+                    left <<= 1;
+                    if ((int)count[len] > left) { status = FB200_OVERSUBSCRIBED_HUFFMAN_TREE; break; }
+                    left -= count[len];
+                }
+                if (status == FB200_OK && left > 0) {
+                    if (!(max_code_bits > 7 && mx == count[1])) status = FB200_INCOMPLETE_HUFFMAN_TREE;  // :148-151
+                }
+            }
+            if (status == FB200_OK) {
+                offs[1] = 0;
+                for (uint32_t len = 1; len < 16; len++) offs[len + 1] = offs[len] + count[len];
+                for (uint32_t i = 0; i < n; i++)
+                    if (lens[i]) symbol[offs[lens[i]]++] = (uint16_t)i;
+            }
+        }
+    }
+    __syncwarp();
+    status = __shfl_sync(0xffffffffu, status, 0);
+    if (status != FB200_OK) return status;
+    if (fast == nullptr) return status;
+    for (uint32_t i = lane; i < (1u << fast_bits); i += 32) fast[i] = 0;
+    __syncwarp();
+    // first canonical code of each length
+    uint32_t code = 0, index = 0;
+    for (uint32_t len = 1; len <= fast_bits && len <= max_code_bits; len++) {
+        const uint32_t cnt = count[len];
+        // symbols symbol[index .. index+cnt) have codes code .. code+cnt-1 (MSB-first)
+        for (uint32_t k = lane; k < cnt; k += 32) {
+            const uint32_t rev = __brev(code + k) >> (32 - len);
+            const uint16_t entry = (uint16_t)(len | (symbol[index + k] << 4));
+            for (uint32_t e = rev; e < (1u << fast_bits); e += (1u << len)) fast[e] = entry;
+        }
+        code = (code + cnt) << 1;
+        index += cnt;
+    }
+    __syncwarp();
+    return status;
+}
+
+__device__ void build_fixed_lens(uint8_t* lit_lens, uint8_t* dist_lens) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = lane; i < 288; i += 32) lit_lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+    for (uint32_t i = lane; i < 30; i += 32) dist_lens[i] = 5;
+    __syncwarp();
+}
+
+// ---- checksums over the member's output, warp-parallel ----
+__device__ __forceinline__ uint32_t multmodp(uint32_t a, uint32_t b) {  // GF(2)[x] mod the reflected CRC-32 polynomial
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) {
+            p ^= b;
+            if ((a & (m - 1)) == 0) break;
+        }
+        m >>= 1;
+        b = (b & 1) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+__device__ uint32_t x8nmodp(uint64_t nbytes) {  // x^(8 n) mod p
+    uint32_t sq = 1u << 30;                     // x^1
+    sq = multmodp(sq, sq);                      // x^2
+    sq = multmodp(sq, sq);                      // x^4
+    sq = multmodp(sq, sq);                      // x^8
+    uint32_t p = 1u << 31;                      // x^0
+    while (nbytes) {
+        if (nbytes & 1) p = multmodp(sq, p);
+        sq = multmodp(sq, sq);
+        nbytes >>= 1;
+    }
+    return p;
+}
+__device__ uint32_t crc32_chunk(const uint32_t* tab, const uint8_t* p, uint64_t n) {
+    uint32_t c = 0xffffffffu;
+    for (uint64_t i = 0; i < n; i++) c = tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
+    return ~c;
+}
+__device__ uint32_t warp_crc32(const uint32_t* tab, const uint8_t* p, uint64_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t per = (n + 31) / 32;
+    const uint64_t b = min(per * lane, n), e = min(b + per, n);
+    uint32_t term = 0;
+    if (e > b) term = multmodp(x8nmodp(n - e), crc32_chunk(tab, p + b, e - b));
+    for (int o = 16; o > 0; o >>= 1) term ^= __shfl_xor_sync(0xffffffffu, term, o);
+    return term;
+}
+__device__ uint32_t warp_adler32(const uint8_t* p, uint64_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t per = (n + 31) / 32;
+    const uint64_t b = min(per * lane, n), e = min(b + per, n);
+    uint64_t a = 0, s = 0, i;  // a = sum of bytes, s = sum of (e - i) * byte_i (weights relative to the lane's end)
+    for (i = b; i < e; i++) {
+        a += p[i];
+        s += a;
+        if ((i & 2047) == 2047) { a %= 65521; s %= 65521; }
+    }
+    a %= 65521;
+    s %= 65521;
+    // Adler over the whole: A = 1 + sum a_l ; B = n + sum_l (s_l + a_l * (n - e_l))
+    uint64_t A = a, B = (s + a * ((n - e) % 65521)) % 65521;
+    for (int o = 16; o > 0; o >>= 1) {
+        A += __shfl_xor_sync(0xffffffffu, A, o);
+        B += __shfl_xor_sync(0xffffffffu, B, o);
+    }
+    A = (A + 1) % 65521;
+    B = (B + n % 65521) % 65521;
+    return (uint32_t)((B << 16) | A);
+}
+
+#define BCAST(x) __shfl_sync(0xffffffffu, (x), 0)
+
+__global__ void __launch_bounds__(kInflateWarps * 32)
+inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const MemberDesc* __restrict__ descs, uint32_t k,
+                       uint8_t* d_out, MemberResult* __restrict__ results) {
+    __shared__ WarpTables tabs_all[kInflateWarps];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t m = blockIdx.x * kInflateWarps + (threadIdx.x >> 5);
+    if (m >= k) return;
+    WarpTables& T = tabs_all[threadIdx.x >> 5];
+    const MemberDesc md = descs[m];
+    uint8_t* out = d_out + md.out_off;
+    const uint64_t cap = md.out_cap;
+    uint64_t pos = 0;  // bytes produced (uniform across the warp)
+    int status = FB200_OK;
+
+    BitCursor bc;
+    bc.next = d_in + md.in_off;
+    bc.end = bc.next + md.in_len;
+    bc.buf = 0;
+    bc.cnt = 0;
+
+    // ---- container header (container.zig:111-152), lane 0 ----
+    if (lane == 0 && container != FB200_RAW) {
+        uint32_t v;
+        if (container == FB200_GZIP) {
+            uint32_t magic1 = 0, magic2 = 0, method = 0, flags = 0;
+            if (!status) status = bc.read(8, magic1);
+            if (!status) status = bc.read(8, magic2);
+            if (!status) status = bc.read(8, method);
+            if (!status) status = bc.read(8, flags);
+            for (int i = 0; i < 6 && !status; i++) status = bc.read(8, v);
+            if (!status && (magic1 != 0x1f || magic2 != 0x8b || method != 0x08)) status = FB200_BAD_GZIP_HEADER;
+            if (!status && (flags & 0x04)) {
+                uint32_t xlen = 0;
+                status = bc.read(16, xlen);
+                for (uint32_t i = 0; i < xlen && !status; i++) status = bc.read(8, v);
+            }
+            if (!status && (flags & 0x08)) do { status = bc.read(8, v); } while (!status && v != 0);
+            if (!status && (flags & 0x10)) do { status = bc.read(8, v); } while (!status && v != 0);
+            if (!status && (flags & 0x02)) {
+                status = bc.read(8, v);
+                if (!status) status = bc.read(8, v);
+            }
+        } else {
+            uint32_t cm = 0, cinfo = 0;
+            status = bc.read(4, cm);
+            if (!status) status = bc.read(4, cinfo);
+            if (!status) status = bc.read(8, v);
+            if (!status && (cm != 8 || cinfo > 7)) status = FB200_BAD_ZLIB_HEADER;
+        }
+    }
+    status = BCAST(status);
+
+    bool fixed_ready = false;
+    while (status == FB200_OK) {  // inflate.zig:251-280 step: one deflate block per iteration
+        uint32_t bfinal = 0, btype = 0;
+        if (lane == 0) {
+            status = bc.read(1, bfinal);
+            if (!status) status = bc.read(2, btype);
+        }
+        status = BCAST(status);
+        if (status) break;
+        bfinal = BCAST(bfinal);
+        btype = BCAST(btype);
+
+        if (btype == 0) {  // stored block, inflate.zig:89-102
+            uint32_t len = 0;
+            const uint8_t* src = nullptr;
+            if (lane == 0) {
+                bc.align_to_byte();
+                uint32_t nlen = 0;
+                status = bc.read(16, len);
+                if (!status) status = bc.read(16, nlen);
+                if (!status && len != ((~nlen) & 0xffffu)) status = FB200_WRONG_STORED_BLOCK_NLEN;
+                if (!status) {
+                    src = bc.byte_pos();
+                    if ((uint64_t)(bc.end - src) < len) status = FB200_END_OF_STREAM;
+                    else if (pos + len > cap) status = FB200_NO_SPACE_LEFT;
+                }
+            }
+            status = BCAST(status);
+            if (status) break;
+            len = BCAST(len);
+            src = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)src, 0);
+            for (uint32_t i = lane; i < len; i += 32) out[pos + i] = src[i];
+            pos += len;
+            if (lane == 0) {  // reposition the cursor after the raw bytes
+                bc.next = src + len;
+                bc.buf = 0;
+                bc.cnt = 0;
+            }
+            __syncwarp();
+        } else if (btype == 1 || btype == 2) {
+            if (btype == 2) {  // dynamicBlockHeader, inflate.zig:144-185
+                fixed_ready = false;
+                uint32_t hlit = 0, hdist = 0;
+                if (lane == 0) {
+                    uint32_t v = 0, hclen = 0;
+                    status = bc.read(5, v); hlit = v + 257;
+                    if (!status) { status = bc.read(5, v); hdist = v + 1; }
+                    if (!status) { status = bc.read(4, v); hclen = v + 4; }
+                    if (!status && (hlit > 286 || hdist > 30)) status = FB200_INVALID_DYNAMIC_BLOCK_HEADER;
+                    // code-length code lengths live in lit_lens[0..19) temporarily (dist_lens as scratch)
+                    if (!status) {
+                        for (uint32_t i = 0; i < 19; i++) T.dist_lens[i] = 0;
+                        for (uint32_t i = 0; i < hclen && !status; i++) {
+                            status = bc.read(3, v);
+                            T.dist_lens[c_cl_order[i]] = (uint8_t)v;
+                        }
+                    }
+                }
+                status = BCAST(status);
+                if (status) break;
+                // CodegenDecoder(19, 7, 7): built into dist_count / dist_sym (no fast table)
+                status = build_decoder(T.dist_lens, 19, false, 7, T.dist_count, T.dist_sym, nullptr, 0);
+                if (status) break;
+                if (lane == 0) {
+                    // two passes: literal lengths then distance lengths (inflate.zig:161-180)
+                    for (uint32_t i = 0; i < kNumLit; i++) T.lit_lens[i] = 0;
+                    uint8_t dl[kNumDist];
+                    for (uint32_t i = 0; i < kNumDist; i++) dl[i] = 0;
+                    for (int pass = 0; pass < 2 && !status; pass++) {
+                        uint8_t* lens = pass == 0 ? T.lit_lens : dl;
+                        const uint32_t lens_len = pass == 0 ? kNumLit : kNumDist;
+                        const uint32_t want = pass == 0 ? hlit : hdist;
+                        uint32_t p = 0;
+                        while (p < want && !status) {
+                            if (bc.empty()) { status = FB200_END_OF_STREAM; break; }  // peekF(u7): fill(7)
+                            uint32_t sym = 0, nb = 0;
+                            status = slow_find(T.dist_count, T.dist_sym, 7, bc.peek(7), sym, nb);
+                            if (status) break;
+                            if (!bc.shift(nb)) { status = FB200_END_OF_STREAM; break; }
+                            // dynamicCodeLength, inflate.zig:189-216
+                            if (p >= lens_len) { status = FB200_INVALID_DYNAMIC_BLOCK_HEADER; break; }
+                            uint32_t v = 0;
+                            if (sym <= 15) {
+                                lens[p] = (uint8_t)sym;
+                                p += 1;
+                            } else if (sym == 16) {
+                                status = bc.read(2, v);
+                                if (status) break;
+                                const uint32_t rep = v + 3;
+                                if (p == 0 || p + rep > lens_len) { status = FB200_INVALID_DYNAMIC_BLOCK_HEADER; break; }
+                                for (uint32_t i = 0; i < rep; i++) lens[p + i] = lens[p + i - 1];
+                                p += rep;
+                            } else if (sym == 17) {
+                                status = bc.read(3, v);
+                                if (status) break;
+                                p += v + 3;
+                            } else {
+                                status = bc.read(7, v);
+                                if (status) break;
+                                p += v + 11;
+                            }
+                        }
+                        if (!status && p > want) status = FB200_INVALID_DYNAMIC_BLOCK_HEADER;
+                    }
+                    for (uint32_t i = 0; i < kNumDist; i++) T.dist_lens[i] = dl[i];
+                }
+                status = BCAST(status);
+                if (status) break;
+                __syncwarp();
+                status = build_decoder(T.lit_lens, kNumLit, true, 15, T.lit_count, T.lit_sym, T.lit_fast, kLitFast);
+                if (status) break;
+                status = build_decoder(T.dist_lens, kNumDist, false, 15, T.dist_count, T.dist_sym, T.dist_fast, kDistFast);
+                if (status) break;
+            } else if (!fixed_ready) {
+                // fixed block: the reference decodes by arithmetic (bit_reader.zig:205-217); the same
+                // symbols come out of the canonical code with lengths 8/9/7/8 and 5-bit distances.
+                build_fixed_lens(T.lit_lens, T.dist_lens);
+                // symbols 286/287 exist in the fixed code (-> InvalidCode, inflate.zig:111); use a 288 alphabet
+                status = build_decoder(T.lit_lens, 288, true, 15, T.lit_count, T.lit_sym, T.lit_fast, kLitFast);
+                if (!status) status = build_decoder(T.dist_lens, 30, false, 15, T.dist_count, T.dist_sym, T.dist_fast, kDistFast);
+                if (status) break;
+                // 5-bit distance codes 30/31 are InvalidCode (inflate.zig:136): a 30-symbol 5-bit code is
+                // incomplete, the fallback reports InvalidCode for them.
+                fixed_ready = true;
+            }
+            // ---- symbol loop (inflate.zig:220-239 dynamicBlock / :104-124 fixedBlock) ----
+            bool done = false;
+            while (!done) {
+                uint32_t ev_len = 0, ev_dist = 0;  // match event (len > 0), or end of block / error
+                if (lane == 0) {
+                    for (;;) {
+                        if (bc.empty()) { status = FB200_END_OF_STREAM; break; }  // fill(15) / fill(7+2)
+                        uint32_t sym, nb;
+                        const uint32_t e = T.lit_fast[bc.peek(kLitFast)];
+                        if (e & 15) {
+                            sym = e >> 4;
+                            nb = e & 15;
+                        } else {
+                            status = slow_find(T.lit_count, T.lit_sym, 15, bc.peek(15), sym, nb);
+                            if (status) break;
+                        }
+                        if (!bc.shift(nb)) { status = FB200_END_OF_STREAM; break; }
+                        if (sym < 256) {
+                            if (pos >= cap) { status = FB200_NO_SPACE_LEFT; break; }
+                            out[pos++] = (uint8_t)sym;
+                            continue;
+                        }
+                        if (sym == 256) { done = true; break; }
+                        // match: fill(5+15+13), decodeLength, distance symbol, decodeDistance.  Symbols 286/287
+                        // only exist in the fixed code, where the reference rejects them before any fill
+                        // (inflate.zig:111); in a dynamic block they cannot occur.
+                        const uint32_t lcode = sym - 257;
+                        if (lcode > 28) { status = FB200_INVALID_CODE; break; }
+                        if (bc.empty()) { status = FB200_END_OF_STREAM; break; }
+                        uint32_t length = c_len_base[lcode];
+                        const uint32_t leb = length_extra_bits(lcode);
+                        if (leb) {
+                            const uint32_t x = bc.peek(leb);
+                            if (!bc.shift(leb)) { status = FB200_END_OF_STREAM; break; }
+                            length += x;
+                        }
+                        uint32_t dsym, dnb;
+                        // fixed block: readF(u5, buffered) shifts 5 bits before the code is looked at
+                        // (inflate.zig:121, bit_reader.zig:113-117), so a short stream is EndOfStream first
+                        if (btype == 1) { bc.refill(); if (bc.cnt < 5) { status = FB200_END_OF_STREAM; break; } }
+                        const uint32_t de = T.dist_fast[bc.peek(kDistFast)];
+                        if (de & 15) {
+                            dsym = de >> 4;
+                            dnb = de & 15;
+                        } else {
+                            status = slow_find(T.dist_count, T.dist_sym, 15, bc.peek(15), dsym, dnb);
+                            if (status) break;
+                        }
+                        if (!bc.shift(dnb)) { status = FB200_END_OF_STREAM; break; }
+                        if (dsym > 29) { status = FB200_INVALID_CODE; break; }
+                        uint32_t distance = c_dist_base[dsym];
+                        const uint32_t deb = distance_extra_bits(dsym);
+                        if (deb) {
+                            const uint32_t x = bc.peek(deb);
+                            if (!bc.shift(deb)) { status = FB200_END_OF_STREAM; break; }
+                            distance += x;
+                        }
+                        // CircularBuffer.zig:45-50 writeMatch validation
+                        if (md.hist + pos < distance) { status = FB200_INVALID_MATCH; break; }
+                        if (pos + length > cap) { status = FB200_NO_SPACE_LEFT; break; }
+                        ev_len = length;
+                        ev_dist = distance;
+                        break;
+                    }
+                }
+                status = BCAST(status);
+                if (status) break;
+                done = BCAST(done);
+                pos = __shfl_sync(0xffffffffu, (unsigned long long)pos, 0);
+                ev_len = BCAST(ev_len);
+                if (ev_len) {
+                    ev_dist = BCAST(ev_dist);
+                    __syncwarp();
+                    const uint8_t* from = out + pos - ev_dist;
+                    if (ev_dist >= ev_len) {
+                        for (uint32_t i = lane; i < ev_len; i += 32) out[pos + i] = from[i];
+                    } else {
+                        for (uint32_t i = lane; i < ev_len; i += 32) out[pos + i] = from[i % ev_dist];
+                    }
+                    pos += ev_len;
+                    __syncwarp();
+                }
+            }
+            if (status) break;
+        } else {
+            status = FB200_INVALID_BLOCK_TYPE;  // inflate.zig:267
+            break;
+        }
+        if (bfinal) break;
+    }
+    pos = __shfl_sync(0xffffffffu, (unsigned long long)pos, 0);
+
+    // ---- protocol footer (inflate.zig:271-275, container.zig:154-166) ----
+    if (status == FB200_OK && container != FB200_RAW) {
+        __syncwarp();
+        uint32_t sum;
+        if (container == FB200_GZIP) {
+            for (uint32_t i = lane; i < 256; i += 32) {
+                uint32_t c = i;
+                for (int b = 0; b < 8; b++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+                T.crc_tab[i] = c;
+            }
+            __syncwarp();
+            sum = warp_crc32(T.crc_tab, out, pos);
+        } else {
+            sum = warp_adler32(out, pos);
+        }
+        if (lane == 0) {
+            bc.align_to_byte();
+            uint32_t v = 0;
+            status = bc.read(32, v);
+            if (container == FB200_GZIP) {
+                if (!status && v != sum) status = FB200_WRONG_GZIP_CHECKSUM;
+                if (!status) status = bc.read(32, v);
+                if (!status && v != (uint32_t)pos) status = FB200_WRONG_GZIP_SIZE;
+            } else {
+                const uint32_t be = __byte_perm(sum, 0, 0x0123);
+                if (!status && v != be) status = FB200_WRONG_ZLIB_CHECKSUM;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (status == FB200_OK) bc.align_to_byte();
+        MemberResult r;
+        r.out_len = pos;
+        // bytes consumed: everything handed to the cursor minus whole bytes still buffered
+        r.consumed = (uint64_t)((bc.next - (bc.cnt >> 3)) - (d_in + md.in_off));
+        r.status = (uint32_t)status;
+        r.pad = 0;
+        results[m] = r;
+    }
+}
+
+// ---- standalone checksum kernels (used for the gzip/zlib footers of compress) ----
+constexpr uint32_t kSumChunk = 4096;
+__global__ void __launch_bounds__(256)
+crc32_chunks_kernel(const uint8_t* __restrict__ data, uint64_t n, uint32_t* __restrict__ result) {
+    __shared__ uint32_t tab[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t c = i;
+        for (int b = 0; b < 8; b++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        tab[i] = c;
+    }
+    __syncthreads();
+    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t b = chunk * kSumChunk;
+    uint32_t term = 0;
+    if (b < n) {
+        const uint64_t e = min(b + kSumChunk, n);
+        term = multmodp(x8nmodp(n - e), crc32_chunk(tab, data + b, e - b));
+    }
+    for (int o = 16; o > 0; o >>= 1) term ^= __shfl_xor_sync(0xffffffffu, term, o);
+    if ((threadIdx.x & 31) == 0 && term) atomicXor(result, term);
+}
+__global__ void __launch_bounds__(256)
+adler32_chunks_kernel(const uint8_t* __restrict__ data, uint64_t n, unsigned long long* __restrict__ acc) {
+    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t b = chunk * kSumChunk;
+    unsigned long long A = 0, B = 0;
+    if (b < n) {
+        const uint64_t e = min(b + kSumChunk, n);
+        uint64_t a = 0, s = 0;
+        for (uint64_t i = b; i < e; i++) {
+            a += data[i];
+            s += a;
+        }
+        a %= 65521;
+        s %= 65521;
+        A = a;
+        B = (s + a * ((n - e) % 65521)) % 65521;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        A += __shfl_xor_sync(0xffffffffu, A, o);
+        B += __shfl_xor_sync(0xffffffffu, B, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc, A);
+        atomicAdd(acc + 1, B);
+    }
+}
+__global__ void adler32_finish_kernel(const unsigned long long* __restrict__ acc, uint64_t n, uint32_t* __restrict__ result) {
+    const uint64_t A = (acc[0] + 1) % 65521;
+    const uint64_t B = (acc[1] + n % 65521) % 65521;
+    *result = (uint32_t)((B << 16) | A);
+}
+
+cudaError_t inflate_members(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
+                            MemberResult* d_res, cudaStream_t st) {
+    if (k == 0) return cudaSuccess;
+    inflate_members_kernel<<<(k + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, 0, st>>>(container, d_in, d_desc, k,
+                                                                                                 d_out, d_res);
+    return cudaGetLastError();
+}
+cudaError_t crc32_device(const uint8_t* d_data, uint64_t n, uint32_t* d_result, cudaStream_t st) {
+    cudaMemsetAsync(d_result, 0, 4, st);
+    const uint64_t chunks = (n + kSumChunk - 1) / kSumChunk;
+    if (chunks) crc32_chunks_kernel<<<(uint32_t)((chunks + 255) / 256), 256, 0, st>>>(d_data, n, d_result);
+    return cudaGetLastError();
+}
+cudaError_t adler32_device(const uint8_t* d_data, uint64_t n, uint32_t* d_result, uint64_t* d_scratch2, cudaStream_t st) {
+    cudaMemsetAsync(d_scratch2, 0, 16, st);
+    const uint64_t chunks = (n + kSumChunk - 1) / kSumChunk;
+    if (chunks)
+        adler32_chunks_kernel<<<(uint32_t)((chunks + 255) / 256), 256, 0, st>>>(d_data, n, (unsigned long long*)d_scratch2);
+    adler32_finish_kernel<<<1, 1, 0, st>>>((const unsigned long long*)d_scratch2, n, d_result);
+    return cudaGetLastError();
+}
+
+}  // namespace fb

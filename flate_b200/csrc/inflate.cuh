@@ -1,0 +1,26 @@
+// inflate.cuh -- inflate side of the path (inflate.zig, huffman_decoder.zig, bit_reader.zig,
+// CircularBuffer.zig) and container checksums (container.zig:168-206) on the device.
+#pragma once
+#include "common.cuh"
+
+namespace fb {
+
+struct MemberDesc {
+    uint64_t in_off, in_len;    // compressed member inside d_in
+    uint64_t out_off, out_cap;  // where its plain bytes go inside d_out
+    uint64_t hist;              // bytes of earlier output directly before out_off the member may reference
+};
+struct MemberResult {
+    uint64_t out_len, consumed;
+    uint32_t status, pad;
+};
+constexpr uint32_t kNeedsHistory = 100;  // internal: match reaches before the member; redo after predecessors
+
+cudaError_t inflate_members(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
+                            MemberResult* d_res, cudaStream_t st);
+
+// CRC-32 (IEEE, reflected) / Adler-32 of d_data[0..n) into *d_result (device u32)
+cudaError_t crc32_device(const uint8_t* d_data, uint64_t n, uint32_t* d_result, cudaStream_t st);
+cudaError_t adler32_device(const uint8_t* d_data, uint64_t n, uint32_t* d_result, uint64_t* d_scratch2, cudaStream_t st);
+
+}  // namespace fb

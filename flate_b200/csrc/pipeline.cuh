@@ -1,0 +1,59 @@
+// pipeline.cuh -- device workspace layout and kernel launchers shared by the C-ABI layer.
+#pragma once
+#include "common.cuh"
+
+namespace fb {
+
+constexpr uint32_t kChunk = 4096;    // positions per lazy-parse chunk
+constexpr uint32_t kEntries = 516;   // possible entry offsets into a chunk (step <= 515)
+constexpr uint32_t kGroup = 256;     // chunks per resolution group
+
+// Workspace of the LZ77 phases for an input of n positions (all device pointers).
+struct Lz77Buffers {
+    uint16_t* link;          // n        distance to previous same-hash position, 0 = none
+    uint32_t* r_full;        // n        findMatch result, full budget
+    uint32_t* r_quarter;     // n        findMatch result, chain >> 2 budget
+    uint32_t* nx;            // n        packed lazy step from a clean arrival
+    uint16_t* exits;         // nchunks * kEntries
+    uint16_t* gexits;        // ngroups * kEntries
+    uint16_t* gentry;        // ngroups
+    uint16_t* entry;         // nchunks
+    uint32_t* bitmap;        // nchunks * kChunk/32   arrivals actually visited
+    uint32_t* chunk_tokens;  // nchunks
+    uint32_t* tok_offset;    // nchunks
+    uint32_t* total_tokens;  // 1
+    uint32_t* tokens;        // up to n
+    uint32_t* cut_rp;        // nblocks: reference `rp` when block b's last token was added
+};
+
+cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st);
+
+// ---- block writer ----
+enum WriteKind : uint32_t { kWrite = 0, kDynamicBlock = 1, kHuffmanBlock = 2 };  // block_writer.zig:307,395,524
+
+struct BlockPlan {           // per-block inputs of the build kernel (device array)
+    uint32_t tok_begin, tok_count;
+    uint64_t in_begin;       // candidate stored-input range / huffman slice
+    uint32_t in_len;
+    uint32_t has_input;      // `input != null` (SlidingWindow.zig:119-123)
+    uint32_t eof;
+    uint32_t kind;           // WriteKind; 3 = stored block verbatim (store mode / sync marker)
+};
+
+// plans for the level modes are derived on the device from the token count and cut_rp
+cudaError_t plan_level_blocks(const uint32_t* total_tokens, const uint32_t* cut_rp, uint32_t n, uint32_t max_blocks,
+                              uint32_t final_flush /*0 none(sync flush) 1 final*/, BlockPlan* plans, uint32_t* nblocks,
+                              cudaStream_t st);
+cudaError_t histogram_tokens(const uint32_t* tokens, const BlockPlan* plans, const uint32_t* nblocks_dev,
+                             uint32_t max_blocks, uint32_t* lit_freq, uint32_t* dist_freq, cudaStream_t st);
+cudaError_t histogram_bytes(const uint8_t* in, const BlockPlan* plans, uint32_t nblocks, uint32_t* lit_freq,
+                            cudaStream_t st);
+cudaError_t build_blocks(const BlockPlan* plans, const uint32_t* nblocks_dev, uint32_t max_blocks,
+                         const uint32_t* lit_freq, const uint32_t* dist_freq, BlockDesc* descs, cudaStream_t st);
+// sequential offset scan; start_bits = container header bits. Writes total bits to *total_bits.
+cudaError_t scan_block_offsets(BlockDesc* descs, const uint32_t* nblocks_dev, uint64_t start_bits, uint64_t* total_bits,
+                               cudaStream_t st);
+cudaError_t pack_blocks(const uint8_t* in, const uint32_t* tokens, const BlockDesc* descs, const uint32_t* nblocks_dev,
+                        uint32_t max_blocks, uint32_t* out_words, cudaStream_t st);
+
+}  // namespace fb

@@ -1,0 +1,140 @@
+/*
+ * flate_b200.h -- C ABI of the B200-native DEFLATE engine (libflate_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of ianic/flate: LZ77 match search + Huffman
+ * encode/decode behind the gzip/zlib/raw compress()/decompress()/Compressor/Decompressor surface.
+ * Plain pointers and sizes only; every call returns a status code that maps 1:1 to the Zig error
+ * names of the reference (see fb200_strerror).  INTEGRATION.md shows the Zig `extern` block and
+ * the shim that re-creates src/{flate,gzip,zlib}.zig on top of these entry points.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   fb200_compress / fb200_compress_device   <- deflate.zig:56-60  compress(container, reader, writer, options)
+ *                                               deflate.zig:402-406 huffman.compress, :421-425 store.compress
+ *   fb200_deflate_*                          <- deflate.zig:63-74,138,304,335,344,351,363 Compressor.{init,compress,
+ *                                               write,flush,finish,setWriter}; :449-529 SimpleCompressor
+ *   fb200_decompress / _device / _members    <- inflate.zig:14-17 decompress(container, reader, writer)
+ *   fb200_inflate_*                          <- inflate.zig:20-22,80,283-353 Decompressor.{init,decompress,next,
+ *                                               get,read,reset,setReader}
+ *   fb200_debug_tokens                       <- the BlockWriterType seam used by the reference's tests
+ *                                               (deflate.zig:118-121, TestTokenWriter :578-608)
+ *   fb200_debug_block_write                  <- block_writer.zig:307 write, :395 dynamicBlock, :524 huffmanBlock
+ *   fb200_debug_match_tables                 <- deflate.zig:233-266 findMatch (per position, both budgets)
+ */
+#ifndef FLATE_B200_H
+#define FLATE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes; 1..16 are the reference's error set (inflate.zig:72-78, huffman_decoder.zig:35-40,
+ * container.zig:45-51, bit_writer.zig:35, inflate.zig:302-304) */
+enum {
+    FB200_OK = 0,
+    FB200_END_OF_STREAM = 1,
+    FB200_INVALID_CODE = 2,
+    FB200_INVALID_MATCH = 3,
+    FB200_INVALID_BLOCK_TYPE = 4,
+    FB200_WRONG_STORED_BLOCK_NLEN = 5,
+    FB200_INVALID_DYNAMIC_BLOCK_HEADER = 6,
+    FB200_OVERSUBSCRIBED_HUFFMAN_TREE = 7,
+    FB200_INCOMPLETE_HUFFMAN_TREE = 8,
+    FB200_MISSING_END_OF_BLOCK_CODE = 9,
+    FB200_BAD_GZIP_HEADER = 10,
+    FB200_BAD_ZLIB_HEADER = 11,
+    FB200_WRONG_GZIP_CHECKSUM = 12,
+    FB200_WRONG_GZIP_SIZE = 13,
+    FB200_WRONG_ZLIB_CHECKSUM = 14,
+    FB200_UNFINISHED_BITS = 15,
+    FB200_INVALID_STATE = 16,
+    /* ours */
+    FB200_NO_SPACE_LEFT = 17, /* caller's output buffer too small (the writer's error in the reference) */
+    FB200_INVALID_ARGUMENT = 18,
+    FB200_ERR_CUDA = 19,      /* CUDA runtime failure; fb200_last_cuda_error() has the text */
+    FB200_NO_DEVICE = 20      /* no CUDA device: there is NO CPU fallback */
+};
+
+/* container.zig:17-21 */
+enum { FB200_RAW = 0, FB200_GZIP = 1, FB200_ZLIB = 2 };
+/* mode: 0 = store (deflate.zig:420), 1 = huffman-only (deflate.zig:401), 4..9 = Level (deflate.zig:23-32);
+ * FB200_LEVEL_DEFAULT = 6, fast = 4, best = 9 */
+enum { FB200_MODE_STORE = 0, FB200_MODE_HUFFMAN = 1, FB200_LEVEL_FAST = 4, FB200_LEVEL_DEFAULT = 6, FB200_LEVEL_BEST = 9 };
+
+/* token layout of fb200_debug_* : literal = byte; match = 0x80000000 | (distance-1) << 8 | (length-3) */
+#define FB200_TOKEN_MATCH 0x80000000u
+
+typedef struct fb200_ctx fb200_ctx;
+
+/* One context per GPU (and per host thread using it).  Owns a stream, the device workspace and
+ * pinned staging buffers; the workspace grows to the largest input seen. */
+int fb200_ctx_create(int device, fb200_ctx** ctx);
+void fb200_ctx_destroy(fb200_ctx* ctx);
+int fb200_device_count(void);
+const char* fb200_strerror(int code);
+const char* fb200_last_cuda_error(void);
+/* number of this library's kernels launched by ctx since creation (bench.py's gpu_launches) */
+uint64_t fb200_kernel_launches(const fb200_ctx* ctx);
+
+/* ---- one-shot, host buffers (H2D and D2H inside) ---- */
+size_t fb200_compress_bound(size_t n, int mode);
+int fb200_compress(fb200_ctx* ctx, int container, int mode, const uint8_t* in, size_t n, uint8_t* out, size_t cap,
+                   size_t* out_len);
+/* One member (like the reference's decompress()).  *consumed = bytes of `in` used, so callers can
+ * loop over concatenated members the way the reference loops reset() (inflate.zig:301, :544-563). */
+int fb200_decompress(fb200_ctx* ctx, int container, const uint8_t* in, size_t n, uint8_t* out, size_t cap,
+                     size_t* out_len, size_t* consumed);
+
+/* ---- device-resident variants: d_in/d_out are device pointers on ctx's GPU; `stream` is a
+ * cudaStream_t (NULL = the context's own stream).  d_out must hold fb200_compress_bound() bytes. ---- */
+int fb200_compress_device(fb200_ctx* ctx, int container, int mode, const void* d_in, size_t n, void* d_out, size_t cap,
+                          size_t* out_len, void* stream);
+/* k independent members (e.g. a multi-member gzip file with a member index): member i occupies
+ * d_in[in_off[i] .. in_off[i]+in_len[i]) and is inflated to d_out[out_off[i] .. +out_cap[i]).
+ * Per member: status[i], out_len[i], consumed[i] (host arrays).  Returns the first non-OK status. */
+int fb200_decompress_members_device(fb200_ctx* ctx, int container, const void* d_in, const uint64_t* in_off,
+                                    const uint64_t* in_len, size_t k, void* d_out, const uint64_t* out_off,
+                                    const uint64_t* out_cap, uint64_t* out_len, uint64_t* consumed, int* status,
+                                    void* stream);
+/* same with host buffers */
+int fb200_decompress_members(fb200_ctx* ctx, int container, const uint8_t* in, const uint64_t* in_off,
+                             const uint64_t* in_len, size_t k, uint8_t* out, const uint64_t* out_off,
+                             const uint64_t* out_cap, uint64_t* out_len, uint64_t* consumed, int* status);
+
+/* ---- streaming compressor (Compressor / SimpleCompressor) ---- */
+typedef struct fb200_deflate fb200_deflate;
+typedef int (*fb200_write_fn)(void* user, const uint8_t* data, size_t len); /* the `writer`; non-zero = error */
+int fb200_deflate_create(fb200_ctx* ctx, int container, int mode, fb200_write_fn writer, void* user, fb200_deflate** d);
+int fb200_deflate_write(fb200_deflate* d, const uint8_t* data, size_t n);
+int fb200_deflate_flush(fb200_deflate* d);
+int fb200_deflate_finish(fb200_deflate* d);
+void fb200_deflate_set_writer(fb200_deflate* d, fb200_write_fn writer, void* user);
+void fb200_deflate_destroy(fb200_deflate* d);
+
+/* ---- streaming decompressor (Decompressor) ---- */
+typedef struct fb200_inflate fb200_inflate;
+typedef size_t (*fb200_read_fn)(void* user, uint8_t* buf, size_t cap); /* the `reader`; 0 = end of input */
+int fb200_inflate_create(fb200_ctx* ctx, int container, fb200_read_fn reader, void* user, fb200_inflate** s);
+/* borrowed slice valid until the next call; *len == 0 at end of the member (inflate.zig:313-336) */
+int fb200_inflate_next(fb200_inflate* s, const uint8_t** data, size_t* len);
+int fb200_inflate_get(fb200_inflate* s, size_t limit, const uint8_t** data, size_t* len);
+int fb200_inflate_read(fb200_inflate* s, uint8_t* buf, size_t cap, size_t* n);
+int fb200_inflate_reset(fb200_inflate* s);
+void fb200_inflate_set_reader(fb200_inflate* s, fb200_read_fn reader, void* user);
+void fb200_inflate_destroy(fb200_inflate* s);
+
+/* ---- test seams (all run on the GPU) ---- */
+int fb200_debug_tokens(fb200_ctx* ctx, int level, const uint8_t* in, size_t n, uint32_t* tokens, size_t cap,
+                       size_t* ntok);
+int fb200_debug_match_tables(fb200_ctx* ctx, int level, const uint8_t* in, size_t n, uint32_t* r_full,
+                             uint32_t* r_quarter);
+/* kind: 0 = write, 1 = dynamicBlock, 2 = huffmanBlock */
+int fb200_debug_block_write(fb200_ctx* ctx, int kind, const uint32_t* tokens, size_t ntok, int eof,
+                            const uint8_t* input, size_t input_len, int has_input, uint8_t* out, size_t cap,
+                            size_t* out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,246 @@
+"""GPU parity tests of the deflate path, through the C ABI, against the CPU oracle and the
+reference's golden vectors.  Bit-exact everywhere (integer/byte work)."""
+import io
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, read_golden
+
+pytestmark = pytest.mark.gpu
+
+LEVELS = [4, 5, 6, 7, 8, 9]
+WBITS = {0: -15, 1: 31, 2: 15}
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import flate_b200
+    c = flate_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def o():
+    from oracle import oracle
+    return oracle
+
+
+def first_diff(a, b):
+    a = np.frombuffer(a, dtype=np.uint8) if isinstance(a, bytes) else np.asarray(a)
+    b = np.frombuffer(b, dtype=np.uint8) if isinstance(b, bytes) else np.asarray(b)
+    n = min(a.size, b.size)
+    d = np.nonzero(a[:n] != b[:n])[0]
+    return (int(d[0]) if d.size else n), a.size, b.size
+
+
+def inputs():
+    from flate_b200 import synth
+    rng = np.random.default_rng(7)
+    cases = {
+        "empty": b"", "one": b"a", "three": b"abc", "four": b"abcd", "five": b"aaaaa",
+        "blah": b"Blah blah blah blah blah!", "abcde": b"ABCDEABCD ABCDEABCD",
+        "rfc": read_golden("rfc1951.txt"),
+        "zeros70k": bytes(70000), "text64k-1": synth.enwik_like(65535).tobytes(),
+        "text64k": synth.enwik_like(65536).tobytes(), "text64k+1": synth.enwik_like(65537).tobytes(),
+        "text70000": synth.enwik_like(70000, seed=3).tobytes(),
+        "text98304": synth.enwik_like(98304, seed=4).tobytes(),
+        "mixed130809": synth.mixed_small(130809, seed=5).tobytes(),
+        "mixed130810": synth.mixed_small(130810, seed=6).tobytes(),
+        "mixed200001": synth.mixed_small(200001, seed=8).tobytes(),
+        "random100k": rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(),
+        "lowentropy": rng.integers(0, 3, 150000, dtype=np.uint8).tobytes(),
+        "text1M": synth.enwik_like(1 << 20, seed=9).tobytes(),
+    }
+    return cases
+
+
+@pytest.fixture(scope="module")
+def data_cases():
+    return inputs()
+
+
+@pytest.mark.parametrize("level", LEVELS)
+def test_match_tables_equal_oracle(ctx, o, data_cases, level):
+    """K1+K2 in isolation: findMatch for every position under both budgets (deflate.zig:233-266)."""
+    for name in ("blah", "rfc", "text70000", "mixed130810", "lowentropy"):
+        d = data_cases[name]
+        if level >= 8 and len(d) > 140000:
+            continue
+        rf, rq = ctx.debug_match_tables(d, level)
+        of, oq = o.match_tables(d, level)
+        assert first_diff(rf, of)[0] == len(d), (name, level, "full", first_diff(rf, of))
+        assert first_diff(rq, oq)[0] == len(d), (name, level, "quarter", first_diff(rq, oq))
+
+
+@pytest.mark.parametrize("level", LEVELS)
+def test_token_stream_equals_oracle(ctx, o, data_cases, level):
+    for name, d in data_cases.items():
+        if not d:
+            continue
+        if level >= 8 and name in ("lowentropy", "text1M"):
+            continue
+        got = ctx.debug_tokens(d, level)
+        want = o.tokenize(d, level)
+        fd = first_diff(got, want)
+        assert fd[0] == want.size and got.size == want.size, (name, level, fd)
+
+
+def test_exact_token_goldens(ctx):
+    """deflate.zig:539-554"""
+    M = lambda d, l: 0x80000000 | ((d - 1) << 8) | (l - 3)
+    L = ord
+    assert ctx.debug_tokens(b"Blah blah blah blah blah!", 6).tolist() == \
+        [L('B'), L('l'), L('a'), L('h'), L(' '), L('b'), M(5, 18), L('!')]
+    assert ctx.debug_tokens(b"ABCDEABCD ABCDEABCD", 6).tolist() == \
+        [L(c) for c in "ABCDEABCD A"] + [M(10, 8)]
+
+
+def test_token_count_goldens(ctx):
+    """deflate.zig:613-643"""
+    table = [
+        (("rfc1951.txt",), [7675, 7672, 7599, 7594, 7598, 7599]),
+        (("block_writer", "huffman-null-max.input"), [257] * 6),
+        (("block_writer", "huffman-pi.input"), [2570, 2564, 2564, 2564, 2564, 2564]),
+        (("block_writer", "huffman-text.input"), [235, 234, 234, 234, 234, 234]),
+        (("fuzz", "roundtrip1.input"), [333, 331, 331, 331, 331, 331]),
+        (("fuzz", "roundtrip2.input"), [334] * 6),
+    ]
+    for path, counts in table:
+        d = read_golden(*path)
+        for level, want in zip(LEVELS, counts):
+            assert ctx.debug_tokens(d, level).size == want, (path, level)
+
+
+@pytest.mark.parametrize("kind", ["wb", "dyn", "huff"])
+def test_block_writer_goldens(ctx, kind):
+    """block_writer.zig:599-706: 43 byte-exact block encodings, eof False and True."""
+    cases = json.load(open(os.path.join(GOLDEN, "block_writer_tokens.json")))
+    extra = [{"input": "huffman-rand-max.input", "want": "huffman-rand-max.{s}.expect", "want_no_input": "",
+              "tokens": []}] if kind == "huff" else []
+    n = 0
+    for tc in cases + extra:
+        toks = np.array([t[0] if len(t) == 1 else (0x80000000 | ((t[0] - 1) << 8) | (t[1] - 3)) for t in tc["tokens"]],
+                        dtype=np.uint32)
+        variants = []
+        if tc["input"] and tc["want"]:
+            variants.append((read_golden("block_writer", tc["input"]),
+                             read_golden("block_writer", tc["want"].replace("{s}", kind))))
+        if kind != "huff" and tc["want_no_input"]:
+            variants.append((None, read_golden("block_writer", tc["want_no_input"].replace("{s}", kind))))
+        for inp, want in variants:
+            got = ctx.debug_block_write(kind, toks, False, inp)
+            assert got == want, (tc["want"] or tc["want_no_input"], kind, inp is None, first_diff(got, want))
+            got_eof = bytearray(ctx.debug_block_write(kind, toks, True, inp))
+            assert got_eof[0] & 1 == 1
+            got_eof[0] &= 0xFE
+            assert bytes(got_eof) == want
+            n += 1
+    assert n == {"wb": 17, "dyn": 17, "huff": 9}[kind]
+
+
+def test_compressed_size_goldens(ctx):
+    """src/flate.zig:95-124: exact sizes for 4 inputs x (6 levels + huffman + store) x 3 containers."""
+    table = [
+        (("rfc1951.txt",), [11513, 11217, 11139, 11126, 11122, 11119], 20287, 36967),
+        (("fuzz", "roundtrip1.input"), [373, 370, 370, 370, 370, 370], 393, 393),
+        (("fuzz", "roundtrip2.input"), [373] * 6, 394, 394),
+        (("fuzz", "deflate-stream.expect"), [351, 347, 347, 347, 347, 347], 498, 747),
+    ]
+    csize = {0: 0, 1: 18, 2: 6}
+    for path, gz, huff, store in table:
+        d = read_golden(*path)
+        for mode, want in list(zip(LEVELS, gz)) + [(1, huff), (0, store)]:
+            for container in (0, 1, 2):
+                c = ctx.compress(d, container, mode)
+                assert len(c) == want - 18 + csize[container], (path, mode, container)
+                assert zlib.decompress(c, WBITS[container]) == d
+
+
+@pytest.mark.parametrize("mode", [0, 1] + LEVELS)
+def test_compress_bit_exact_vs_oracle(ctx, o, data_cases, mode):
+    for name, d in data_cases.items():
+        if mode >= 8 and name in ("lowentropy", "text1M"):
+            continue
+        for container in ((0, 1, 2) if len(d) < 100000 else (0,)):
+            got = ctx.compress(d, container, mode)
+            want = o.compress(d, container, mode)
+            assert got == want, (name, mode, container, first_diff(got, want))
+
+
+def test_kats(ctx):
+    """SURVEY appendix A6 + src/flate.zig:356-384"""
+    for lvl in LEVELS:
+        assert ctx.compress(b"", 0, lvl) == bytes([0x03, 0x00])
+    assert ctx.compress(b"a", 0, 6) == bytes([0x4B, 0x04, 0x00])
+    assert ctx.compress(b"", 0, 1) == bytes([0x01, 0x00, 0x00, 0xFF, 0xFF])
+    hello = b"Hello world\n"
+    stored = bytes([1, 12, 0, 0xF3, 0xFF]) + hello
+    assert ctx.compress(hello, 0, 0) == stored
+    assert ctx.compress(hello, 1, 0) == bytes([0x1F, 0x8B, 8, 0, 0, 0, 0, 0, 0, 3]) + stored + \
+        bytes([0xD5, 0xE0, 0x39, 0xB7, 0x0C, 0, 0, 0])
+    assert ctx.compress(hello, 2, 0) == bytes([0x78, 0x9C]) + stored + bytes([0x1C, 0xF2, 0x04, 0x47])
+    assert ctx.compress(b"Hello world!", 0, 1) == bytes([1, 12, 0, 0xF3, 0xFF]) + b"Hello world!"
+
+
+def test_stored_input_quirk(ctx, o):
+    """the 32768-th token is a match whose bytes are not in `input`; the reference
+    then emits a stored block that drops them.  Bit-exactness means reproducing it."""
+    rng = np.random.default_rng(11)
+    rnd = rng.integers(0, 256, 32770, dtype=np.uint8).tobytes()
+    from flate_b200 import synth
+    d = rnd[:32767] + rnd[100:130] + synth.enwik_like(40000, seed=21).tobytes()
+    for lvl in (4, 6, 9):
+        assert ctx.compress(d, 0, lvl) == o.compress(d, 0, lvl)
+
+
+def test_huffman_only_and_store_multiblock(ctx, o):
+    from flate_b200 import synth
+    d = synth.random_zero_mix(65535 * 3 + 17).tobytes()
+    for mode in (0, 1):
+        for n in (65534, 65535, 65536, 65535 * 2, len(d)):
+            got = ctx.compress(d[:n], 0, mode)
+            assert got == o.compress(d[:n], 0, mode), (mode, n)
+            assert zlib.decompress(got, -15) == d[:n]
+
+
+def test_public_interface_compressor(ctx, o):
+    """src/flate.zig:386-481 testInterface, all API spellings"""
+    import flate_b200
+    plain = b"Hello world\n" * 50 + read_golden("rfc1951.txt")[:5000]
+    for mod, container in ((flate_b200.flate, 0), (flate_b200.gzip, 1), (flate_b200.zlib, 2)):
+        w = io.BytesIO()
+        mod.compress(io.BytesIO(plain), w, level=flate_b200.Level.default, ctx=ctx)
+        assert w.getvalue() == o.compress(plain, container, 6)
+        w2 = io.BytesIO()
+        c = mod.compressor(w2, level=flate_b200.Level.best, ctx=ctx)
+        for i in range(0, len(plain), 777):
+            c.writer().write(plain[i:i + 777])
+        c.finish()
+        assert w2.getvalue() == o.compress(plain, container, 9)
+        for simple, mode in ((mod.huffman, 1), (mod.store, 0)):
+            w3 = io.BytesIO()
+            simple.compress(io.BytesIO(plain), w3, ctx=ctx)
+            assert w3.getvalue() == o.compress(plain, container, mode)
+            w4 = io.BytesIO()
+            sc = simple.compressor(w4, ctx=ctx)
+            sc.compress(io.BytesIO(plain))
+            sc.finish()
+            assert w4.getvalue() == w3.getvalue()
+
+
+def test_device_resident_compress(ctx, o):
+    import torch
+    from flate_b200 import synth
+    d = synth.enwik_like(3 << 20, seed=31)
+    t_in = torch.from_numpy(d).cuda()
+    cap = ctx.lib.fb200_compress_bound(d.size, 6) + 64
+    t_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    n = ctx.compress_device(t_in.data_ptr(), d.size, t_out.data_ptr(), cap, mode=6,
+                            stream=torch.cuda.current_stream().cuda_stream)
+    got = t_out[:n].cpu().numpy().tobytes()
+    assert got == o.compress(d.tobytes(), 0, 6)

@@ -1,0 +1,189 @@
+"""GPU parity tests of the inflate path through the C ABI: golden streams, the reference's fuzz
+corpus error classes, container errors, multi-member inputs, and round trips."""
+import io
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import read_golden
+from test_oracle_golden import DYNAMIC, FIXED, FUZZ, GZ_FTR, GZ_HDR, HELLO, STORED
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import flate_b200
+    c = flate_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def o():
+    from oracle import oracle
+    return oracle
+
+
+def err_name(ctx, data, container=0):
+    import flate_b200
+    with pytest.raises(flate_b200.FlateError) as ei:
+        ctx.decompress(bytes(data), container)
+    return type(ei.value).__name__
+
+
+def test_block_types(ctx):
+    """inflate.zig:357-479"""
+    assert ctx.decompress(STORED)[0] == HELLO
+    assert ctx.decompress(FIXED)[0] == HELLO
+    assert ctx.decompress(DYNAMIC)[0] == b"ABCDEABCD ABCDEABCD"
+    assert ctx.decompress(GZ_HDR + STORED + GZ_FTR, 1)[0] == HELLO
+    assert ctx.decompress(GZ_HDR + DYNAMIC + bytes([0x17, 0x1C, 0x39, 0xB4, 0x13, 0, 0, 0]), 1)[0] == \
+        b"ABCDEABCD ABCDEABCD"
+    named = bytes([0x1F, 0x8B, 0x08, 0x08, 0xE5, 0x70, 0xB1, 0x65, 0x00, 0x03, 0x68, 0x65, 0x6C, 0x6C, 0x6F, 0x2E,
+                   0x74, 0x78, 0x74, 0x00]) + FIXED + GZ_FTR
+    assert ctx.decompress(named, 1)[0] == HELLO
+    assert ctx.decompress(bytes([0x78, 0x9C]) + STORED + bytes([0x1C, 0xF2, 0x04, 0x47]), 2)[0] == HELLO
+
+
+@pytest.mark.parametrize("name,out,err", FUZZ)
+def test_fuzz_corpus(ctx, name, out, err):
+    """inflate.zig:487-526: error class per corrupt input"""
+    data = read_golden("fuzz", name + ".input")
+    if err:
+        assert err_name(ctx, data) == err
+    else:
+        want = read_golden("fuzz", name + ".expect") if out == "FILE" else out
+        assert ctx.decompress(data)[0] == want
+
+
+def test_container_errors(ctx):
+    """src/flate.zig:255-354"""
+    assert err_name(ctx, [0x78], 2) == "EndOfStream"
+    assert err_name(ctx, [0x79, 0x94], 2) == "BadZlibHeader"
+    assert err_name(ctx, [0x88, 0x98], 2) == "BadZlibHeader"
+    assert err_name(ctx, [0x78, 0xDA, 0x03, 0x00, 0x00, 0x00, 0x00, 0x00], 2) == "WrongZlibChecksum"
+    assert err_name(ctx, [0x78, 0xDA, 0x03, 0x00, 0x00], 2) == "EndOfStream"
+    assert err_name(ctx, [0x1F, 0x8B], 1) == "EndOfStream"
+    assert err_name(ctx, [0x1F, 0x8B, 0x09, 0, 0, 0, 0, 0, 0, 0x03], 1) == "BadGzipHeader"
+    h = [0x1F, 0x8B, 0x08, 0, 0, 0, 0, 0, 0, 0x03]
+    assert err_name(ctx, h + [0x03, 0x00, 0, 0, 0, 0x01, 0, 0, 0, 0], 1) == "WrongGzipChecksum"
+    assert err_name(ctx, h + [0x03, 0x00, 0, 0, 0], 1) == "EndOfStream"
+    assert err_name(ctx, h + [0x03, 0x00, 0, 0, 0, 0, 0, 0, 0, 0x01], 1) == "WrongGzipSize"
+    assert err_name(ctx, h + [0x03, 0x00, 0, 0, 0, 0, 0, 0, 0], 1) == "EndOfStream"
+    fhcrc = [0x1F, 0x8B, 0x08, 0x12, 0x00, 0x09, 0x6E, 0x88, 0x00, 0xFF, 0x48, 0x65, 0x6C, 0x6C, 0x6F, 0x00,
+             0x99, 0xD6, 0x01, 0x00, 0x00, 0xFF, 0xFF, 0, 0, 0, 0, 0, 0, 0, 0]
+    assert ctx.decompress(bytes(fhcrc), 1)[0] == b""
+    data = bytes([0x08, 0xD7, 0x63, 0xF8, 0xCF, 0xC0, 0xC0, 0x00, 0xC1, 0xFF, 0xFF, 0x43, 0x30, 0x03, 0x03, 0xC3,
+                  0xFF, 0xFF, 0xFF, 0x01, 0x83, 0x95, 0x0B, 0xF5])
+    want = bytes([0x00, 0xFF, 0x00, 0x00, 0x00, 0xFF, 0x00, 0x00, 0x00, 0xFF, 0x00, 0xFF, 0xFF, 0xFF, 0x00, 0xFF,
+                  0xFF, 0xFF, 0x00, 0x00, 0x00, 0x00, 0xFF, 0xFF, 0xFF])
+    assert ctx.decompress(data, 2)[0] == want
+
+
+def test_two_zlib_members_via_reset(ctx):
+    """inflate.zig:544-563 'flate bug 18967'"""
+    import flate_b200
+    data = read_golden("fuzz", "first.input") + read_golden("fuzz", "second.input")
+    want = read_golden("fuzz", "first.expect") + read_golden("fuzz", "second.expect")
+    out = io.BytesIO()
+    d = flate_b200.zlib.decompressor(io.BytesIO(data), ctx=ctx)
+    d.decompress(out)
+    d.reset()
+    d.decompress(out)
+    assert out.getvalue() == want
+
+
+def test_reset_before_end_is_invalid_state(ctx):
+    import flate_b200
+    d = flate_b200.flate.decompressor(io.BytesIO(FIXED), ctx=ctx)
+    with pytest.raises(flate_b200.FlateError) as ei:
+        d.reset()
+    assert type(ei.value).__name__ == "InvalidState"
+
+
+def test_roundtrip_all_modes_vs_oracle_and_zlib(ctx, o):
+    """bin/roundtrip.zig:14-75 behaviour: every level + huffman + store must round-trip"""
+    from flate_b200 import synth
+    rng = np.random.default_rng(3)
+    datas = [synth.enwik_like(300000, seed=41).tobytes(), synth.mixed_small(250000, seed=42).tobytes(),
+             rng.integers(0, 256, 70000, dtype=np.uint8).tobytes(), bytes(100000), b"", b"x"]
+    for d in datas:
+        for mode in (0, 1, 4, 6, 9):
+            for container in (0, 1, 2):
+                c = o.compress(d, container, mode)
+                plain, used = ctx.decompress(c, container)
+                assert plain == d and used == len(c), (len(d), mode, container)
+        # streams produced by zlib itself (different block structure, fixed blocks, long distances)
+        for lvl in (1, 6, 9):
+            co = zlib.compressobj(lvl, zlib.DEFLATED, -15)
+            c = co.compress(d) + co.flush()
+            assert ctx.decompress(c, 0)[0] == d
+
+
+def test_reader_interface_and_limits(ctx, o):
+    import flate_b200
+    d = read_golden("rfc1951.txt")
+    c = o.compress(d, 1, 6)
+    dec = flate_b200.gzip.decompressor(io.BytesIO(c), ctx=ctx)
+    got = bytearray()
+    while True:
+        b = dec.reader().read(1000)
+        if not b:
+            break
+        assert len(b) <= 1000
+        got += b
+    assert bytes(got) == d
+
+
+def test_members_batch(ctx, o):
+    """many independent gzip members in one launch (config C3 shape, small)"""
+    from flate_b200 import synth
+    members, plains = [], []
+    for i in range(37):
+        p = synth.enwik_like(20000 + 1777 * i, seed=100 + i).tobytes()
+        plains.append(p)
+        members.append(o.compress(p, 1, 6))
+    blob = b"".join(members)
+    off = np.cumsum([0] + [len(m) for m in members[:-1]])
+    outs, st, used = ctx.decompress_members(blob, off, [len(m) for m in members], [len(p) + 64 for p in plains], 1)
+    assert st == [0] * len(members)
+    assert outs == plains
+    assert used == [len(m) for m in members]
+    # corrupt one member: only that one fails, with the reference's class
+    bad = bytearray(blob)
+    bad[int(off[5]) + len(members[5]) - 6] ^= 0xFF  # CRC byte
+    outs, st, _ = ctx.decompress_members(bytes(bad), off, [len(m) for m in members], [len(p) + 64 for p in plains], 1)
+    assert st[5] == 12 and all(s == 0 for i, s in enumerate(st) if i != 5)
+
+
+def test_puff_cross_check(ctx, o):
+    """the reference's own differential oracle (bin/fuzz_puff.zig:42-50): output and success must agree"""
+    try:
+        o.puff(b"\x03\x00")
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libpuff.so absent")
+    import flate_b200
+    rng = np.random.default_rng(5)
+    base = o.compress(read_golden("rfc1951.txt")[:3000], 0, 6)
+    for trial in range(60):
+        b = bytearray(base)
+        for _ in range(1 + trial % 3):
+            b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        rc, plain, _ = o.puff(bytes(b), cap=1 << 20)
+        try:
+            got = ctx.decompress(bytes(b), 0, cap=1 << 20)[0]
+            ok = True
+        except flate_b200.FlateError:
+            ok = False
+        assert ok == (rc == 0), trial
+        if ok:
+            assert got == plain
+        # and the error class equals the oracle's
+        try:
+            want = o.decompress(bytes(b), cap=1 << 20)[0]
+            assert ok and want == got
+        except o.OracleError as e:
+            assert not ok
+            assert err_name(ctx, b) == e.name
