@@ -19,6 +19,10 @@ SIGNATURES = {
     "fb200_strerror": (C.c_char_p, [_I]),
     "fb200_last_cuda_error": (C.c_char_p, []),
     "fb200_kernel_launches": (C.c_uint64, [_P]),
+    "fb200_profile_enable": (_I, [_P, _I]),
+    "fb200_profile_phases": (_I, []),
+    "fb200_profile_phase_name": (C.c_char_p, [_I]),
+    "fb200_profile_read": (_I, [_P, _P, _P, _I]),
     "fb200_compress_bound": (_SZ, [_SZ, _I]),
     "fb200_compress": (_I, [_P, _I, _I, _P, _SZ, _P, _SZ, _SZP]),
     "fb200_decompress": (_I, [_P, _I, _P, _SZ, _P, _SZ, _SZP, _SZP]),

@@ -80,6 +80,17 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.fb200_kernel_launches(self.h))
 
+    def profile(self, on=True):
+        self.lib.fb200_profile_enable(self.h, int(on))
+
+    def profile_read(self):
+        """{phase name: (total ms, launches)} accumulated since profile(True)."""
+        n = self.lib.fb200_profile_phases()
+        ms = np.zeros(n, dtype=np.float64)
+        cnt = np.zeros(n, dtype=np.uint64)
+        self.lib.fb200_profile_read(self.h, ms.ctypes.data, cnt.ctypes.data, n)
+        return {self.lib.fb200_profile_phase_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
     # ---- one-shot, host buffers ----
     def compress(self, data, container=RAW, mode=Level.default):
         a = _as_u8(data)

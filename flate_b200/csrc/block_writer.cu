@@ -320,6 +320,9 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
         sh.dist_freq[i] = pl.kind == kHuffmanBlock ? 0 : (uint16_t)dist_freq_g[(size_t)b * kNumDist + i];
     __syncwarp();
     uint32_t num_literals, num_distances;
+    // the reference counts one distance symbol that is never written when a block has no match
+    // (:476-481, :531): it is part of the size estimates but not of the emitted body
+    bool phantom_dist = pl.kind == kHuffmanBlock;
     if (pl.kind == kHuffmanBlock) {  // block_writer.zig:528-532
         if (lane == 0) { sh.lit_freq[kEndBlock] = 1; sh.dist_freq[0] = 1; }
         num_literals = kEndBlock + 1;
@@ -334,6 +337,7 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
         if (num_distances == 0) {
             if (lane == 0) sh.dist_freq[0] = 1;
             num_distances = 1;
+            phantom_dist = true;
         }
     }
     __syncwarp();
@@ -447,7 +451,7 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
         sh.body_bits = 0;
     } else if (type == kFixed) {
         hw.put(pl.eof ? 3 : 2, 3);  // :293-300
-        sh.body_bits = (uint64_t)fixed_bits + true_extra;
+        sh.body_bits = (uint64_t)fixed_bits + true_extra - (phantom_dist ? 5 : 0);
     } else {  // dynamicHeader, :237-281
         hw.put(pl.eof ? 5 : 4, 3);
         hw.put(num_literals - 257, 5);
@@ -462,7 +466,7 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
             else if (cw == 17) hw.put(sh.codegen[i++], 3);
             else if (cw == 18) hw.put(sh.codegen[i++], 7);
         }
-        sh.body_bits = (uint64_t)lit_bits + dist_bits + true_extra;
+        sh.body_bits = (uint64_t)lit_bits + dist_bits + true_extra - (phantom_dist ? (sh.dist_code[0] >> 16) : 0);
     }
     sh.hdr_bits = hw.nbits;
     }  // lane 0

@@ -77,6 +77,7 @@ struct fb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
+    PhaseTimer timer;
     // LZ77 workspace
     DevBuf<uint16_t> link, exits, gexits, gentry, entry;
     DevBuf<uint32_t> r_full, r_quarter, nx, bitmap, chunk_tokens, tok_offset, tokens, cut_rp;
@@ -113,6 +114,24 @@ const char* fb200_strerror(int code) {
     return names[code];
 }
 uint64_t fb200_kernel_launches(const fb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int fb200_profile_enable(fb200_ctx* ctx, int on) {
+    if (!ctx) return FB200_INVALID_ARGUMENT;
+    ctx->timer.on = on != 0;
+    for (int i = 0; i < kPhCount; i++) ctx->timer.ms[i] = 0, ctx->timer.count[i] = 0;
+    return FB200_OK;
+}
+int fb200_profile_phases(void) { return kPhCount; }
+const char* fb200_profile_phase_name(int i) {
+    static const char* names[] = {"hash_link", "match_search", "lazy_step", "chunk_exit", "resolve_entries", "orbit_mark",
+                                  "scan_tokens", "emit_tokens", "plan+histogram", "build_blocks", "offsets+zero", "pack_blocks",
+                                  "inflate_members"};
+    return (i >= 0 && i < kPhCount) ? names[i] : "?";
+}
+int fb200_profile_read(const fb200_ctx* ctx, double* ms, uint64_t* count, int n) {
+    if (!ctx || !ms || !count) return FB200_INVALID_ARGUMENT;
+    for (int i = 0; i < n && i < kPhCount; i++) ms[i] = ctx->timer.ms[i], count[i] = ctx->timer.count[i];
+    return FB200_OK;
+}
 
 int fb200_ctx_create(int device, fb200_ctx** out) {
     if (!out) return FB200_INVALID_ARGUMENT;
@@ -212,12 +231,14 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         max_blocks = (uint32_t)(n / kTokensPerBlock + 3);
         if ((rc = ensure_blocks(c, max_blocks))) return rc;
         Lz77Buffers b = lz77_view(c);
-        FB_CUDA_CHECK(lz77_tokenize(b, d_in, (uint32_t)n, lv, st));
+        c->timer.begin(st);
+        FB_CUDA_CHECK(lz77_tokenize(b, d_in, (uint32_t)n, lv, st, &c->timer));
         c->launches += n ? 10 : 0;
         FB_CUDA_CHECK(plan_level_blocks(b.total_tokens, b.cut_rp, (uint32_t)n, max_blocks, final_flush ? 1 : 0, c->plans.p,
                                         nblocks_dev, st));
         FB_CUDA_CHECK(histogram_tokens(b.tokens, c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, st));
         c->launches += 2;
+        c->timer.mark(st, kPhHist);
         tokens = b.tokens;
     } else if (mode == FB200_MODE_HUFFMAN || mode == FB200_MODE_STORE) {
         const uint64_t nb64 = n / kMaxStore + 1;
@@ -225,6 +246,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         max_blocks = (uint32_t)nb64;
         int rc = ensure_blocks(c, max_blocks);
         if (rc) return rc;
+        c->timer.begin(st);
         plan_simple_blocks_kernel<<<(max_blocks + 255) / 256, 256, 0, st>>>(n, max_blocks,
                                                                             mode == FB200_MODE_HUFFMAN ? kHuffmanBlock : 3u,
                                                                             c->plans.p, nblocks_dev);
@@ -233,20 +255,25 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         if (mode == FB200_MODE_HUFFMAN) {
             FB_CUDA_CHECK(histogram_bytes(d_in, c->plans.p, max_blocks, c->lit_freq.p, st));
             c->launches += 1;
+            c->timer.mark(st, kPhHist);
         }
     } else {
         return FB200_INVALID_ARGUMENT;
     }
     FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, c->descs.p, st));
+    c->timer.mark(st, kPhBuild);
     FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, header_size(container) * 8, total_bits_dev, st));
     zero_output_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<uint32_t*>(d_out), total_bits_dev, cap / 4);
     FB_CUDA_CHECK(cudaGetLastError());
     if (container == FB200_GZIP) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kGzipHeader, 10, cudaMemcpyHostToDevice, st));
     if (container == FB200_ZLIB) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kZlibHeader, 2, cudaMemcpyHostToDevice, st));
+    c->timer.mark(st, kPhOffsets);
     FB_CUDA_CHECK(pack_blocks(d_in, tokens, c->descs.p, nblocks_dev, max_blocks, reinterpret_cast<uint32_t*>(d_out), st));
+    c->timer.mark(st, kPhPack);
     c->launches += 4;
     FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    c->timer.collect();
     *end_bytes = (size_t)((c->h_scalars[0] + 7) >> 3);
     return FB200_OK;
 }
@@ -443,10 +470,13 @@ static int run_members(fb200_ctx* c, int container, const uint8_t* d_in, const M
     MemberDesc* d_desc = reinterpret_cast<MemberDesc*>(c->m_desc.p);
     MemberResult* d_res = reinterpret_cast<MemberResult*>(c->m_desc.p + desc_words);
     FB_CUDA_CHECK(cudaMemcpyAsync(d_desc, h_desc, k * sizeof(MemberDesc), cudaMemcpyHostToDevice, st));
+    c->timer.begin(st);
     FB_CUDA_CHECK(inflate_members(container, d_in, d_desc, (uint32_t)k, d_out, d_res, st));
+    c->timer.mark(st, kPhInflate);
     c->launches += 1;
     FB_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, k * sizeof(MemberResult), cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    c->timer.collect();
     return FB200_OK;
 }
 

@@ -228,19 +228,57 @@ __device__ uint32_t warp_adler32(const uint8_t* p, uint64_t n) {
 
 #define BCAST(x) __shfl_sync(0xffffffffu, (x), 0)
 
-__global__ void __launch_bounds__(kInflateWarps * 32)
+// ---- output window: the reference's CircularBuffer (CircularBuffer.zig) as a per-warp ring in
+// shared memory.  Literals and match copies stay on the SM; the ring is drained to HBM in
+// 16-byte coalesced stores.  Ring slot of output position p is (p + A) mod kRing with
+// A = (address of out) mod 16, so ring and global alignment agree.
+constexpr uint32_t kRing = 32768;
+constexpr uint32_t kFlushAt = 8192;  // drain when this many bytes are pending
+
+struct OutWindow {
+    uint8_t* ring;
+    uint8_t* out;
+    uint32_t A;
+    uint64_t flushed;  // output positions [0, flushed) are in HBM
+    __device__ __forceinline__ uint32_t slot(uint64_t p) const { return (uint32_t)(p + A) & (kRing - 1); }
+    // drain [flushed, upto); whole warp.  upto is either 16-byte aligned in (p + A) or final.
+    __device__ void drain(uint64_t upto) {
+        const uint32_t lane = threadIdx.x & 31;
+        uint64_t f = flushed;
+        // head: bytes until (f + A) is 16-byte aligned
+        const uint64_t head_end = min(upto, (f + A + 15) / 16 * 16 - A);
+        for (uint64_t p = f + lane; p < head_end; p += 32) out[p] = ring[slot(p)];
+        f = head_end;
+        const uint64_t nvec = (upto - f) / 16;
+        for (uint64_t v = lane; v < nvec; v += 32) {
+            const uint64_t p = f + v * 16;
+            *reinterpret_cast<uint4*>(out + p) = *reinterpret_cast<const uint4*>(ring + slot(p));
+        }
+        f += nvec * 16;
+        for (uint64_t p = f + lane; p < upto; p += 32) out[p] = ring[slot(p)];
+        flushed = upto;
+        __syncwarp();
+    }
+};
+
+__global__ void __launch_bounds__(32)
 inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const MemberDesc* __restrict__ descs, uint32_t k,
                        uint8_t* d_out, MemberResult* __restrict__ results) {
-    __shared__ WarpTables tabs_all[kInflateWarps];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t m = blockIdx.x * kInflateWarps + (threadIdx.x >> 5);
+    const uint32_t m = blockIdx.x;
     if (m >= k) return;
-    WarpTables& T = tabs_all[threadIdx.x >> 5];
+    WarpTables& T = *reinterpret_cast<WarpTables*>(smem_raw + kRing);
     const MemberDesc md = descs[m];
     uint8_t* out = d_out + md.out_off;
     const uint64_t cap = md.out_cap;
-    uint64_t pos = 0;  // bytes produced (uniform across the warp)
+    uint64_t pos = 0;  // bytes produced (uniform across the warp after each broadcast)
     int status = FB200_OK;
+    OutWindow W;
+    W.ring = smem_raw;
+    W.out = out;
+    W.A = (uint32_t)((uintptr_t)out & 15);
+    W.flushed = 0;
 
     BitCursor bc;
     bc.next = d_in + md.in_off;
@@ -311,8 +349,14 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
             if (status) break;
             len = BCAST(len);
             src = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)src, 0);
-            for (uint32_t i = lane; i < len; i += 32) out[pos + i] = src[i];
-            pos += len;
+            for (uint32_t done = 0; done < len;) {  // through the ring in pieces so history stays valid
+                const uint32_t piece = min(len - done, 4096u);
+                for (uint32_t i = lane; i < piece; i += 32) W.ring[W.slot(pos + i)] = src[done + i];
+                __syncwarp();
+                pos += piece;
+                done += piece;
+                if (pos - W.flushed >= kFlushAt) W.drain(pos - ((pos + W.A) & 15));
+            }
             if (lane == 0) {  // reposition the cursor after the raw bytes
                 bc.next = src + len;
                 bc.buf = 0;
@@ -329,7 +373,7 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                     if (!status) { status = bc.read(5, v); hdist = v + 1; }
                     if (!status) { status = bc.read(4, v); hclen = v + 4; }
                     if (!status && (hlit > 286 || hdist > 30)) status = FB200_INVALID_DYNAMIC_BLOCK_HEADER;
-                    // code-length code lengths live in lit_lens[0..19) temporarily (dist_lens as scratch)
+                    // code-length code lengths go to dist_lens[0..19) temporarily
                     if (!status) {
                         for (uint32_t i = 0; i < 19; i++) T.dist_lens[i] = 0;
                         for (uint32_t i = 0; i < hclen && !status; i++) {
@@ -394,23 +438,22 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                 status = build_decoder(T.dist_lens, kNumDist, false, 15, T.dist_count, T.dist_sym, T.dist_fast, kDistFast);
                 if (status) break;
             } else if (!fixed_ready) {
-                // fixed block: the reference decodes by arithmetic (bit_reader.zig:205-217); the same
-                // symbols come out of the canonical code with lengths 8/9/7/8 and 5-bit distances.
+                // fixed block: the reference decodes by arithmetic (bit_reader.zig:205-217); the same symbols
+                // come out of the canonical code with lengths 8/9/7/8 over 288 symbols and 32 five-bit
+                // distance codes.  286/287 and 30/31 decode and are then rejected (inflate.zig:111,136).
                 build_fixed_lens(T.lit_lens, T.dist_lens);
-                // symbols 286/287 exist in the fixed code (-> InvalidCode, inflate.zig:111); use a 288 alphabet
                 status = build_decoder(T.lit_lens, 288, true, 15, T.lit_count, T.lit_sym, T.lit_fast, kLitFast);
-                if (!status) status = build_decoder(T.dist_lens, 30, false, 15, T.dist_count, T.dist_sym, T.dist_fast, kDistFast);
+                if (!status) status = build_decoder(T.dist_lens, 32, false, 15, T.dist_count, T.dist_sym, T.dist_fast, kDistFast);
                 if (status) break;
-                // 5-bit distance codes 30/31 are InvalidCode (inflate.zig:136): a 30-symbol 5-bit code is
-                // incomplete, the fallback reports InvalidCode for them.
                 fixed_ready = true;
             }
             // ---- symbol loop (inflate.zig:220-239 dynamicBlock / :104-124 fixedBlock) ----
             bool done = false;
             while (!done) {
-                uint32_t ev_len = 0, ev_dist = 0;  // match event (len > 0), or end of block / error
+                uint32_t ev_len = 0, ev_dist = 0;  // match event (len > 0); otherwise flush / end of block / error
                 if (lane == 0) {
                     for (;;) {
+                        if (pos - W.flushed >= kFlushAt) break;                    // drain request
                         if (bc.empty()) { status = FB200_END_OF_STREAM; break; }  // fill(15) / fill(7+2)
                         uint32_t sym, nb;
                         const uint32_t e = T.lit_fast[bc.peek(kLitFast)];
@@ -424,7 +467,8 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                         if (!bc.shift(nb)) { status = FB200_END_OF_STREAM; break; }
                         if (sym < 256) {
                             if (pos >= cap) { status = FB200_NO_SPACE_LEFT; break; }
-                            out[pos++] = (uint8_t)sym;
+                            W.ring[W.slot(pos)] = (uint8_t)sym;
+                            pos++;
                             continue;
                         }
                         if (sym == 256) { done = true; break; }
@@ -442,9 +486,7 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                             length += x;
                         }
                         uint32_t dsym, dnb;
-                        // fixed block: readF(u5, buffered) shifts 5 bits before the code is looked at
-                        // (inflate.zig:121, bit_reader.zig:113-117), so a short stream is EndOfStream first
-                        if (btype == 1) { bc.refill(); if (bc.cnt < 5) { status = FB200_END_OF_STREAM; break; } }
+                        bc.refill();
                         const uint32_t de = T.dist_fast[bc.peek(kDistFast)];
                         if (de & 15) {
                             dsym = de >> 4;
@@ -470,6 +512,7 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                         break;
                     }
                 }
+                __syncwarp();
                 status = BCAST(status);
                 if (status) break;
                 done = BCAST(done);
@@ -477,16 +520,30 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                 ev_len = BCAST(ev_len);
                 if (ev_len) {
                     ev_dist = BCAST(ev_dist);
-                    __syncwarp();
-                    const uint8_t* from = out + pos - ev_dist;
-                    if (ev_dist >= ev_len) {
-                        for (uint32_t i = lane; i < ev_len; i += 32) out[pos + i] = from[i];
+                    if (ev_dist <= kRing - 264 && ev_dist <= pos) {
+                        // source still in the ring: shared memory to shared memory
+                        const uint64_t from = pos - ev_dist;
+                        if (ev_dist >= ev_len) {
+                            for (uint32_t i = lane; i < ev_len; i += 32) W.ring[W.slot(pos + i)] = W.ring[W.slot(from + i)];
+                        } else {
+                            for (uint32_t i = lane; i < ev_len; i += 32)
+                                W.ring[W.slot(pos + i)] = W.ring[W.slot(from + i % ev_dist)];
+                        }
                     } else {
-                        for (uint32_t i = lane; i < ev_len; i += 32) out[pos + i] = from[i % ev_dist];
+                        // far match, or one that reaches into an earlier member's output: the source left the
+                        // ring but was drained to HBM long ago (pending <= kFlushAt + 258 < kRing - 264)
+                        for (uint32_t i = lane; i < ev_len; i += 32) {
+                            const int64_t sp = (int64_t)pos - ev_dist + (ev_dist >= ev_len ? i : i % ev_dist);
+                            uint8_t b;
+                            if (sp >= (int64_t)W.flushed) b = W.ring[W.slot((uint64_t)sp)];
+                            else b = __ldcg(out + sp);
+                            W.ring[W.slot(pos + i)] = b;
+                        }
                     }
                     pos += ev_len;
                     __syncwarp();
                 }
+                if (pos - W.flushed >= kFlushAt) W.drain(pos - ((pos + W.A) & 15));
             }
             if (status) break;
         } else {
@@ -496,6 +553,8 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
         if (bfinal) break;
     }
     pos = __shfl_sync(0xffffffffu, (unsigned long long)pos, 0);
+    __syncwarp();
+    W.drain(pos);  // whatever was produced, also on error (the caller sees out_len and the status)
 
     // ---- protocol footer (inflate.zig:271-275, container.zig:154-166) ----
     if (status == FB200_OK && container != FB200_RAW) {
@@ -594,8 +653,13 @@ __global__ void adler32_finish_kernel(const unsigned long long* __restrict__ acc
 cudaError_t inflate_members(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
                             MemberResult* d_res, cudaStream_t st) {
     if (k == 0) return cudaSuccess;
-    inflate_members_kernel<<<(k + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, 0, st>>>(container, d_in, d_desc, k,
-                                                                                                 d_out, d_res);
+    static bool attr_set = false;
+    const size_t smem = kRing + sizeof(WarpTables);
+    if (!attr_set) {
+        cudaFuncSetAttribute(inflate_members_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    inflate_members_kernel<<<k, 32, smem, st>>>(container, d_in, d_desc, k, d_out, d_res);
     return cudaGetLastError();
 }
 cudaError_t crc32_device(const uint8_t* d_data, uint64_t n, uint32_t* d_result, cudaStream_t st) {

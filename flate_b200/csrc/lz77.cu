@@ -423,7 +423,10 @@ emit_tokens_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // host-side launcher
 // ------------------------------------------------------------------------------------------
-cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st) {
+cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
+                          PhaseTimer* pt) {
+    PhaseTimer dummy;
+    if (!pt) pt = &dummy;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(hash_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4 + kLinkTile + 16);
@@ -436,18 +439,26 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n,
     }
     const uint32_t ntiles = (n + kLinkTile - 1) / kLinkTile;
     hash_link_kernel<<<(ntiles + kLinkRun - 1) / kLinkRun, 32, 32768 * 4 + kLinkTile + 16, st>>>(d_in, n, b.link);
+    pt->mark(st, kPhLink);
     match_search_kernel<<<(n + kSearchTile - 1) / kSearchTile, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv,
                                                                                                 b.r_full, b.r_quarter);
+    pt->mark(st, kPhSearch);
     lazy_step_kernel<<<(n + 255) / 256, 256, 0, st>>>(b.r_full, b.r_quarter, n, lv, b.nx);
+    pt->mark(st, kPhLazy);
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
     const uint32_t ngroups = (nchunks + kGroup - 1) / kGroup;
     chunk_exit_kernel<<<nchunks, 1024, 0, st>>>(b.nx, n, b.exits);
+    pt->mark(st, kPhChunkExit);
     group_exit_kernel<<<ngroups, 544, 0, st>>>(b.exits, nchunks, b.gexits);
     group_entry_kernel<<<1, 32, 0, st>>>(b.gexits, ngroups, b.gentry);
     chunk_entry_kernel<<<(ngroups + 127) / 128, 128, 0, st>>>(b.exits, b.gentry, nchunks, b.entry);
+    pt->mark(st, kPhResolve);
     orbit_mark_kernel<<<nchunks, kMarkThreads, 0, st>>>(b.nx, n, b.entry, b.bitmap, b.chunk_tokens);
+    pt->mark(st, kPhMark);
     scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
+    pt->mark(st, kPhScan);
     emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_in, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp);
+    pt->mark(st, kPhEmit);
     return cudaGetLastError();
 }
 

@@ -4,6 +4,49 @@
 
 namespace fb {
 
+// Optional per-phase device timing (CUDA events on the launching stream), used by bench.py to report
+// the dominant kernel's duration live.  Off by default: mark() is then a no-op.
+enum Phase : int {
+    kPhLink = 0, kPhSearch, kPhLazy, kPhChunkExit, kPhResolve, kPhMark, kPhScan, kPhEmit, kPhHist, kPhBuild,
+    kPhOffsets, kPhPack, kPhInflate, kPhCount
+};
+struct PhaseTimer {
+    static constexpr int kMaxMarks = 64;
+    bool on = false;
+    cudaEvent_t ev[kMaxMarks];
+    int phase_of[kMaxMarks];
+    int n = 0;
+    bool created = false;
+    double ms[kPhCount] = {0};
+    uint64_t count[kPhCount] = {0};
+    void begin(cudaStream_t st) {
+        if (!on) return;
+        if (!created) {
+            for (int i = 0; i < kMaxMarks; i++) cudaEventCreate(&ev[i]);
+            created = true;
+        }
+        n = 0;
+        cudaEventRecord(ev[n], st);
+        phase_of[n++] = -1;
+    }
+    void mark(cudaStream_t st, int phase) {  // call after the phase's kernels were launched
+        if (!on || n >= kMaxMarks) return;
+        cudaEventRecord(ev[n], st);
+        phase_of[n++] = phase;
+    }
+    void collect() {  // after the stream was synchronized
+        if (!on) return;
+        for (int i = 1; i < n; i++) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, ev[i - 1], ev[i]) == cudaSuccess && phase_of[i] >= 0) {
+                ms[phase_of[i]] += t;
+                count[phase_of[i]] += 1;
+            }
+        }
+        n = 0;
+    }
+};
+
 constexpr uint32_t kChunk = 4096;    // positions per lazy-parse chunk
 constexpr uint32_t kEntries = 516;   // possible entry offsets into a chunk (step <= 515)
 constexpr uint32_t kGroup = 256;     // chunks per resolution group
@@ -26,7 +69,8 @@ struct Lz77Buffers {
     uint32_t* cut_rp;        // nblocks: reference `rp` when block b's last token was added
 };
 
-cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st);
+cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
+                          PhaseTimer* pt = nullptr);
 
 // ---- block writer ----
 enum WriteKind : uint32_t { kWrite = 0, kDynamicBlock = 1, kHuffmanBlock = 2 };  // block_writer.zig:307,395,524

@@ -76,6 +76,11 @@ const char* fb200_strerror(int code);
 const char* fb200_last_cuda_error(void);
 /* number of this library's kernels launched by ctx since creation (bench.py's gpu_launches) */
 uint64_t fb200_kernel_launches(const fb200_ctx* ctx);
+/* optional per-phase device timing with CUDA events on the launching stream (for bench.py's roofline) */
+int fb200_profile_enable(fb200_ctx* ctx, int on); /* also clears the accumulated times */
+int fb200_profile_phases(void);
+const char* fb200_profile_phase_name(int phase);
+int fb200_profile_read(const fb200_ctx* ctx, double* ms, uint64_t* count, int n);
 
 /* ---- one-shot, host buffers (H2D and D2H inside) ---- */
 size_t fb200_compress_bound(size_t n, int mode);
