@@ -159,7 +159,7 @@ __device__ int build_decoder(const uint8_t* lens, uint32_t n, bool is_lit, uint3
 __device__ void build_fixed_lens(uint8_t* lit_lens, uint8_t* dist_lens) {
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t i = lane; i < 288; i += 32) lit_lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
-    for (uint32_t i = lane; i < 30; i += 32) dist_lens[i] = 5;
+    for (uint32_t i = lane; i < 32; i += 32) dist_lens[i] = 5;
     __syncwarp();
 }
 

@@ -109,6 +109,42 @@ def main():
         if p != d:
             return "inflate mismatch"
     stage("big 8MiB", big)
+
+    def members():
+        plains, mem = [], []
+        for i in range(40):
+            p = synth.enwik_like(300000 + 1777 * i, seed=100 + i).tobytes()
+            plains.append(p)
+            mem.append(o.compress(p, 1, 6))
+        blob = b"".join(mem)
+        off = np.cumsum([0] + [len(m) for m in mem[:-1]])
+        for rep in range(3):
+            t = time.time()
+            outs, st, used = ctx.decompress_members(blob, off, [len(m) for m in mem], [len(p) + 64 for p in plains], 1)
+            dt = time.time() - t
+        print("  members: %.4fs for %d bytes -> %.1f MB/s; status %s" % (dt, sum(map(len, plains)), sum(map(len, plains)) / dt / 1e6, st))
+        bad = [i for i in range(40) if outs[i] != plains[i]]
+        if bad:
+            return "members differ: %s offs %s" % (bad, [int(off[i]) % 16 for i in bad])
+    stage("members", members)
+
+    def timing():
+        d = synth.enwik_like(32 << 20, seed=19).tobytes()
+        g = ctx.compress(d, 0, 6)
+        for rep in range(3):
+            t = time.time()
+            g = ctx.compress(d, 0, 6)
+            t1 = time.time() - t
+        ctx.profile(True)
+        g = ctx.compress(d, 0, 6)
+        print("  32MiB L6 e2e: %.4fs (%.1f MB/s) phases %s" % (t1, len(d) / t1 / 1e6, {k: round(v[0], 3) for k, v in ctx.profile_read().items() if v[1]}))
+        ctx.profile(False)
+        for rep in range(2):
+            t = time.time()
+            p, _ = ctx.decompress(g, 0, cap=len(d) + 64)
+            t2 = time.time() - t
+        print("  32MiB single-member inflate: %.4fs (%.1f MB/s)" % (t2, len(d) / t2 / 1e6))
+    stage("timing", timing)
     print("launches", ctx.kernel_launches)
 
 
