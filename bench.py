@@ -190,20 +190,19 @@ def main():
     def device_step():
         return ctx.compress_device(d_in.data_ptr(), n, d_out.data_ptr(), cap, mode=level, stream=sp)
 
+    from flate_b200 import sharding
     gather_buf = None
     out_len = device_step()
     if world > 1:
         # per-shard outputs are all-gathered (north star); pad to a common size agreed on once
-        sizes = torch.tensor([out_len], device="cuda", dtype=torch.int64)
-        allsz = [torch.zeros_like(sizes) for _ in range(world)]
-        dist.all_gather(allsz, sizes)
-        pad = int(max(int(s.item()) for s in allsz) * 1.02) + 4096
+        allsz = sharding.all_gather_sizes(out_len, d_out.device)
+        pad = (int(max(allsz) * 1.02) + 4096) // 256 * 256
         gather_buf = torch.empty(world * pad, dtype=torch.uint8, device="cuda")
 
     def full_step():
         ln = device_step()
         if world > 1:
-            dist.all_gather_into_tensor(gather_buf, d_out[:pad])
+            sharding.all_gather_ragged(d_out, ln, pad_to=pad, out=gather_buf)
         return ln
 
     # ---- device-resident timing (value) ----

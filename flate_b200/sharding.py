@@ -1,0 +1,42 @@
+"""Host-side sharding of independent units (chunks, members, 65535-byte blocks) over ranks, and the
+all-gather of ragged per-shard outputs.  One process per GPU; torch.distributed is plumbing only.
+The deflate/inflate path has no data-path collective: units are independent."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_units, rank, world):
+    """Contiguous, balanced [lo, hi) of n_units for `rank` (first n_units % world ranks get one more)."""
+    base, extra = divmod(n_units, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_gather_sizes(size, device):
+    """Every rank's byte count, as a python list."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [int(size)]
+    t = torch.tensor([int(size)], dtype=torch.int64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [int(x.item()) for x in out]
+
+
+def all_gather_ragged(shard, size, pad_to=None, out=None):
+    """All-gather of per-shard outputs of different lengths.  `shard` is a uint8 tensor holding at
+    least `pad_to` bytes of which the first `size` are payload.  Returns (buffer, sizes, pad) where
+    rank r's payload is buffer[r*pad : r*pad + sizes[r]]."""
+    sizes = all_gather_sizes(size, shard.device)
+    world = len(sizes)
+    pad = pad_to if pad_to is not None else (max(sizes) + 255) // 256 * 256
+    if world == 1:
+        return shard[:pad], sizes, pad
+    if out is None:
+        out = torch.empty(world * pad, dtype=torch.uint8, device=shard.device)
+    dist.all_gather_into_tensor(out, shard[:pad].contiguous())
+    return out, sizes, pad
+
+
+def concat_ragged(buffer, sizes, pad):
+    """Byte-exact concatenation of the gathered payloads (host bytes)."""
+    return b"".join(buffer[r * pad: r * pad + sizes[r]].cpu().numpy().tobytes() for r in range(len(sizes)))
