@@ -14,74 +14,170 @@
 #include "common.cuh"
 #include "pipeline.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace fb {
 
 // ------------------------------------------------------------------------------------------
-// K1: hash links.  Lookup.zig:23-84.  One warp walks a run of tiles in position order; the
-// head table (hash -> most recent position + 1) lives in shared memory.  Within a group of 32
-// consecutive positions the predecessor is found with __match_any_sync; the last lane of each
-// hash group publishes the new head.  A warm-up tile primes the head table so runs are
-// independent (links farther than 32768 are dropped anyway, deflate.zig:250).
+// K1: hash links.  Lookup.zig:23-84.
+// "Previous position with the same hash" is an ordered-predecessor problem.  A block walks a run
+// of 8192-position tiles; inside a tile the 15-bit hash space is split over the block's 16 warps
+// (warp w owns hashes with top 4 bits == w), so 16 sequential chains advance in parallel:
+//   1. all threads hash the tile into shared memory (u16 per position, 0xFFFF = not insertable)
+//   2. every warp scans the tile's hashes in order (128 positions per step), compacts the positions
+//      it owns into a staging buffer, and resolves them 32 at a time: predecessor inside the group
+//      via __match_any_sync, otherwise from its slice of the head table; the last lane of each hash
+//      group publishes the new head
+//   3. links are collected in shared memory and flushed coalesced; the head table is rebased by one
+//      tile (the reference's Lookup.slide, Lookup.zig:43-51, is the same saturating subtract)
+// Head entries are u16 codes c = p - (tile_base - 32768) + 1 in [1, 40960], 0 = none.
+// Four warm-up tiles (32768 positions) prime the table so runs are independent (links farther than
+// 32768 are dropped anyway, deflate.zig:250).
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kLinkTile = 32768;
-constexpr uint32_t kLinkRun = 8;  // tiles per block (plus one warm-up tile)
+constexpr uint32_t kLinkTile = 8192;
+constexpr uint32_t kLinkWarm = kHist / kLinkTile;  // warm-up tiles
+constexpr uint32_t kLinkWarps = 16;
+constexpr uint32_t kLinkThreads = kLinkWarps * 32;
+constexpr uint32_t kLinkStage = 256;  // staging entries per warp
+constexpr uint32_t kLinkSmem = 32768 * 2 /*head*/ + kLinkTile * 2 /*hash*/ + kLinkTile * 2 /*link*/ +
+                               kLinkWarps * kLinkStage * 4;
 
-__device__ __forceinline__ uint32_t hash4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
-    uint32_t v = (b0 << 24) | (b1 << 16) | (b2 << 8) | b3;  // Lookup.zig:75-80 (big-endian read)
-    return (v * 0x9E3779B1u) >> 17;                       // Lookup.zig:12,82-84
+__device__ __forceinline__ uint32_t hash_be(uint32_t le32) {
+    // Lookup.zig:75-84: big-endian read of 4 bytes, times 0x9E3779B1, top 15 bits
+    return (__byte_perm(le32, 0, 0x0123) * 0x9E3779B1u) >> 17;
 }
 
-__global__ void __launch_bounds__(32, 1)
-hash_link_kernel(const uint8_t* __restrict__ in, uint32_t n, uint16_t* __restrict__ link) {
+__global__ void __launch_bounds__(kLinkThreads, 2)
+hash_link_kernel(const uint8_t* __restrict__ in, uint32_t n, uint32_t run, uint16_t* __restrict__ link) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint32_t* head = reinterpret_cast<uint32_t*>(smem_raw);             // 32768 * 4
-    uint8_t* bytes = smem_raw + 32768 * 4;                                // kLinkTile + 16
-    const uint32_t lane = threadIdx.x;
+    uint16_t* head = reinterpret_cast<uint16_t*>(smem_raw);
+    uint16_t* hs = head + 32768;
+    uint16_t* lk = hs + kLinkTile;
+    uint32_t* stage_all = reinterpret_cast<uint32_t*>(lk + kLinkTile);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t* stage = stage_all + w * kLinkStage;
+    const uint32_t ltmask = (1u << lane) - 1;
     const uint32_t ntiles = (n + kLinkTile - 1) / kLinkTile;
-    const uint32_t first = blockIdx.x * kLinkRun;
+    const uint32_t first = blockIdx.x * run;
     if (first >= ntiles) return;
-    const uint32_t last = min(first + kLinkRun, ntiles);
-    for (uint32_t i = lane; i < 32768; i += 32) head[i] = 0;
-    __syncwarp();
-    const uint32_t t0 = first > 0 ? first - 1 : 0;
+    const uint32_t last = min(first + run, ntiles);
+    for (uint32_t i = tid; i < 32768 / 2; i += kLinkThreads) reinterpret_cast<uint32_t*>(head)[i] = 0;
+    const uint32_t t0 = first > kLinkWarm ? first - kLinkWarm : 0;
+    const bool aligned = ((uintptr_t)in & 3) == 0;
     for (uint32_t t = t0; t < last; t++) {
         const bool emit = t >= first;
         const uint32_t base = t * kLinkTile;
         const uint32_t cnt = min(kLinkTile, n - base);
-        // stage the tile (+3 bytes look-ahead) in shared memory
-        const uint32_t need = min(cnt + 3, n - base);
-        if (((uintptr_t)(in + base) & 15) == 0) {
-            const uint4* src = reinterpret_cast<const uint4*>(in + base);
-            uint4* dst = reinterpret_cast<uint4*>(bytes);
-            const uint32_t nv = need / 16;
-            for (uint32_t i = lane; i < nv; i += 32) dst[i] = src[i];
-            for (uint32_t i = nv * 16 + lane; i < need; i += 32) bytes[i] = in[base + i];
-        } else {
-            for (uint32_t i = lane; i < need; i += 32) bytes[i] = in[base + i];
-        }
-        __syncwarp();
-        for (uint32_t it = 0; it < cnt; it += 32) {
-            const uint32_t off = it + lane;
-            const uint32_t p = base + off;
-            const bool valid = off < cnt && (uint64_t)p + 4 <= n;  // Lookup.zig:24 needs 4 bytes
-            uint32_t h = 0x10000u | lane;                          // unique key for idle lanes
-            if (valid) h = hash4(bytes[off], bytes[off + 1], bytes[off + 2], bytes[off + 3]);
-            const uint32_t peers = __match_any_sync(0xffffffffu, h);
-            uint32_t lnk = 0;
-            if (valid) {
-                const uint32_t lower = peers & ((1u << lane) - 1);
-                uint32_t q1;  // previous position + 1, 0 = none
-                if (lower) q1 = base + it + (31 - __clz(lower)) + 1;
-                else q1 = head[h];
-                if (q1 != 0) {
-                    const uint32_t d = p + 1 - q1;
-                    if (d <= kMaxDist) lnk = d;
+        // ---- 1. hashes of the tile ----
+        if (aligned) {
+            const uint32_t* words = reinterpret_cast<const uint32_t*>(in + base);
+            const uint32_t nwords_total = (n - base + 3) / 4;  // readable words from base
+            for (uint32_t i = tid; i < kLinkTile / 4; i += kLinkThreads) {
+                uint32_t w0 = 0, w1 = 0;
+                if (i < nwords_total) w0 = words[i];
+                if (i + 1 < nwords_total) w1 = words[i + 1];
+                uint32_t hh[4];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++) {
+                    const uint32_t off = i * 4 + k;
+                    const bool valid = off < cnt && (uint64_t)base + off + 4 <= n;  // Lookup.zig:24 needs 4 bytes
+                    hh[k] = valid ? hash_be(__funnelshift_r(w0, w1, 8 * k)) : 0xFFFFu;
                 }
-                if ((peers >> lane) == 1u) head[h] = p + 1;  // highest lane of the hash group
+                reinterpret_cast<uint2*>(hs)[i] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
             }
-            if (emit && off < cnt) link[p] = (uint16_t)lnk;  // 32768 wraps to 0x8000, fits
-            __syncwarp();
+        } else {
+            for (uint32_t off = tid; off < kLinkTile; off += kLinkThreads) {
+                uint32_t h = 0xFFFFu;
+                if (off < cnt && (uint64_t)base + off + 4 <= n) {
+                    const uint8_t* b = in + base + off;
+                    h = hash_be((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
+                }
+                hs[off] = (uint16_t)h;
+            }
         }
+        __syncthreads();
+        // ---- 2. per-warp ordered scan of the owned hash slice ----
+        {
+            uint32_t fill = 0;
+            constexpr uint32_t kSteps = kLinkTile / 128;
+            for (uint32_t g = 0; g <= kSteps; g++) {
+                if (g < kSteps) {
+                    // lane L holds positions 128 g + 4 L .. + 3 (ascending order = lane-major, then j)
+                    const uint2 v = reinterpret_cast<const uint2*>(hs)[g * 32 + lane];
+                    const uint32_t h0 = v.x & 0xffffu, h1 = v.x >> 16, h2 = v.y & 0xffffu, h3 = v.y >> 16;
+                    const bool m0 = (h0 >> 11) == w, m1 = (h1 >> 11) == w, m2 = (h2 >> 11) == w, m3 = (h3 >> 11) == w;
+                    const uint32_t mine = (uint32_t)m0 + m1 + m2 + m3;
+                    // exclusive prefix of `mine` over lanes
+                    uint32_t incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= (uint32_t)o) incl += y;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    uint32_t at = fill + incl - mine;
+                    const uint32_t off0 = g * 128 + lane * 4;
+                    if (m0) stage[at++] = (off0 << 16) | h0;
+                    if (m1) stage[at++] = ((off0 + 1) << 16) | h1;
+                    if (m2) stage[at++] = ((off0 + 2) << 16) | h2;
+                    if (m3) stage[at++] = ((off0 + 3) << 16) | h3;
+                    fill += total;
+                    __syncwarp();
+                    if (fill + 128 <= kLinkStage && g + 1 < kSteps) continue;  // room for another step: keep scanning
+                }
+                // resolve everything staged so far, 32 entries per step, in order
+                for (uint32_t sidx = 0; sidx < fill; sidx += 32) {
+                    uint32_t h = 0x10000u | lane, off = 0;  // unique key for idle lanes
+                    const bool have = sidx + lane < fill;
+                    if (have) {
+                        const uint32_t ent = stage[sidx + lane];
+                        off = ent >> 16;
+                        h = ent & 0xffffu;
+                    }
+                    const uint32_t peers = __match_any_sync(0xffffffffu, h);
+                    const uint32_t lower = peers & ltmask;
+                    const uint32_t src = lower ? 31 - __clz(lower) : lane;
+                    const uint32_t off_prev = __shfl_sync(0xffffffffu, off, src);
+                    if (have) {
+                        uint32_t d = 0;
+                        if (lower) {
+                            d = off - off_prev;  // same tile
+                        } else {
+                            const uint32_t e = head[h];
+                            if (e) {
+                                d = off + (kHist + 1) - e;
+                                if (d > kMaxDist) d = 0;
+                            }
+                        }
+                        if ((peers >> lane) == 1u) head[h] = (uint16_t)(off + kHist + 1);
+                        if (emit) lk[off] = (uint16_t)d;
+                    }
+                    __syncwarp();
+                }
+                fill = 0;
+            }
+        }
+        __syncthreads();
+        // ---- 3. flush links, rebase the head table by one tile ----
+        if (emit) {
+            // positions that cannot be inserted (fewer than 4 bytes left) have no link
+            for (uint32_t i = tid; i < cnt; i += kLinkThreads)
+                if (hs[i] == 0xFFFFu) lk[i] = 0;
+            __syncthreads();
+            uint16_t* dst = link + base;
+            const uint32_t nv = cnt / 8;
+            for (uint32_t i = tid; i < nv; i += kLinkThreads) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(lk)[i];
+            for (uint32_t i = nv * 8 + tid; i < cnt; i += kLinkThreads) dst[i] = lk[i];
+        }
+        if (t + 1 < last) {
+            for (uint32_t i = tid; i < 32768 / 2; i += kLinkThreads) {
+                const uint32_t v = reinterpret_cast<uint32_t*>(head)[i];
+                const uint32_t lo = v & 0xffffu, hi = v >> 16;
+                reinterpret_cast<uint32_t*>(head)[i] = (lo > kLinkTile ? lo - kLinkTile : 0u) | ((hi > kLinkTile ? hi - kLinkTile : 0u) << 16);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -95,8 +191,9 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t n, uint16_t* __restric
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kSearchTile = 4096;
 constexpr uint32_t kSearchThreads = 512;
-constexpr uint32_t kSearchBytes = kHist + kSearchTile + 272;   // window + look-ahead, 16B multiple
-constexpr uint32_t kSearchLinks = kHist + kSearchTile;
+constexpr uint32_t kSearchOff = 16;                                          // index shift: slot 0 means "none"
+constexpr uint32_t kSearchBytes = kSearchOff + kHist + kSearchTile + 272;   // window + look-ahead, 16B multiple
+constexpr uint32_t kSearchLinks = kSearchOff + kHist + kSearchTile;
 constexpr uint32_t kSearchSmem = kSearchBytes + kSearchLinks * 2;
 
 // unaligned 4-byte little-endian load from shared memory (two aligned words + funnel shift)
@@ -105,91 +202,208 @@ __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t* base, uint3
     return __funnelshift_r(w[0], w[1], (idx & 3) * 8);
 }
 
+__device__ __forceinline__ uint32_t lds_shared_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_shared_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+struct SearchTune {
+    uint32_t pend_at;    // run the batched full compares once this many lanes wait for one
+    uint32_t refill_at;  // re-arm finished lanes once this many are idle
+};
+
+// Lane states of the walk
+enum : uint32_t { kIdle = 0, kStepping = 1, kPending = 2, kDone = 3 };
+
+template <int kStepsPerRound>
 __global__ void __launch_bounds__(kSearchThreads, 2)
 match_search_kernel(const uint8_t* __restrict__ in, uint32_t n, const uint16_t* __restrict__ link,
-                    LevelArgs lv, uint32_t* __restrict__ r_full, uint32_t* __restrict__ r_quarter) {
+                    LevelArgs lv, SearchTune tune, uint32_t* __restrict__ r_full, uint32_t* __restrict__ r_quarter) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    uint8_t* sb = smem_raw;                                                 // bytes
-    uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + kSearchBytes);    // links
+    __shared__ uint32_t tile_next;
+    uint8_t* sb = smem_raw;                                                 // bytes, slot i+16 = position wb+i
+    uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + kSearchBytes);    // slot of the previous same-hash position, 0 = none
     const uint32_t s = blockIdx.x * kSearchTile;                            // first new position
     const int64_t wb = (int64_t)s - kHist;                                  // window base (may be < 0)
-    const uint32_t lo = wb < 0 ? (uint32_t)(-wb) : 0;                       // first valid smem index
+    const uint32_t lo = wb < 0 ? (uint32_t)(-wb) : 0;                       // first valid window index
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ltmask = (1u << lane) - 1;
 
-    // ---- stage window ----
+    // ---- stage window: bytes verbatim, links converted from distances to slots ----
     {
-        const uint32_t byte_hi = (uint32_t)min((int64_t)kSearchBytes, (int64_t)n - wb);  // exclusive
-        // 16-byte vector body (wb is a multiple of 4096, input assumed 16B aligned) + scalar tail
-        const bool aligned = ((uintptr_t)in & 15) == 0;
+        const uint32_t byte_hi = (uint32_t)min((int64_t)(kSearchBytes - kSearchOff), (int64_t)n - wb);  // exclusive
+        const bool aligned = ((uintptr_t)in & 15) == 0;  // wb is a multiple of 4096
         const uint32_t v_lo = lo / 16, v_hi = aligned ? byte_hi / 16 : v_lo;
         const uint4* src = reinterpret_cast<const uint4*>(in + wb);
-        uint4* dst = reinterpret_cast<uint4*>(sb);
+        uint4* dst = reinterpret_cast<uint4*>(sb + kSearchOff);
         for (uint32_t i = v_lo + threadIdx.x; i < v_hi; i += kSearchThreads) dst[i] = src[i];
-        for (uint32_t i = max(lo, v_hi * 16) + threadIdx.x; i < byte_hi; i += kSearchThreads) sb[i] = in[wb + i];
-        for (uint32_t i = byte_hi + threadIdx.x; i < kSearchBytes; i += kSearchThreads) sb[i] = 0;
-        const uint32_t link_hi = (uint32_t)min((int64_t)kSearchLinks, (int64_t)n - wb);
+        for (uint32_t i = max(lo, v_hi * 16) + threadIdx.x; i < byte_hi; i += kSearchThreads) sb[kSearchOff + i] = in[wb + i];
+        for (uint32_t i = byte_hi + threadIdx.x; i < kSearchBytes - kSearchOff; i += kSearchThreads) sb[kSearchOff + i] = 0;
+        const uint32_t link_hi = (uint32_t)min((int64_t)(kSearchLinks - kSearchOff), (int64_t)n - wb);
         const uint32_t lv_lo = lo / 8, lv_hi = link_hi / 8;
         const uint4* lsrc = reinterpret_cast<const uint4*>(link + wb);
-        uint4* ldst = reinterpret_cast<uint4*>(sl);
-        for (uint32_t i = lv_lo + threadIdx.x; i < lv_hi; i += kSearchThreads) ldst[i] = lsrc[i];
-        for (uint32_t i = max(lo, lv_hi * 8) + threadIdx.x; i < link_hi; i += kSearchThreads) sl[i] = link[wb + i];
+        for (uint32_t i = lv_lo + threadIdx.x; i < lv_hi; i += kSearchThreads) {
+            const uint4 v = lsrc[i];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t slot0 = kSearchOff + i * 8 + 2 * k, slot1 = slot0 + 1;
+                const uint32_t l0 = w[k] & 0xffffu, l1 = w[k] >> 16;
+                // a link that leaves the window is farther than 32768 from every tile position: none
+                const uint32_t t0 = (l0 && l0 + kSearchOff <= slot0) ? slot0 - l0 : 0;
+                const uint32_t t1 = (l1 && l1 + kSearchOff <= slot1) ? slot1 - l1 : 0;
+                o[k] = t0 | (t1 << 16);
+            }
+            reinterpret_cast<uint4*>(sl + kSearchOff)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        for (uint32_t i = max(lo, lv_hi * 8) + threadIdx.x; i < link_hi; i += kSearchThreads) {
+            const uint32_t l = link[wb + i], slot = kSearchOff + i;
+            sl[slot] = (uint16_t)((l && l + kSearchOff <= slot) ? slot - l : 0);
+        }
+        if (threadIdx.x == 0) tile_next = kSearchThreads;  // the first kSearchThreads positions are pre-assigned
     }
     __syncthreads();
 
+    const uint32_t tile_cnt = min(kSearchTile, n - s);  // positions of this tile that exist
     const uint32_t quarter = lv.chain >> 2;
-    for (uint32_t k = threadIdx.x; k < kSearchTile; k += kSearchThreads) {
+    // 32-bit shared-window addresses: explicit ld.shared keeps the address arithmetic out of the hot loop
+    uint32_t sb_addr = (uint32_t)__cvta_generic_to_shared(sb);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sb_addr));  // opaque: keep it in a register instead of rematerialising it per step
+    const uint32_t sl_addr = sb_addr + kSearchBytes;
+
+    // Per-lane walk state.  The warp alternates between
+    //   phase A: kStepsPerRound chain steps for every stepping lane (link load + one-byte reject test)
+    //   phase B: the full compares of all pending lanes together
+    // and re-arms finished lanes in batches from a tile-wide counter, so all phases run with many
+    // lanes busy although chain lengths differ wildly between neighbouring positions.
+    // `left` = candidates this lane may still visit before its next budget event; 0 whenever the lane
+    // is not stepping, so the step guard is a single test.
+    uint32_t st = kIdle, left = 0, saved = 0;
+    uint32_t pi = 0, qi = 0, lim = 0, best_len = 0, best_dist = 0, snap = 0, ro_addr = 0, cb = 0, first4 = 0, max_len = 0;
+    bool snapped = false;
+
+    auto arm = [&](uint32_t k) {  // start the walk of tile position k (deflate.zig:233-245)
+        if (k >= tile_cnt) return;
         const uint32_t p = s + k;
-        if (p >= n) break;
-        uint32_t best_len = 0, best_dist = 0, snap = 0;
-        bool snapped = false;
         const uint32_t remaining = n - p;
-        if (remaining >= kMinMatch) {  // Lookup.zig:24: no insertion / search with < 4 bytes left
-            const uint32_t max_len = min(remaining, kMaxMatch);  // SlidingWindow.zig:82
-            const uint32_t base = slide_base(p, n);
-            const uint32_t pi = p - (uint32_t)wb;  // smem index of p  (wb <= p always)
-            const uint32_t first4 = lds_u32_unaligned(sb, pi);
-            uint32_t qi = pi;
-            uint32_t cnt = 0;
-            while (true) {  // deflate.zig:248 "Hot path loop!"
-                const uint32_t l = sl[qi];
-                if (l == 0) break;
-                qi -= l;
-                const uint32_t dist = pi - qi;
-                const int64_t q = wb + qi;
-                if (dist > kMaxDist || q <= (int64_t)base) break;  // deflate.zig:250, :248 (pos 0 = none)
-                cnt++;
-                // ---- SlidingWindow.match with the running best as min_len ----
-                // a candidate only matters if it is strictly longer than best_len, i.e. bytes
-                // [0, best_len] all agree; test the first word and the byte at best_len first.
-                if (lds_u32_unaligned(sb, qi) == first4 && (best_len == 0 || sb[qi + best_len] == sb[pi + best_len])) {
-                    uint32_t i = 4;
-                    while (i < max_len) {
-                        const uint32_t x = lds_u32_unaligned(sb, qi + i) ^ lds_u32_unaligned(sb, pi + i);
-                        if (x) {
-                            i += (__ffs(x) - 1) >> 3;
-                            break;
-                        }
-                        i += 4;
-                    }
-                    if (i > max_len) i = max_len;
-                    if (i > best_len) {
-                        best_len = i;
-                        best_dist = dist;
-                        if (i >= lv.nice) break;    // deflate.zig:256-259
-                        if (i >= max_len) {          // nothing can be strictly longer: the rest of the
-                            break;                   // walk cannot change either result
-                        }
-                    }
+        pi = kSearchOff + kHist + k;          // slot of p
+        best_len = 0;
+        best_dist = 0;
+        snapped = false;
+        snap = 0;
+        if (remaining < kMinMatch) {  // Lookup.zig:24: no insertion / search with < 4 bytes left
+            st = kDone;
+            return;
+        }
+        max_len = min(remaining, kMaxMatch);  // SlidingWindow.zig:82
+        qi = pi;
+        // candidates must satisfy  p - q <= 32768 (deflate.zig:250)  and  q > slide base (:248, pos 0 = none)
+        const int64_t base_slot = (int64_t)slide_base(p, n) - wb + kSearchOff;
+        lim = (uint32_t)max((int64_t)pi - (int64_t)kMaxDist, base_slot + 1);
+        left = quarter;  // first budget event: the quarter snapshot (deflate.zig:241-245)
+        first4 = lds_u32_unaligned(sb, pi);
+        ro_addr = sb_addr + 3;  // a useful candidate agrees on byte `ro` = max(best_len, 3)
+        cb = sb[pi + 3];
+        st = kStepping;
+    };
+    // budget events (deflate.zig:241-248): after chain>>2 candidates the quarter-budget result is
+    // snapshotted, after `chain` candidates the walk ends
+    auto event = [&]() {
+        if (!snapped) {
+            snap = best_len ? pack_match(best_len, best_dist) : 0;
+            snapped = true;
+            left = lv.chain - quarter;
+        } else {
+            st = kDone;
+        }
+    };
+
+    arm(threadIdx.x);
+    bool exhausted = false;  // warp-uniform: the tile has no unassigned position left
+    while (true) {
+        // ---- phase A: chain steps (deflate.zig:248 "Hot path loop!") ----
+#pragma unroll
+        for (int u = 0; u < kStepsPerRound; u++) {
+            if (left) {
+                qi = lds_shared_u16(sl_addr + 2 * qi);
+                if (qi < lim) {  // end of chain, too far, or at/below the slide base
+                    st = kDone;
+                    left = 0;
+                } else if (lds_shared_u8(ro_addr + qi) == cb) {  // may beat the best so far: needs the full compare
+                    st = kPending;
+                    saved = left;
+                    left = 0;
+                } else {
+                    left--;
                 }
-                if (cnt == quarter) {
-                    snap = best_len ? pack_match(best_len, best_dist) : 0;
-                    snapped = true;
-                }
-                if (cnt >= lv.chain) break;
             }
         }
-        const uint32_t full = best_len ? pack_match(best_len, best_dist) : 0;
-        r_full[p] = full;
-        r_quarter[p] = snapped ? snap : full;
+        if (st == kStepping && left == 0) event();
+        // ---- phase B: full compares (SlidingWindow.match with the running best as min_len) ----
+        const uint32_t pend = __ballot_sync(0xffffffffu, st == kPending);
+        if (pend) {
+            const uint32_t stepping = __ballot_sync(0xffffffffu, st == kStepping);
+            if (__popc(pend) >= tune.pend_at || stepping == 0) {
+                if (st == kPending) {
+                    st = kStepping;
+                    left = saved - 1;  // this candidate is paid for either way
+                    if (lds_u32_unaligned(sb, qi) == first4) {
+                        uint32_t i = 4;
+                        while (i < max_len) {
+                            const uint32_t x = lds_u32_unaligned(sb, qi + i) ^ lds_u32_unaligned(sb, pi + i);
+                            if (x) {
+                                i += (__ffs(x) - 1) >> 3;
+                                break;
+                            }
+                            i += 4;
+                        }
+                        if (i > max_len) i = max_len;
+                        if (i > best_len) {
+                            best_len = i;
+                            best_dist = pi - qi;
+                            // deflate.zig:256-259 nice; or nothing can be strictly longer: neither result can change
+                            if (i >= lv.nice || i >= max_len) {
+                                st = kDone;
+                                left = 0;
+                            } else {
+                                ro_addr = sb_addr + i;
+                                cb = sb[pi + i];
+                            }
+                        }
+                    }
+                    if (st == kStepping && left == 0) event();
+                }
+            }
+        }
+        // ---- results of finished lanes, re-arm ----
+        const uint32_t idle = __ballot_sync(0xffffffffu, st == kIdle || st == kDone);
+        if (idle) {
+            const uint32_t nidle = __popc(idle);
+            if ((!exhausted && nidle >= tune.refill_at) || idle == 0xffffffffu) {
+                if (st == kDone) {
+                    const uint32_t p = (uint32_t)(wb + (int64_t)(pi - kSearchOff));
+                    const uint32_t full = best_len ? pack_match(best_len, best_dist) : 0;
+                    r_full[p] = full;
+                    r_quarter[p] = snapped ? snap : full;
+                    st = kIdle;
+                }
+                if (!exhausted) {
+                    uint32_t base_k = 0;
+                    if (lane == 0) base_k = atomicAdd(&tile_next, nidle);
+                    base_k = __shfl_sync(0xffffffffu, base_k, 0);
+                    if (base_k >= tile_cnt) exhausted = true;
+                    else if (st == kIdle) arm(base_k + __popc(idle & ltmask));
+                }
+                if (exhausted && __ballot_sync(0xffffffffu, st != kIdle) == 0) break;
+            }
+        }
     }
 }
 
@@ -429,8 +643,11 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n,
     if (!pt) pt = &dummy;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(hash_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4 + kLinkTile + 16);
-        cudaFuncSetAttribute(match_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
+        cudaFuncSetAttribute(hash_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinkSmem);
+        cudaFuncSetAttribute(match_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
+        cudaFuncSetAttribute(match_search_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
+        cudaFuncSetAttribute(match_search_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
+        cudaFuncSetAttribute(match_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
         attr_set = true;
     }
     if (n == 0) {
@@ -438,10 +655,32 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n,
         return cudaGetLastError();
     }
     const uint32_t ntiles = (n + kLinkTile - 1) / kLinkTile;
-    hash_link_kernel<<<(ntiles + kLinkRun - 1) / kLinkRun, 32, 32768 * 4 + kLinkTile + 16, st>>>(d_in, n, b.link);
+    // run length: long enough to amortise the 4 warm-up tiles, short enough to fill the GPU
+    const uint32_t run = ntiles >= 32 * 600 ? 32 : ntiles >= 8 * 600 ? 16 : 8;
+    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, n, run, b.link);
     pt->mark(st, kPhLink);
-    match_search_kernel<<<(n + kSearchTile - 1) / kSearchTile, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv,
-                                                                                                b.r_full, b.r_quarter);
+    {
+        // development knob: FB200_TUNE="steps,pend_at,refill_at"
+        static int steps = 8;
+        static SearchTune tune{4, 8};
+        static bool tune_read = false;
+        if (!tune_read) {
+            tune_read = true;
+            if (const char* e = getenv("FB200_TUNE")) {
+                int a = 0, p = 0, r = 0;
+                if (sscanf(e, "%d,%d,%d", &a, &p, &r) == 3) {
+                    steps = a;
+                    tune.pend_at = (uint32_t)p;
+                    tune.refill_at = (uint32_t)r;
+                }
+            }
+        }
+        const uint32_t grid = (n + kSearchTile - 1) / kSearchTile;
+        if (steps == 2) match_search_kernel<2><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv, tune, b.r_full, b.r_quarter);
+        else if (steps == 16) match_search_kernel<16><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv, tune, b.r_full, b.r_quarter);
+        else if (steps == 8) match_search_kernel<8><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv, tune, b.r_full, b.r_quarter);
+        else match_search_kernel<4><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv, tune, b.r_full, b.r_quarter);
+    }
     pt->mark(st, kPhSearch);
     lazy_step_kernel<<<(n + 255) / 256, 256, 0, st>>>(b.r_full, b.r_quarter, n, lv, b.nx);
     pt->mark(st, kPhLazy);
