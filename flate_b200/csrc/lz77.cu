@@ -662,7 +662,7 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n,
     {
         // development knob: FB200_TUNE="steps,pend_at,refill_at"
         static int steps = 8;
-        static SearchTune tune{4, 8};
+        static SearchTune tune{3, 8};
         static bool tune_read = false;
         if (!tune_read) {
             tune_read = true;
