@@ -18,7 +18,7 @@ __constant__ uint8_t c_codegen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11
 // candidate is the reference's window[fp .. rp) at the moment of the cut.
 // ------------------------------------------------------------------------------------------
 __global__ void plan_level_blocks_kernel(const uint32_t* __restrict__ total_tokens, const uint32_t* __restrict__ cut_rp,
-                                         uint32_t n, uint32_t max_blocks, uint32_t final_flush, BlockPlan* __restrict__ plans,
+                                         uint32_t begin, uint32_t n, uint32_t max_blocks, uint32_t final_flush, BlockPlan* __restrict__ plans,
                                          uint32_t* __restrict__ nblocks_out) {
     const uint32_t T = *total_tokens;
     const uint32_t ntok_blocks = T / kTokensPerBlock + 1;  // last one may be empty (deflate.zig:227-230,344)
@@ -30,8 +30,9 @@ __global__ void plan_level_blocks_kernel(const uint32_t* __restrict__ total_toke
     if (b < ntok_blocks) {
         pl.tok_begin = b * kTokensPerBlock;
         pl.tok_count = min(kTokensPerBlock, T - pl.tok_begin);
-        const uint32_t rp = (b + 1 < ntok_blocks) ? cut_rp[b] : n;
-        const uint32_t fp = b == 0 ? 0 : cut_rp[b - 1];
+        // cut_rp is relative to the segment start; fp after a flush is the flush point (SlidingWindow.zig:113)
+        const uint32_t rp = (b + 1 < ntok_blocks) ? begin + cut_rp[b] : n;
+        const uint32_t fp = b == 0 ? begin : begin + cut_rp[b - 1];
         pl.in_begin = fp;
         pl.in_len = rp - fp;
         pl.has_input = fp >= slide_base(rp, n);  // fp < 0 after a slide => null (SlidingWindow.zig:121)
@@ -661,9 +662,9 @@ pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-cudaError_t plan_level_blocks(const uint32_t* total_tokens, const uint32_t* cut_rp, uint32_t n, uint32_t max_blocks,
-                              uint32_t final_flush, BlockPlan* plans, uint32_t* nblocks, cudaStream_t st) {
-    plan_level_blocks_kernel<<<(max_blocks + 127) / 128, 128, 0, st>>>(total_tokens, cut_rp, n, max_blocks, final_flush,
+cudaError_t plan_level_blocks(const uint32_t* total_tokens, const uint32_t* cut_rp, uint32_t begin, uint32_t n,
+                              uint32_t max_blocks, uint32_t final_flush, BlockPlan* plans, uint32_t* nblocks, cudaStream_t st) {
+    plan_level_blocks_kernel<<<(max_blocks + 127) / 128, 128, 0, st>>>(total_tokens, cut_rp, begin, n, max_blocks, final_flush,
                                                                        plans, nblocks);
     return cudaGetLastError();
 }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/flate_b200.h"
@@ -19,20 +20,30 @@ void set_last_cuda_error(cudaError_t e, const char* file, int line) {
     snprintf(g_cuda_err, sizeof g_cuda_err, "%s (%s:%d)", cudaGetErrorString(e), file, line);
 }
 
-__global__ void plan_simple_blocks_kernel(uint64_t n, uint32_t nblocks, uint32_t kind, BlockPlan* __restrict__ plans,
-                                          uint32_t* __restrict__ nblocks_dev) {
+__global__ void plan_simple_blocks_kernel(uint64_t begin, uint64_t end, uint32_t nblocks, uint32_t kind, uint32_t final_flush,
+                                          BlockPlan* __restrict__ plans, uint32_t* __restrict__ nblocks_dev) {
+    // SimpleCompressor (deflate.zig:449-529): the segment is cut into 65535-byte slices, the last
+    // (possibly empty) one closes the segment; a sync flush appends an empty stored block (:474-478).
+    const uint32_t total = nblocks + (final_flush ? 0 : 1);
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0) *nblocks_dev = nblocks;
-    if (b >= nblocks) return;
+    if (b == 0) *nblocks_dev = total;
+    if (b >= total) return;
     BlockPlan pl;
     pl.tok_begin = 0;
     pl.tok_count = 0;
-    pl.in_begin = (uint64_t)b * kMaxStore;  // deflate.zig:456: 65535-byte slices
-    const uint64_t rem = n - pl.in_begin;
-    pl.in_len = (uint32_t)(rem < kMaxStore ? rem : kMaxStore);
     pl.has_input = 1;
-    pl.eof = b + 1 == nblocks;
-    pl.kind = kind;
+    if (b < nblocks) {
+        pl.in_begin = begin + (uint64_t)b * kMaxStore;  // deflate.zig:456: 65535-byte slices
+        const uint64_t rem = end - pl.in_begin;
+        pl.in_len = (uint32_t)(rem < kMaxStore ? rem : kMaxStore);
+        pl.eof = (b + 1 == nblocks) && final_flush;
+        pl.kind = kind;
+    } else {
+        pl.in_begin = 0;
+        pl.in_len = 0;
+        pl.eof = 0;
+        pl.kind = 3;
+    }
     plans[b] = pl;
 }
 
@@ -144,7 +155,7 @@ int fb200_ctx_create(int device, fb200_ctx** out) {
     if (!c) return FB200_INVALID_ARGUMENT;
     c->device = device;
     FB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    FB_CUDA_CHECK(cudaMalloc(&c->d_scalars, 64));
+    FB_CUDA_CHECK(cudaMalloc(&c->d_scalars, 128));
     FB_CUDA_CHECK(cudaMallocHost(&c->h_scalars, 64));
     *out = c;
     return FB200_OK;
@@ -212,12 +223,17 @@ static const uint8_t kZlibHeader[2] = {0x78, 0x9c};                             
 static inline size_t header_size(int container) { return container == FB200_GZIP ? 10 : container == FB200_ZLIB ? 2 : 0; }
 static inline size_t footer_size(int container) { return container == FB200_GZIP ? 8 : container == FB200_ZLIB ? 4 : 0; }
 
-// Runs the deflate body on the device: d_out[hdr .. hdr+body) ; returns body end (bytes from d_out start)
-static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint8_t* d_in, size_t n, uint8_t* d_out,
-                               size_t cap, size_t* end_bytes, bool final_flush, cudaStream_t st) {
-    if (container < 0 || container > 2) return FB200_INVALID_ARGUMENT;
+// Runs the deflate body of stream positions [begin, n) on the device.  One-shot calls pass begin = 0
+// and get the container header in front; the streaming compressor passes the flush point and gets
+// just the blocks of the segment (plus the sync marker when !final_flush).  Returns the end of the
+// written bytes (from d_out start).  The checksum of d_in[0..n) is left in c->h_scalars[1].
+static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint8_t* d_in, size_t begin, size_t n,
+                               const uint32_t* d_skip, uint32_t nskip, uint8_t* d_out, size_t cap, size_t* end_bytes,
+                               bool final_flush, bool with_header, cudaStream_t st) {
+    if (container < 0 || container > 2 || begin > n) return FB200_INVALID_ARGUMENT;
     if (((uintptr_t)d_out & 15) != 0) return FB200_INVALID_ARGUMENT;
-    const size_t bound = fb200_compress_bound(n, mode) + header_size(container) + footer_size(container);
+    const size_t hdr = with_header ? header_size(container) : 0;
+    const size_t bound = fb200_compress_bound(n - begin, mode) + header_size(container) + footer_size(container);
     if (cap < bound) return FB200_NO_SPACE_LEFT;
     uint32_t* nblocks_dev = c->d_scalars + 1;
     uint64_t* total_bits_dev = reinterpret_cast<uint64_t*>(c->d_scalars + 2);
@@ -228,28 +244,29 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         if (n > (1ull << 31)) return FB200_INVALID_ARGUMENT;  // single-stream position space is 32-bit
         int rc = ensure_lz77(c, n);
         if (rc) return rc;
-        max_blocks = (uint32_t)(n / kTokensPerBlock + 3);
+        max_blocks = (uint32_t)((n - begin) / kTokensPerBlock + 3);
         if ((rc = ensure_blocks(c, max_blocks))) return rc;
         Lz77Buffers b = lz77_view(c);
         c->timer.begin(st);
-        FB_CUDA_CHECK(lz77_tokenize(b, d_in, (uint32_t)n, lv, st, &c->timer));
-        c->launches += n ? 10 : 0;
-        FB_CUDA_CHECK(plan_level_blocks(b.total_tokens, b.cut_rp, (uint32_t)n, max_blocks, final_flush ? 1 : 0, c->plans.p,
-                                        nblocks_dev, st));
+        FB_CUDA_CHECK(lz77_tokenize(b, d_in, (uint32_t)begin, (uint32_t)n, d_skip, nskip, lv, st, &c->timer));
+        c->launches += n > begin ? 10 : 0;
+        FB_CUDA_CHECK(plan_level_blocks(b.total_tokens, b.cut_rp, (uint32_t)begin, (uint32_t)n, max_blocks,
+                                        final_flush ? 1 : 0, c->plans.p, nblocks_dev, st));
         FB_CUDA_CHECK(histogram_tokens(b.tokens, c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, st));
         c->launches += 2;
         c->timer.mark(st, kPhHist);
         tokens = b.tokens;
     } else if (mode == FB200_MODE_HUFFMAN || mode == FB200_MODE_STORE) {
-        const uint64_t nb64 = n / kMaxStore + 1;
-        if (nb64 > 0x7fffffffull) return FB200_INVALID_ARGUMENT;
-        max_blocks = (uint32_t)nb64;
+        const uint64_t nb64 = (n - begin) / kMaxStore + 1;
+        if (nb64 > 0x7ffffff0ull) return FB200_INVALID_ARGUMENT;
+        const uint32_t nslices = (uint32_t)nb64;
+        max_blocks = nslices + (final_flush ? 0 : 1);
         int rc = ensure_blocks(c, max_blocks);
         if (rc) return rc;
         c->timer.begin(st);
-        plan_simple_blocks_kernel<<<(max_blocks + 255) / 256, 256, 0, st>>>(n, max_blocks,
+        plan_simple_blocks_kernel<<<(max_blocks + 255) / 256, 256, 0, st>>>(begin, n, nslices,
                                                                             mode == FB200_MODE_HUFFMAN ? kHuffmanBlock : 3u,
-                                                                            c->plans.p, nblocks_dev);
+                                                                            final_flush ? 1 : 0, c->plans.p, nblocks_dev);
         FB_CUDA_CHECK(cudaGetLastError());
         c->launches += 1;
         if (mode == FB200_MODE_HUFFMAN) {
@@ -262,15 +279,27 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     }
     FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, c->descs.p, st));
     c->timer.mark(st, kPhBuild);
-    FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, header_size(container) * 8, total_bits_dev, st));
+    FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, hdr * 8, total_bits_dev, st));
     zero_output_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<uint32_t*>(d_out), total_bits_dev, cap / 4);
     FB_CUDA_CHECK(cudaGetLastError());
-    if (container == FB200_GZIP) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kGzipHeader, 10, cudaMemcpyHostToDevice, st));
-    if (container == FB200_ZLIB) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kZlibHeader, 2, cudaMemcpyHostToDevice, st));
+    if (hdr && container == FB200_GZIP) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kGzipHeader, 10, cudaMemcpyHostToDevice, st));
+    if (hdr && container == FB200_ZLIB) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kZlibHeader, 2, cudaMemcpyHostToDevice, st));
     c->timer.mark(st, kPhOffsets);
     FB_CUDA_CHECK(pack_blocks(d_in, tokens, c->descs.p, nblocks_dev, max_blocks, reinterpret_cast<uint32_t*>(d_out), st));
     c->timer.mark(st, kPhPack);
     c->launches += 4;
+    // container checksum of the plain bytes on the device (container.zig:168-206), SURVEY.md §8(f) rank 1
+    uint32_t* sum_dev = c->d_scalars + 4;
+    if (!final_flush) {
+        // the footer is only written by finish()
+    } else if (container == FB200_GZIP) {
+        FB_CUDA_CHECK(crc32_device(d_in, n, sum_dev, st));
+        c->launches += n ? 1 : 0;
+    } else if (container == FB200_ZLIB) {
+        FB_CUDA_CHECK(adler32_device(d_in, n, sum_dev, reinterpret_cast<uint64_t*>(c->d_scalars + 8), st));
+        c->launches += n ? 2 : 1;
+    }
+    if (container != FB200_RAW && final_flush) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 1, sum_dev, 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
     c->timer.collect();
@@ -278,57 +307,15 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     return FB200_OK;
 }
 
-// host-side checksums for the container footer (container.zig:85-109).  The device path for
-// these is SURVEY.md §8(f) rank 1; the footer is 8 bytes of framing outside the hot path.
-static uint32_t crc32_host(const uint8_t* p, size_t n) {
-    static uint32_t table[8][256];
-    static bool ready = false;
-    if (!ready) {
-        for (uint32_t i = 0; i < 256; i++) {
-            uint32_t c = i;
-            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-            table[0][i] = c;
-        }
-        for (uint32_t i = 0; i < 256; i++)
-            for (int t = 1; t < 8; t++) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xff];
-        ready = true;
-    }
-    uint32_t c = 0xffffffffu;
-    while (n >= 8) {
-        uint32_t a, b;
-        memcpy(&a, p, 4);
-        memcpy(&b, p + 4, 4);
-        a ^= c;
-        c = table[7][a & 0xff] ^ table[6][(a >> 8) & 0xff] ^ table[5][(a >> 16) & 0xff] ^ table[4][a >> 24] ^
-            table[3][b & 0xff] ^ table[2][(b >> 8) & 0xff] ^ table[1][(b >> 16) & 0xff] ^ table[0][b >> 24];
-        p += 8;
-        n -= 8;
-    }
-    while (n--) c = table[0][(c ^ *p++) & 0xff] ^ (c >> 8);
-    return ~c;
-}
-static uint32_t adler32_host(const uint8_t* p, size_t n) {
-    uint32_t a = 1, b = 0;
-    while (n) {
-        size_t k = n < 5552 ? n : 5552;
-        n -= k;
-        while (k--) {
-            a += *p++;
-            b += a;
-        }
-        a %= 65521;
-        b %= 65521;
-    }
-    return (b << 16) | a;
-}
-static size_t make_footer(int container, const uint8_t* plain, size_t n, uint8_t* f) {
+// container footer (container.zig:85-109) from the device-computed checksum
+static size_t make_footer(int container, uint32_t sum, size_t n, uint8_t* f) {
     if (container == FB200_GZIP) {
-        const uint32_t c = crc32_host(plain, n), sz = (uint32_t)n;
+        const uint32_t c = sum, sz = (uint32_t)n;
         for (int i = 0; i < 4; i++) f[i] = (uint8_t)(c >> (8 * i)), f[4 + i] = (uint8_t)(sz >> (8 * i));
         return 8;
     }
     if (container == FB200_ZLIB) {
-        const uint32_t c = adler32_host(plain, n);
+        const uint32_t c = sum;
         for (int i = 0; i < 4; i++) f[i] = (uint8_t)(c >> (24 - 8 * i));
         return 4;
     }
@@ -340,13 +327,16 @@ extern "C" {
 int fb200_compress_device(fb200_ctx* c, int container, int mode, const void* d_in, size_t n, void* d_out, size_t cap,
                           size_t* out_len, void* stream) {
     if (!c || !out_len || (!d_in && n)) return FB200_INVALID_ARGUMENT;
-    if (container != FB200_RAW) return FB200_INVALID_ARGUMENT;  // footer checksum needs the host copy: use fb200_compress
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     size_t end = 0;
-    int rc = deflate_body_device(c, container, mode, (const uint8_t*)d_in, n, (uint8_t*)d_out, cap, &end, true, st);
+    int rc = deflate_body_device(c, container, mode, (const uint8_t*)d_in, 0, n, nullptr, 0, (uint8_t*)d_out, cap, &end, true, true, st);
     if (rc) return rc;
-    *out_len = end;
+    uint8_t footer[8];
+    const size_t flen = make_footer(container, (uint32_t)c->h_scalars[1], n, footer);
+    if (flen) FB_CUDA_CHECK(cudaMemcpyAsync((uint8_t*)d_out + end, footer, flen, cudaMemcpyHostToDevice, st));
+    if (flen) FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    *out_len = end + flen;
     return FB200_OK;
 }
 
@@ -360,10 +350,10 @@ int fb200_compress(fb200_ctx* c, int container, int mode, const uint8_t* in, siz
     cudaStream_t st = c->stream;
     if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
     size_t end = 0;
-    int rc = deflate_body_device(c, container, mode, c->d_in.p, n, c->d_out.p, c->d_out.cap, &end, true, st);
+    int rc = deflate_body_device(c, container, mode, c->d_in.p, 0, n, nullptr, 0, c->d_out.p, c->d_out.cap, &end, true, true, st);
     if (rc) return rc;
     uint8_t footer[8];
-    const size_t flen = make_footer(container, in, n, footer);
+    const size_t flen = make_footer(container, (uint32_t)c->h_scalars[1], n, footer);
     if (end + flen > cap) return FB200_NO_SPACE_LEFT;
     FB_CUDA_CHECK(cudaMemcpyAsync(out, c->d_out.p, end, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -383,7 +373,7 @@ int fb200_debug_tokens(fb200_ctx* c, int level, const uint8_t* in, size_t n, uin
     cudaStream_t st = c->stream;
     if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
     Lz77Buffers b = lz77_view(c);
-    FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, (uint32_t)n, lv, st));
+    FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, 0, (uint32_t)n, nullptr, 0, lv, st));
     c->launches += n ? 10 : 0;
     uint32_t total = 0;
     FB_CUDA_CHECK(cudaMemcpyAsync(&total, b.total_tokens, 4, cudaMemcpyDeviceToHost, st));
@@ -404,7 +394,7 @@ int fb200_debug_match_tables(fb200_ctx* c, int level, const uint8_t* in, size_t 
     cudaStream_t st = c->stream;
     FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
     Lz77Buffers b = lz77_view(c);
-    FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, (uint32_t)n, lv, st));
+    FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, 0, (uint32_t)n, nullptr, 0, lv, st));
     c->launches += 10;
     FB_CUDA_CHECK(cudaMemcpyAsync(r_full, b.r_full, n * 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaMemcpyAsync(r_quarter, b.r_quarter, n * 4, cudaMemcpyDeviceToHost, st));
@@ -543,18 +533,22 @@ int fb200_decompress(fb200_ctx* c, int container, const uint8_t* in, size_t n, u
 
 // =============================================================================================
 // streaming compressor: Compressor / SimpleCompressor (deflate.zig:121-373, 449-529).
-// Input is accumulated; finish() runs the device pipeline over the whole stream and hands the
-// bytes to the writer.  Chunking of write() calls is not observable in the reference's output
-// (the slide schedule depends on stream position only), so this is byte-identical for
-// write*/finish.  flush() (sync marker) needs the segmented pipeline and is rejected until then.
+// write() accumulates; flush() and finish() run the device pipeline over the segment since the last
+// flush point, with the whole earlier stream kept in HBM as match history.
 // =============================================================================================
 struct fb200_deflate {
     fb200_ctx* ctx;
+    int device = 0;                 // the context may be destroyed before us: never dereference it in destroy()
     int container, mode;
     fb200_write_fn writer;
     void* user;
-    std::vector<uint8_t> pending;
-    bool header_written = false, finished = false;
+    std::vector<uint8_t> pending;   // bytes written since the last flush: stream positions [begin, begin + pending.size())
+    size_t begin = 0;               // flush point: everything before it has been emitted
+    DevBuf<uint8_t> stream;         // device copy of the whole stream so far (history for later segments)
+    DevBuf<uint16_t> link;          // hash links of the whole stream (private: the context's are per call)
+    std::vector<uint32_t> skip;     // positions never inserted into the chains (3 before every flush point)
+    DevBuf<uint32_t> d_skip;
+    bool finished = false;
     int err = 0;
 };
 
@@ -565,6 +559,7 @@ int fb200_deflate_create(fb200_ctx* ctx, int container, int mode, fb200_write_fn
     fb200_deflate* d = new (std::nothrow) fb200_deflate();
     if (!d) return FB200_INVALID_ARGUMENT;
     d->ctx = ctx;
+    d->device = ctx->device;
     d->container = container;
     d->mode = mode;
     d->writer = writer;
@@ -573,7 +568,6 @@ int fb200_deflate_create(fb200_ctx* ctx, int container, int mode, fb200_write_fn
     int rc = 0;
     if (container == FB200_GZIP) rc = writer(user, kGzipHeader, 10);
     else if (container == FB200_ZLIB) rc = writer(user, kZlibHeader, 2);
-    d->header_written = true;
     if (rc) {
         delete d;
         return FB200_NO_SPACE_LEFT;
@@ -588,23 +582,79 @@ int fb200_deflate_write(fb200_deflate* d, const uint8_t* data, size_t n) {
     d->pending.insert(d->pending.end(), data, data + n);
     return FB200_OK;
 }
+
+// Emits the segment [begin, begin + pending) -- non-final + sync marker for flush (deflate.zig:335-337,
+// :268-288), final + footer for finish (:344-347).  Chunking of write() calls inside a segment is not
+// observable in the reference's output (the slide schedule depends on stream position only).
+static int deflate_emit_segment(fb200_deflate* d, bool final_flush) {
+    fb200_ctx* c = d->ctx;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t begin = d->begin, end = begin + d->pending.size();
+    if (end > (1ull << 31) && d->mode >= 4) return FB200_INVALID_ARGUMENT;
+    // grow the device copy of the stream, keeping the history
+    if (end + 512 > d->stream.cap) {
+        DevBuf<uint8_t> bigger;
+        FB_CUDA_CHECK(bigger.ensure(end + end / 2 + (1 << 20)));
+        if (begin) FB_CUDA_CHECK(cudaMemcpyAsync(bigger.p, d->stream.p, begin, cudaMemcpyDeviceToDevice, st));
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        d->stream.release();
+        d->stream = bigger;
+    }
+    if (d->mode >= 4 && end + 64 > d->link.cap) {
+        DevBuf<uint16_t> bigger;
+        FB_CUDA_CHECK(bigger.ensure(end + end / 2 + (1 << 20)));
+        if (begin) FB_CUDA_CHECK(cudaMemcpyAsync(bigger.p, d->link.p, begin * 2, cudaMemcpyDeviceToDevice, st));
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        d->link.release();
+        d->link = bigger;
+    }
+    if (end > begin) FB_CUDA_CHECK(cudaMemcpyAsync(d->stream.p + begin, d->pending.data(), end - begin, cudaMemcpyHostToDevice, st));
+    const uint32_t nskip = d->mode >= 4 ? (uint32_t)d->skip.size() : 0;
+    if (nskip) {
+        FB_CUDA_CHECK(d->d_skip.ensure(nskip));
+        FB_CUDA_CHECK(cudaMemcpyAsync(d->d_skip.p, d->skip.data(), nskip * 4, cudaMemcpyHostToDevice, st));
+    }
+    const size_t bound = round_up(fb200_compress_bound(end - begin, d->mode) + 64, 16);
+    FB_CUDA_CHECK(c->d_out.ensure(bound));
+    // the pipeline uses the context's link buffer: lend it ours for the call
+    std::swap(c->link, d->link);
+    size_t out_end = 0;
+    int rc = deflate_body_device(c, d->container, d->mode, d->stream.p, begin, end, d->d_skip.p, nskip, c->d_out.p,
+                                 c->d_out.cap, &out_end, final_flush, false, st);
+    std::swap(c->link, d->link);
+    if (rc) return rc;
+    std::vector<uint8_t> out(out_end + 8);
+    if (out_end) FB_CUDA_CHECK(cudaMemcpy(out.data(), c->d_out.p, out_end, cudaMemcpyDeviceToHost));
+    size_t total = out_end;
+    if (final_flush) total += make_footer(d->container, (uint32_t)c->h_scalars[1], end, out.data() + out_end);
+    if (total && d->writer(d->user, out.data(), total)) return FB200_NO_SPACE_LEFT;
+    // positions with fewer than 4 bytes before the flush point were never hashed (Lookup.zig:24) and
+    // stay that way for later segments
+    if (!final_flush && d->mode >= 4)
+        for (size_t p = end >= 3 ? end - 3 : 0; p < end; p++)
+            if (p >= begin || d->skip.empty() || d->skip.back() < p) d->skip.push_back((uint32_t)p);
+    // only flush points within the last 32 KiB + one tile can matter again
+    while (!d->skip.empty() && (size_t)d->skip.front() + 2 * kHist < end) d->skip.erase(d->skip.begin());
+    d->begin = end;
+    d->pending.clear();
+    return FB200_OK;
+}
 int fb200_deflate_flush(fb200_deflate* d) {
     if (!d) return FB200_INVALID_ARGUMENT;
-    return FB200_INVALID_STATE;  // TODO(segments): sync-flush marker, deflate.zig:335-337
+    if (d->err) return d->err;
+    if (d->finished) return d->err = FB200_INVALID_STATE;
+    int rc = deflate_emit_segment(d, false);
+    if (rc) d->err = rc;
+    return rc;
 }
 int fb200_deflate_finish(fb200_deflate* d) {
     if (!d) return FB200_INVALID_ARGUMENT;
     if (d->err) return d->err;
     if (d->finished) return d->err = FB200_INVALID_STATE;
-    const size_t n = d->pending.size();
-    std::vector<uint8_t> out(fb200_compress_bound(n, d->mode) + 64);
-    size_t out_len = 0;
-    int rc = fb200_compress(d->ctx, d->container, d->mode, d->pending.data(), n, out.data(), out.size(), &out_len);
+    int rc = deflate_emit_segment(d, true);
     if (rc) return d->err = rc;
-    const size_t hs = header_size(d->container);  // already written in create()
-    if (d->writer(d->user, out.data() + hs, out_len - hs)) return d->err = FB200_NO_SPACE_LEFT;
     d->finished = true;
-    d->pending.clear();
     return FB200_OK;
 }
 void fb200_deflate_set_writer(fb200_deflate* d, fb200_write_fn writer, void* user) {
@@ -612,7 +662,14 @@ void fb200_deflate_set_writer(fb200_deflate* d, fb200_write_fn writer, void* use
     d->writer = writer;
     d->user = user;
 }
-void fb200_deflate_destroy(fb200_deflate* d) { delete d; }
+void fb200_deflate_destroy(fb200_deflate* d) {
+    if (!d) return;
+    if (cudaSetDevice(d->device) != cudaSuccess) (void)cudaGetLastError();
+    d->stream.release();
+    d->link.release();
+    d->d_skip.release();
+    delete d;
+}
 
 // =============================================================================================
 // streaming decompressor: Decompressor (inflate.zig:43-355).  One member per decompress()/next()

@@ -191,7 +191,25 @@ __device__ uint32_t x8nmodp(uint64_t nbytes) {  // x^(8 n) mod p
 }
 __device__ uint32_t crc32_chunk(const uint32_t* tab, const uint8_t* p, uint64_t n) {
     uint32_t c = 0xffffffffu;
-    for (uint64_t i = 0; i < n; i++) c = tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
+    uint64_t i = 0;
+    while (i < n && (((uintptr_t)(p + i)) & 15)) {
+        c = tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
+        i++;
+    }
+    for (; i + 16 <= n; i += 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t x = w[k];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                c = tab[(c ^ x) & 0xff] ^ (c >> 8);
+                x >>= 8;
+            }
+        }
+    }
+    for (; i < n; i++) c = tab[(c ^ p[i]) & 0xff] ^ (c >> 8);
     return ~c;
 }
 __device__ uint32_t warp_crc32(const uint32_t* tab, const uint8_t* p, uint64_t n) {

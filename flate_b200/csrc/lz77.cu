@@ -49,7 +49,8 @@ __device__ __forceinline__ uint32_t hash_be(uint32_t le32) {
 }
 
 __global__ void __launch_bounds__(kLinkThreads, 2)
-hash_link_kernel(const uint8_t* __restrict__ in, uint32_t n, uint32_t run, uint16_t* __restrict__ link) {
+hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, uint32_t run, const uint32_t* __restrict__ skip,
+                 uint32_t nskip, uint16_t* __restrict__ link) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint16_t* head = reinterpret_cast<uint16_t*>(smem_raw);
     uint16_t* hs = head + 32768;
@@ -58,8 +59,11 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t n, uint32_t run, uint1
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     uint32_t* stage = stage_all + w * kLinkStage;
     const uint32_t ltmask = (1u << lane) - 1;
+    // [begin, n) is the segment being compressed (begin > 0 after a sync flush); earlier positions are
+    // history: hashed again to prime the table, never re-linked.  `skip` lists history positions that
+    // the reference never inserted (the last 3 bytes before each flush point, Lookup.zig:24).
     const uint32_t ntiles = (n + kLinkTile - 1) / kLinkTile;
-    const uint32_t first = blockIdx.x * run;
+    const uint32_t first = begin / kLinkTile + blockIdx.x * run;
     if (first >= ntiles) return;
     const uint32_t last = min(first + run, ntiles);
     for (uint32_t i = tid; i < 32768 / 2; i += kLinkThreads) reinterpret_cast<uint32_t*>(head)[i] = 0;
@@ -94,6 +98,13 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t n, uint32_t run, uint1
                     h = hash_be((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
                 }
                 hs[off] = (uint16_t)h;
+            }
+        }
+        if (nskip) {
+            __syncthreads();
+            for (uint32_t j = tid; j < nskip; j += kLinkThreads) {
+                const uint32_t q = skip[j];
+                if (q >= base && q < base + cnt) hs[q - base] = 0xFFFFu;
             }
         }
         __syncthreads();
@@ -166,9 +177,14 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t n, uint32_t run, uint1
                 if (hs[i] == 0xFFFFu) lk[i] = 0;
             __syncthreads();
             uint16_t* dst = link + base;
-            const uint32_t nv = cnt / 8;
-            for (uint32_t i = tid; i < nv; i += kLinkThreads) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(lk)[i];
-            for (uint32_t i = nv * 8 + tid; i < cnt; i += kLinkThreads) dst[i] = lk[i];
+            if (base >= begin) {
+                const uint32_t nv = cnt / 8;
+                for (uint32_t i = tid; i < nv; i += kLinkThreads) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(lk)[i];
+                for (uint32_t i = nv * 8 + tid; i < cnt; i += kLinkThreads) dst[i] = lk[i];
+            } else {  // the tile straddles the segment start: keep the links of earlier segments
+                for (uint32_t i = tid; i < cnt; i += kLinkThreads)
+                    if (base + i >= begin) dst[i] = lk[i];
+            }
         }
         if (t + 1 < last) {
             for (uint32_t i = tid; i < 32768 / 2; i += kLinkThreads) {
@@ -223,13 +239,15 @@ enum : uint32_t { kIdle = 0, kStepping = 1, kPending = 2, kDone = 3 };
 
 template <int kStepsPerRound>
 __global__ void __launch_bounds__(kSearchThreads, 2)
-match_search_kernel(const uint8_t* __restrict__ in, uint32_t n, const uint16_t* __restrict__ link,
+match_search_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, const uint16_t* __restrict__ link,
                     LevelArgs lv, SearchTune tune, uint32_t* __restrict__ r_full, uint32_t* __restrict__ r_quarter) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t tile_next;
     uint8_t* sb = smem_raw;                                                 // bytes, slot i+16 = position wb+i
     uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + kSearchBytes);    // slot of the previous same-hash position, 0 = none
-    const uint32_t s = blockIdx.x * kSearchTile;                            // first new position
+    const uint32_t s = (begin / kSearchTile + blockIdx.x) * kSearchTile;    // first new position (tiles are absolute)
+    r_full -= begin;                                                        // result tables are segment relative
+    r_quarter -= begin;
     const int64_t wb = (int64_t)s - kHist;                                  // window base (may be < 0)
     const uint32_t lo = wb < 0 ? (uint32_t)(-wb) : 0;                       // first valid window index
     const uint32_t lane = threadIdx.x & 31;
@@ -292,6 +310,7 @@ match_search_kernel(const uint8_t* __restrict__ in, uint32_t n, const uint16_t* 
     auto arm = [&](uint32_t k) {  // start the walk of tile position k (deflate.zig:233-245)
         if (k >= tile_cnt) return;
         const uint32_t p = s + k;
+        if (p < begin) return;                // belongs to an earlier segment
         const uint32_t remaining = n - p;
         pi = kSearchOff + kHist + k;          // slot of p
         best_len = 0;
@@ -637,8 +656,8 @@ emit_tokens_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // host-side launcher
 // ------------------------------------------------------------------------------------------
-cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
-                          PhaseTimer* pt) {
+cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const uint32_t* d_skip,
+                          uint32_t nskip, const LevelArgs& lv, cudaStream_t st, PhaseTimer* pt) {
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
     static bool attr_set = false;
@@ -650,14 +669,14 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n,
         cudaFuncSetAttribute(match_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
         attr_set = true;
     }
-    if (n == 0) {
+    if (n == begin) {
         cudaMemsetAsync(b.total_tokens, 0, sizeof(uint32_t), st);
         return cudaGetLastError();
     }
-    const uint32_t ntiles = (n + kLinkTile - 1) / kLinkTile;
+    const uint32_t ntiles = (n + kLinkTile - 1) / kLinkTile - begin / kLinkTile;
     // run length: long enough to amortise the 4 warm-up tiles, short enough to fill the GPU
     const uint32_t run = ntiles >= 32 * 600 ? 32 : ntiles >= 8 * 600 ? 16 : 8;
-    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, n, run, b.link);
+    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, begin, n, run, d_skip, nskip, b.link);
     pt->mark(st, kPhLink);
     {
         // development knob: FB200_TUNE="steps,pend_at,refill_at"
@@ -675,13 +694,16 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n,
                 }
             }
         }
-        const uint32_t grid = (n + kSearchTile - 1) / kSearchTile;
-        if (steps == 2) match_search_kernel<2><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv, tune, b.r_full, b.r_quarter);
-        else if (steps == 16) match_search_kernel<16><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv, tune, b.r_full, b.r_quarter);
-        else if (steps == 8) match_search_kernel<8><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv, tune, b.r_full, b.r_quarter);
-        else match_search_kernel<4><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, n, b.link, lv, tune, b.r_full, b.r_quarter);
+        const uint32_t grid = (n + kSearchTile - 1) / kSearchTile - begin / kSearchTile;
+        if (steps == 2) match_search_kernel<2><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
+        else if (steps == 16) match_search_kernel<16><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
+        else if (steps == 8) match_search_kernel<8><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
+        else match_search_kernel<4><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
     }
     pt->mark(st, kPhSearch);
+    // everything after the match search works in segment-relative positions
+    const uint8_t* d_seg = d_in + begin;
+    n -= begin;
     lazy_step_kernel<<<(n + 255) / 256, 256, 0, st>>>(b.r_full, b.r_quarter, n, lv, b.nx);
     pt->mark(st, kPhLazy);
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
@@ -696,7 +718,7 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n,
     pt->mark(st, kPhMark);
     scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
     pt->mark(st, kPhScan);
-    emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_in, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp);
+    emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_seg, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp);
     pt->mark(st, kPhEmit);
     return cudaGetLastError();
 }

@@ -69,8 +69,11 @@ struct Lz77Buffers {
     uint32_t* cut_rp;        // nblocks: reference `rp` when block b's last token was added
 };
 
-cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
-                          PhaseTimer* pt = nullptr);
+// Tokenizes stream positions [begin, n); earlier bytes are history (begin > 0 after a sync flush).
+// d_skip/nskip: history positions the reference never inserted into its hash chains.  r_full,
+// r_quarter, nx, tokens and cut_rp are relative to `begin`.
+cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const uint32_t* d_skip,
+                          uint32_t nskip, const LevelArgs& lv, cudaStream_t st, PhaseTimer* pt = nullptr);
 
 // ---- block writer ----
 enum WriteKind : uint32_t { kWrite = 0, kDynamicBlock = 1, kHuffmanBlock = 2 };  // block_writer.zig:307,395,524
@@ -85,7 +88,7 @@ struct BlockPlan {           // per-block inputs of the build kernel (device arr
 };
 
 // plans for the level modes are derived on the device from the token count and cut_rp
-cudaError_t plan_level_blocks(const uint32_t* total_tokens, const uint32_t* cut_rp, uint32_t n, uint32_t max_blocks,
+cudaError_t plan_level_blocks(const uint32_t* total_tokens, const uint32_t* cut_rp, uint32_t begin, uint32_t n, uint32_t max_blocks,
                               uint32_t final_flush /*0 none(sync flush) 1 final*/, BlockPlan* plans, uint32_t* nblocks,
                               cudaStream_t st);
 cudaError_t histogram_tokens(const uint32_t* tokens, const BlockPlan* plans, const uint32_t* nblocks_dev,

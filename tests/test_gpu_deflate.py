@@ -244,3 +244,63 @@ def test_device_resident_compress(ctx, o):
                             stream=torch.cuda.current_stream().cuda_stream)
     got = t_out[:n].cpu().numpy().tobytes()
     assert got == o.compress(d.tobytes(), 0, 6)
+
+
+def _stream_both(ctx, o, container, mode, pieces):
+    """pieces: list of bytes or the string 'flush'.  Returns (gpu_bytes, oracle_bytes)."""
+    import flate_b200
+    w = io.BytesIO()
+    c = flate_b200.Compressor(container, w, mode, ctx=ctx)
+    d = o.Deflate(container, mode)
+    for p in pieces:
+        if isinstance(p, str):
+            c.flush()
+            d.flush()
+        else:
+            c.write(p)
+            d.write(p)
+    c.finish()
+    d.finish()
+    return w.getvalue(), d.output()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 4, 6, 9])
+def test_streaming_flush_bit_exact(ctx, o, mode):
+    """deflate.zig:335-337 flush (sync marker 00 00 ff ff), :351 history kept across flushes; the last 3
+    bytes before a flush point are never hashed (Lookup.zig:24)."""
+    from flate_b200 import synth
+    text = synth.enwik_like(400000, seed=61).tobytes()
+    mixed = synth.mixed_small(150000, seed=62).tobytes()
+    scripts = [
+        [text[:10000], "flush", text[10000:30000]],
+        [b"Blah blah blah blah blah!", "flush"],                                   # deflate.zig:556-566
+        [text[:3], "flush", text[3:5], "flush", text[5:6], "flush", text[6:5000]],   # flush points closer than 4 bytes
+        ["flush", "flush", text[:100], "flush"],                                    # empty segments
+        [text[:65536], "flush", text[65536:200000], "flush", text[200000:]],       # across window slides
+        [text[:70001], "flush", text[70001:70004], "flush", text[70004:140000]],
+        [mixed[:33000], "flush", mixed[33000:99000], "flush", mixed[99000:]],
+        [text[:65535], "flush", text[65535:65535 * 2], "flush"],                    # SimpleCompressor slice boundaries
+    ]
+    for i, sc in enumerate(scripts):
+        for container in (0, 1):
+            got, want = _stream_both(ctx, o, container, mode, sc)
+            assert got == want, (mode, i, container, first_diff(got, want))
+    # and the flushed prefix is decodable on its own (the point of a sync flush)
+    import flate_b200
+    w = io.BytesIO()
+    c = flate_b200.Compressor(0, w, mode, ctx=ctx)
+    c.write(text[:50000])
+    c.flush()
+    part = w.getvalue()
+    assert part.endswith(b"\x00\x00\xff\xff")
+    assert zlib.decompressobj(-15).decompress(part) == text[:50000]
+    c.finish()
+
+
+def test_gzip_zlib_footer_from_device_checksum(ctx, o):
+    from flate_b200 import synth
+    for n in (0, 1, 4095, 4096, 4097, 1 << 20, (1 << 20) + 13):
+        d = synth.mixed_small(n, seed=70 + n % 7).tobytes() if n else b""
+        for container in (1, 2):
+            got = ctx.compress(d, container, 6)
+            assert got[-8:] == o.compress(d, container, 6)[-8:], (n, container)
