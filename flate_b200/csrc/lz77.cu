@@ -427,6 +427,258 @@ match_search_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, 
 }
 
 // ------------------------------------------------------------------------------------------
+// K2 (rolling form).  Same walk as match_search_kernel, but one persistent CTA per SM rolls a
+// 64 KiB ring of bytes + links over a long run of positions, loading 4 KiB epochs ahead of the
+// walks.  Lanes claim positions from a run-wide counter, so the pool of work never drains the way
+// a 4096-position tile does (the tile kernel spends a large part of its time in the tail where only
+// the longest chains are still walking).  Ring slot of position p is p mod 65536; links are kept as
+// distances with 0xFFFF = none.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kRing = 65536;
+constexpr uint32_t kEpoch = 4096;
+constexpr uint32_t kRollThreads = 1024;
+constexpr uint32_t kLookahead = 272;  // bytes a walk may read past its position (258 + word slack)
+constexpr uint32_t kRollSmem = kRing + kRing * 2 + 64;
+enum : uint32_t { kClaimed = 4 };  // lane holds a position whose data is not loaded yet
+
+__device__ __forceinline__ uint32_t ring_u32_unaligned(uint32_t sb_addr, uint32_t p) {
+    const uint32_t a0 = (p & ~3u) & (kRing - 1), a1 = (a0 + 4) & (kRing - 1);
+    uint32_t w0, w1;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(sb_addr + a0));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(sb_addr + a1));
+    return __funnelshift_r(w0, w1, (p & 3) * 8);
+}
+
+template <int kStepsPerRound>
+__global__ void __launch_bounds__(kRollThreads, 1)
+match_search_roll_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, const uint16_t* __restrict__ link,
+                         LevelArgs lv, SearchTune tune, uint32_t run_epochs, uint32_t* __restrict__ r_full,
+                         uint32_t* __restrict__ r_quarter) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* sb = smem_raw;
+    uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + kRing);
+    volatile uint32_t* ctl = reinterpret_cast<volatile uint32_t*>(smem_raw + kRing * 3);
+    // ctl[0] next position to hand out, ctl[1] avail (positions < avail have their data), ctl[2] lb (load front),
+    // ctl[3] want_load, ctl[4] pmin
+    const uint32_t lane = threadIdx.x & 31, tid = threadIdx.x;
+    const uint32_t ltmask = (1u << lane) - 1;
+    r_full -= begin;
+    r_quarter -= begin;
+
+    const uint32_t r0 = (begin / kEpoch + blockIdx.x * run_epochs) * kEpoch;
+    if (r0 >= n) return;
+    const uint32_t r1 = (uint32_t)min((uint64_t)n, (uint64_t)r0 + (uint64_t)run_epochs * kEpoch);  // positions [r0, r1)
+    const uint32_t load_end = (uint32_t)min((uint64_t)((n + kEpoch - 1) / kEpoch) * kEpoch,
+                                            (uint64_t)(r1 + kEpoch - 1) / kEpoch * kEpoch + kEpoch);
+
+    // cooperative load of positions [a, b) (multiples of 16) into the ring; bytes past n are zero, links none
+    auto load_range = [&](uint32_t a, uint32_t b) {
+        const bool aligned = ((uintptr_t)in & 15) == 0;
+        for (uint32_t p = a + tid * 16; p < b; p += kRollThreads * 16) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (aligned && p + 16 <= n) v = *reinterpret_cast<const uint4*>(in + p);
+            else {
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (uint32_t j = 0; j < 16 && p + j < n; j++) w[j >> 2] |= (uint32_t)in[p + j] << (8 * (j & 3));
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4*>(sb + (p & (kRing - 1))) = v;
+        }
+        for (uint32_t p = a + tid * 8; p < b; p += kRollThreads * 8) {
+            uint32_t w[4];
+            if (p + 8 <= n) {
+                const uint4 v = *reinterpret_cast<const uint4*>(link + p);
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            } else {
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t l0 = p + 2 * k < n ? link[p + 2 * k] : 0u, l1 = p + 2 * k + 1 < n ? link[p + 2 * k + 1] : 0u;
+                    w[k] = l0 | (l1 << 16);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {  // distance 0 (none) -> 0xFFFF
+                const uint32_t lo16 = w[k] & 0xffffu, hi16 = w[k] >> 16;
+                w[k] = (lo16 ? lo16 : 0xffffu) | ((hi16 ? hi16 : 0xffffu) << 16);
+            }
+            *reinterpret_cast<uint4*>(sl + (p & (kRing - 1))) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    };
+    {
+        const uint32_t hs = r0 >= kHist ? r0 - kHist : 0;
+        const uint32_t lb0 = min(load_end, r0 + 3 * kEpoch);
+        load_range(hs, lb0);
+        if (tid == 0) {
+            ctl[0] = r0;
+            ctl[2] = lb0;
+            ctl[1] = lb0 >= n ? r1 : min(r1, lb0 - kLookahead);
+            ctl[3] = 0;
+            ctl[4] = 0xffffffffu;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t quarter = lv.chain >> 2;
+    uint32_t sb_addr = (uint32_t)__cvta_generic_to_shared(sb);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sb_addr));
+    const uint32_t sl_addr = sb_addr + kRing;
+
+    uint32_t st = kIdle, left = 0, saved = 0;
+    uint32_t p = 0, q = 0, best_len = 0, best_dist = 0, snap = 0, ro = 3, cb = 0, first4 = 0, max_len = 0;
+    int32_t lim = 0;
+    bool snapped = false;
+
+    auto arm = [&]() {  // start the walk of position p (deflate.zig:233-245); its data is in the ring
+        best_len = 0;
+        best_dist = 0;
+        snapped = false;
+        snap = 0;
+        if (p < begin) {  // belongs to an earlier segment
+            st = kIdle;
+            return;
+        }
+        const uint32_t remaining = n - p;
+        if (remaining < kMinMatch) {  // Lookup.zig:24
+            st = kDone;
+            return;
+        }
+        max_len = min(remaining, kMaxMatch);  // SlidingWindow.zig:82
+        q = p;
+        // candidates must satisfy  p - q <= 32768 (deflate.zig:250)  and  q > slide base (:248, pos 0 = none)
+        lim = (int32_t)max((int64_t)p - (int64_t)kMaxDist, (int64_t)slide_base(p, n) + 1);
+        left = quarter;
+        first4 = ring_u32_unaligned(sb_addr, p);
+        ro = 3;
+        cb = lds_shared_u8(sb_addr + ((p + 3) & (kRing - 1)));
+        st = kStepping;
+    };
+    auto event = [&]() {
+        if (!snapped) {
+            snap = best_len ? pack_match(best_len, best_dist) : 0;
+            snapped = true;
+            left = lv.chain - quarter;
+        } else {
+            st = kDone;
+        }
+    };
+
+    while (true) {
+        // ---- epoch loads: every warp passes here once per round, so the barriers line up ----
+        if (ctl[3]) {
+            __syncthreads();
+            {
+                uint32_t mine = (st == kStepping || st == kPending) ? p : 0xffffffffu;
+                for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+                if (lane == 0 && mine != 0xffffffffu) atomicMin((uint32_t*)&ctl[4], mine);
+            }
+            __syncthreads();
+            const uint32_t lb = ctl[2], pmin = ctl[4];
+            // the new epoch overwrites positions [lb - 65536, lb - 61440): every walk in flight must be past them
+            const bool safe = lb < load_end && (pmin == 0xffffffffu || (uint64_t)pmin + 28672 >= lb);
+            if (safe) load_range(lb, lb + kEpoch);
+            __syncthreads();
+            if (tid == 0) {
+                if (safe) {
+                    const uint32_t nlb = lb + kEpoch;
+                    ctl[2] = nlb;
+                    ctl[1] = nlb >= n ? r1 : min(r1, nlb - kLookahead);
+                }
+                ctl[3] = 0;
+                ctl[4] = 0xffffffffu;
+            }
+            __syncthreads();
+        }
+        // ---- phase A: chain steps (deflate.zig:248 "Hot path loop!") ----
+#pragma unroll
+        for (int u = 0; u < kStepsPerRound; u++) {
+            if (left) {
+                const uint32_t l = lds_shared_u16(sl_addr + ((q & (kRing - 1)) << 1));
+                q -= l;
+                if ((int32_t)q < lim) {  // end of chain (l = 0xFFFF), too far, or at/below the slide base
+                    st = kDone;
+                    left = 0;
+                } else if (lds_shared_u8(sb_addr + ((q + ro) & (kRing - 1))) == cb) {
+                    st = kPending;
+                    saved = left;
+                    left = 0;
+                } else {
+                    left--;
+                }
+            }
+        }
+        if (st == kStepping && left == 0) event();
+        // ---- phase B: full compares (SlidingWindow.match with the running best as min_len) ----
+        const uint32_t pend = __ballot_sync(0xffffffffu, st == kPending);
+        if (pend) {
+            const uint32_t stepping = __ballot_sync(0xffffffffu, st == kStepping);
+            if (__popc(pend) >= tune.pend_at || stepping == 0) {
+                if (st == kPending) {
+                    st = kStepping;
+                    left = saved - 1;
+                    if (ring_u32_unaligned(sb_addr, q) == first4) {
+                        uint32_t i = 4;
+                        while (i < max_len) {
+                            const uint32_t x = ring_u32_unaligned(sb_addr, q + i) ^ ring_u32_unaligned(sb_addr, p + i);
+                            if (x) {
+                                i += (__ffs(x) - 1) >> 3;
+                                break;
+                            }
+                            i += 4;
+                        }
+                        if (i > max_len) i = max_len;
+                        if (i > best_len) {
+                            best_len = i;
+                            best_dist = p - q;
+                            if (i >= lv.nice || i >= max_len) {  // deflate.zig:256-259, or nothing can be longer
+                                st = kDone;
+                                left = 0;
+                            } else {
+                                ro = i;
+                                cb = lds_shared_u8(sb_addr + ((p + i) & (kRing - 1)));
+                            }
+                        }
+                    }
+                    if (st == kStepping && left == 0) event();
+                }
+            }
+        }
+        // ---- results of finished lanes, claims, re-arm ----
+        const uint32_t avail = ctl[1];
+        if (st == kClaimed && p < avail) arm();
+        const uint32_t idle = __ballot_sync(0xffffffffu, st == kIdle || st == kDone);
+        if (idle) {
+            const uint32_t nidle = __popc(idle);
+            const uint32_t nxt = ctl[0];
+            const bool exhausted = nxt >= r1;
+            if ((!exhausted && nidle >= tune.refill_at) || idle == 0xffffffffu) {
+                if (st == kDone) {
+                    const uint32_t full = best_len ? pack_match(best_len, best_dist) : 0;
+                    r_full[p] = full;
+                    r_quarter[p] = snapped ? snap : full;
+                    st = kIdle;
+                }
+                if (!exhausted && nxt < avail) {
+                    uint32_t base_p = 0;
+                    if (lane == 0) base_p = atomicAdd((uint32_t*)&ctl[0], nidle);
+                    base_p = __shfl_sync(0xffffffffu, base_p, 0);
+                    if (st == kIdle) {
+                        const uint32_t mine = base_p + __popc(idle & ltmask);
+                        if (mine < r1) {
+                            p = mine;
+                            if (p < avail) arm();
+                            else st = kClaimed;
+                        }
+                    }
+                }
+            }
+        }
+        // ask for the next epoch when the hand-out front gets close to the loaded front (every warp, every
+        // round: waiting lanes must not depend on somebody else being idle)
+        if (lane == 0 && ctl[2] < load_end && ctl[0] + 2048 >= avail) ctl[3] = 1;
+        if (ctl[2] >= load_end && ctl[0] >= r1 && __ballot_sync(0xffffffffu, st != kIdle) == 0) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K3a: lazy step.  deflate.zig:160-193 restricted to arrivals with no pending match.
 // From such an arrival at p the reference emits k literals p..p+k-1 (each displaced by a strictly
 // longer match one byte later) and then one match at p+k, or a single literal if nothing matches.
@@ -694,11 +946,30 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t be
                 }
             }
         }
+        static int use_roll = -1;
+        static int num_sms = 148;
+        if (use_roll < 0) {
+            const char* e = getenv("FB200_SEARCH");
+            use_roll = (e && e[0] == 'r') ? 1 : 0;  // FB200_SEARCH=roll selects the persistent rolling-window kernel
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(match_search_roll_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
+            cudaFuncSetAttribute(match_search_roll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
+        }
+        if (use_roll) {
+            const uint32_t epochs = (n + kEpoch - 1) / kEpoch - begin / kEpoch;
+            const uint32_t run_epochs = (epochs + num_sms - 1) / num_sms;
+            const uint32_t rgrid = (epochs + run_epochs - 1) / run_epochs;
+            if (steps == 4) match_search_roll_kernel<4><<<rgrid, kRollThreads, kRollSmem, st>>>(d_in, begin, n, b.link, lv, tune, run_epochs, b.r_full, b.r_quarter);
+            else match_search_roll_kernel<8><<<rgrid, kRollThreads, kRollSmem, st>>>(d_in, begin, n, b.link, lv, tune, run_epochs, b.r_full, b.r_quarter);
+        } else {
         const uint32_t grid = (n + kSearchTile - 1) / kSearchTile - begin / kSearchTile;
         if (steps == 2) match_search_kernel<2><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
         else if (steps == 16) match_search_kernel<16><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
         else if (steps == 8) match_search_kernel<8><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
         else match_search_kernel<4><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
+        }
     }
     pt->mark(st, kPhSearch);
     // everything after the match search works in segment-relative positions
