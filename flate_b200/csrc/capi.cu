@@ -133,7 +133,7 @@ int fb200_profile_enable(fb200_ctx* ctx, int on) {
 }
 int fb200_profile_phases(void) { return kPhCount; }
 const char* fb200_profile_phase_name(int i) {
-    static const char* names[] = {"hash_link", "match_search", "lazy_step", "chunk_exit", "resolve_entries", "orbit_mark",
+    static const char* names[] = {"hash_link", "match_search", "lazy_step(fused)", "lazy+chunk_exit", "resolve_entries", "orbit_mark",
                                   "scan_tokens", "emit_tokens", "plan+histogram", "build_blocks", "offsets+zero", "pack_blocks",
                                   "inflate_members"};
     return (i >= 0 && i < kPhCount) ? names[i] : "?";
@@ -249,7 +249,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         Lz77Buffers b = lz77_view(c);
         c->timer.begin(st);
         FB_CUDA_CHECK(lz77_tokenize(b, d_in, (uint32_t)begin, (uint32_t)n, d_skip, nskip, lv, st, &c->timer));
-        c->launches += n > begin ? 10 : 0;
+        c->launches += n > begin ? 9 : 0;
         FB_CUDA_CHECK(plan_level_blocks(b.total_tokens, b.cut_rp, (uint32_t)begin, (uint32_t)n, max_blocks,
                                         final_flush ? 1 : 0, c->plans.p, nblocks_dev, st));
         FB_CUDA_CHECK(histogram_tokens(b.tokens, c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, st));
@@ -374,7 +374,7 @@ int fb200_debug_tokens(fb200_ctx* c, int level, const uint8_t* in, size_t n, uin
     if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
     Lz77Buffers b = lz77_view(c);
     FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, 0, (uint32_t)n, nullptr, 0, lv, st));
-    c->launches += n ? 10 : 0;
+    c->launches += n ? 9 : 0;
     uint32_t total = 0;
     FB_CUDA_CHECK(cudaMemcpyAsync(&total, b.total_tokens, 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -395,7 +395,7 @@ int fb200_debug_match_tables(fb200_ctx* c, int level, const uint8_t* in, size_t 
     FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
     Lz77Buffers b = lz77_view(c);
     FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, 0, (uint32_t)n, nullptr, 0, lv, st));
-    c->launches += 10;
+    c->launches += 9;
     FB_CUDA_CHECK(cudaMemcpyAsync(r_full, b.r_full, n * 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaMemcpyAsync(r_quarter, b.r_quarter, n * 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));

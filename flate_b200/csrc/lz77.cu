@@ -39,13 +39,25 @@ constexpr uint32_t kLinkTile = 8192;
 constexpr uint32_t kLinkWarm = kHist / kLinkTile;  // warm-up tiles
 constexpr uint32_t kLinkWarps = 16;
 constexpr uint32_t kLinkThreads = kLinkWarps * 32;
-constexpr uint32_t kLinkStage = 256;  // staging entries per warp
-constexpr uint32_t kLinkSmem = 32768 * 2 /*head*/ + kLinkTile * 2 /*hash*/ + kLinkTile * 2 /*link*/ +
-                               kLinkWarps * kLinkStage * 4;
+constexpr uint32_t kLinkPerWarp = kLinkTile / kLinkWarps;  // positions each warp splits
+constexpr uint32_t kLinkSmem = 32768 * 2 /*head*/ + kLinkTile * 2 /*partition lists*/ + kLinkTile * 2 /*hash, then link*/ +
+                               (kLinkWarps * 17 + 32) * 4;
 
 __device__ __forceinline__ uint32_t hash_be(uint32_t le32) {
     // Lookup.zig:75-84: big-endian read of 4 bytes, times 0x9E3779B1, top 15 bits
     return (__byte_perm(le32, 0, 0x0123) * 0x9E3779B1u) >> 17;
+}
+
+// lanes of the warp whose `part` (0..15) equals mine; 16 ballots pipeline far better than MATCH.ANY,
+// whose latency grows with the number of distinct values
+__device__ __forceinline__ uint32_t part_peers(uint32_t part) {
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kLinkWarps; k++) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, part == k);
+        if (part == k) mine = bal;
+    }
+    return mine;
 }
 
 __global__ void __launch_bounds__(kLinkThreads, 2)
@@ -53,11 +65,11 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, uin
                  uint32_t nskip, uint16_t* __restrict__ link) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint16_t* head = reinterpret_cast<uint16_t*>(smem_raw);
-    uint16_t* hs = head + 32768;
-    uint16_t* lk = hs + kLinkTile;
-    uint32_t* stage_all = reinterpret_cast<uint32_t*>(lk + kLinkTile);
+    uint16_t* lists = reinterpret_cast<uint16_t*>(smem_raw + 65536);          // tile offsets grouped by owner warp, in position order
+    uint16_t* hl = reinterpret_cast<uint16_t*>(smem_raw + 65536 + kLinkTile * 2);  // hash per position, later its link
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(hl + kLinkTile);              // [warp][17] counts -> running bases
+    uint32_t* pstart = cnt + kLinkWarps * 17;                                 // [17] partition starts
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    uint32_t* stage = stage_all + w * kLinkStage;
     const uint32_t ltmask = (1u << lane) - 1;
     // [begin, n) is the segment being compressed (begin > 0 after a sync flush); earlier positions are
     // history: hashed again to prime the table, never re-linked.  `skip` lists history positions that
@@ -72,8 +84,8 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, uin
     for (uint32_t t = t0; t < last; t++) {
         const bool emit = t >= first;
         const uint32_t base = t * kLinkTile;
-        const uint32_t cnt = min(kLinkTile, n - base);
-        // ---- 1. hashes of the tile ----
+        const uint32_t cnt_pos = min(kLinkTile, n - base);
+        // ---- 1. hashes of the tile (0xFFFF = not insertable) ----
         if (aligned) {
             const uint32_t* words = reinterpret_cast<const uint32_t*>(in + base);
             const uint32_t nwords_total = (n - base + 3) / 4;  // readable words from base
@@ -85,105 +97,138 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, uin
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++) {
                     const uint32_t off = i * 4 + k;
-                    const bool valid = off < cnt && (uint64_t)base + off + 4 <= n;  // Lookup.zig:24 needs 4 bytes
+                    const bool valid = off < cnt_pos && (uint64_t)base + off + 4 <= n;  // Lookup.zig:24 needs 4 bytes
                     hh[k] = valid ? hash_be(__funnelshift_r(w0, w1, 8 * k)) : 0xFFFFu;
                 }
-                reinterpret_cast<uint2*>(hs)[i] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
+                reinterpret_cast<uint2*>(hl)[i] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
             }
         } else {
             for (uint32_t off = tid; off < kLinkTile; off += kLinkThreads) {
                 uint32_t h = 0xFFFFu;
-                if (off < cnt && (uint64_t)base + off + 4 <= n) {
+                if (off < cnt_pos && (uint64_t)base + off + 4 <= n) {
                     const uint8_t* b = in + base + off;
                     h = hash_be((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
                 }
-                hs[off] = (uint16_t)h;
+                hl[off] = (uint16_t)h;
             }
         }
+        for (uint32_t i = tid; i < kLinkWarps * 17; i += kLinkThreads) cnt[i] = 0;
         if (nskip) {
             __syncthreads();
             for (uint32_t j = tid; j < nskip; j += kLinkThreads) {
                 const uint32_t q = skip[j];
-                if (q >= base && q < base + cnt) hs[q - base] = 0xFFFFu;
+                if (q >= base && q < base + cnt_pos) hl[q - base] = 0xFFFFu;
             }
         }
         __syncthreads();
-        // ---- 2. per-warp ordered scan of the owned hash slice ----
+        // ---- 2. stable split of the tile's positions by owner warp (hash >> 11) ----
+        // 2a. every warp counts, per owner, the positions of its own 512-position slice
+        for (uint32_t it = 0; it < kLinkPerWarp / 32; it++) {
+            const uint32_t off = w * kLinkPerWarp + it * 32 + lane;
+            const uint32_t part = hl[off] >> 11;  // 0..15, or 31 for not insertable
+            const uint32_t peers = part_peers(part);
+            if ((peers & ltmask) == 0 && part < kLinkWarps) cnt[w * 17 + part] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // 2b. exclusive prefix down each owner's column, then over the owners
+        if (tid < kLinkWarps) {
+            uint32_t run_sum = 0;
+            for (uint32_t ww = 0; ww < kLinkWarps; ww++) {
+                const uint32_t c = cnt[ww * 17 + tid];
+                cnt[ww * 17 + tid] = run_sum;
+                run_sum += c;
+            }
+            pstart[tid + 1] = run_sum;  // totals for now
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = 0;
+            pstart[0] = 0;
+            for (uint32_t k = 1; k <= kLinkWarps; k++) {
+                acc += pstart[k];
+                pstart[k] = acc;
+            }
+        }
+        __syncthreads();
+        // 2c. scatter (off, hash) into the owner's list, keeping position order
+        for (uint32_t it = 0; it < kLinkPerWarp / 32; it++) {
+            const uint32_t off = w * kLinkPerWarp + it * 32 + lane;
+            const uint32_t h = hl[off];
+            const uint32_t part = h >> 11;
+            uint32_t peers = part_peers(part);
+            if (part >= kLinkWarps) peers = 1u << lane;  // not insertable: alone
+            const uint32_t leader = __ffs(peers) - 1;
+            uint32_t at = 0;
+            if (lane == leader && part < kLinkWarps) {
+                at = cnt[w * 17 + part];
+                cnt[w * 17 + part] = at + __popc(peers);
+            }
+            at = __shfl_sync(0xffffffffu, at, leader);
+            if (part < kLinkWarps) lists[pstart[part] + at + __popc(peers & ltmask)] = (uint16_t)off;
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- 3. every warp resolves its own list in order, 32 entries per step ----
         {
-            uint32_t fill = 0;
-            constexpr uint32_t kSteps = kLinkTile / 128;
-            for (uint32_t g = 0; g <= kSteps; g++) {
-                if (g < kSteps) {
-                    // lane L holds positions 128 g + 4 L .. + 3 (ascending order = lane-major, then j)
-                    const uint2 v = reinterpret_cast<const uint2*>(hs)[g * 32 + lane];
-                    const uint32_t h0 = v.x & 0xffffu, h1 = v.x >> 16, h2 = v.y & 0xffffu, h3 = v.y >> 16;
-                    const bool m0 = (h0 >> 11) == w, m1 = (h1 >> 11) == w, m2 = (h2 >> 11) == w, m3 = (h3 >> 11) == w;
-                    const uint32_t mine = (uint32_t)m0 + m1 + m2 + m3;
-                    // exclusive prefix of `mine` over lanes
-                    uint32_t incl = mine;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= (uint32_t)o) incl += y;
-                    }
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    uint32_t at = fill + incl - mine;
-                    const uint32_t off0 = g * 128 + lane * 4;
-                    if (m0) stage[at++] = (off0 << 16) | h0;
-                    if (m1) stage[at++] = ((off0 + 1) << 16) | h1;
-                    if (m2) stage[at++] = ((off0 + 2) << 16) | h2;
-                    if (m3) stage[at++] = ((off0 + 3) << 16) | h3;
-                    fill += total;
-                    __syncwarp();
-                    if (fill + 128 <= kLinkStage && g + 1 < kSteps) continue;  // room for another step: keep scanning
+            const uint32_t lo = pstart[w], hi = pstart[w + 1];
+            for (uint32_t sidx = lo; sidx < hi; sidx += 32) {
+                uint32_t h = 0x10000u | lane, off = 0;  // unique key for idle lanes
+                const bool have = sidx + lane < hi;
+                if (have) {
+                    off = lists[sidx + lane];
+                    h = hl[off];
                 }
-                // resolve everything staged so far, 32 entries per step, in order
-                for (uint32_t sidx = 0; sidx < fill; sidx += 32) {
-                    uint32_t h = 0x10000u | lane, off = 0;  // unique key for idle lanes
-                    const bool have = sidx + lane < fill;
-                    if (have) {
-                        const uint32_t ent = stage[sidx + lane];
-                        off = ent >> 16;
-                        h = ent & 0xffffu;
-                    }
+                // optimistic step: most groups hold 32 different hashes.  Everybody reads its old head,
+                // publishes itself and reads back; a lane that does not find its own code lost to a peer
+                // with the same hash, and only then is the group ordered with MATCH.ANY.
+                const uint32_t code = off + kHist + 1;
+                uint32_t e = 0;
+                if (have) {
+                    e = head[h];
+                    head[h] = (uint16_t)code;
+                }
+                __syncwarp();
+                const bool lost = have && head[h] != code;
+                uint32_t d = 0;
+                if (e) {
+                    d = code - e;
+                    if (d > kMaxDist) d = 0;
+                }
+                if (__any_sync(0xffffffffu, lost)) {
                     const uint32_t peers = __match_any_sync(0xffffffffu, h);
                     const uint32_t lower = peers & ltmask;
                     const uint32_t src = lower ? 31 - __clz(lower) : lane;
                     const uint32_t off_prev = __shfl_sync(0xffffffffu, off, src);
                     if (have) {
-                        uint32_t d = 0;
-                        if (lower) {
-                            d = off - off_prev;  // same tile
-                        } else {
-                            const uint32_t e = head[h];
-                            if (e) {
-                                d = off + (kHist + 1) - e;
-                                if (d > kMaxDist) d = 0;
-                            }
-                        }
-                        if ((peers >> lane) == 1u) head[h] = (uint16_t)(off + kHist + 1);
-                        if (emit) lk[off] = (uint16_t)d;
+                        if (lower) d = off - off_prev;  // predecessor inside the group, same tile
+                        if ((peers >> lane) == 1u) head[h] = (uint16_t)code;  // the group's last lane wins
                     }
-                    __syncwarp();
                 }
-                fill = 0;
+                if (have) hl[off] = (uint16_t)d;  // only this lane ever needed the hash of this position
+                __syncwarp();
             }
         }
         __syncthreads();
-        // ---- 3. flush links, rebase the head table by one tile ----
+        // ---- 4. flush links (0xFFFF = never inserted -> no link), rebase the head table by one tile ----
         if (emit) {
-            // positions that cannot be inserted (fewer than 4 bytes left) have no link
-            for (uint32_t i = tid; i < cnt; i += kLinkThreads)
-                if (hs[i] == 0xFFFFu) lk[i] = 0;
-            __syncthreads();
             uint16_t* dst = link + base;
             if (base >= begin) {
-                const uint32_t nv = cnt / 8;
-                for (uint32_t i = tid; i < nv; i += kLinkThreads) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(lk)[i];
-                for (uint32_t i = nv * 8 + tid; i < cnt; i += kLinkThreads) dst[i] = lk[i];
+                const uint32_t nv = cnt_pos / 8;
+                for (uint32_t i = tid; i < nv; i += kLinkThreads) {
+                    uint4 v = reinterpret_cast<const uint4*>(hl)[i];
+                    uint32_t* x = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if ((x[k] & 0xffffu) == 0xffffu) x[k] &= 0xffff0000u;
+                        if ((x[k] >> 16) == 0xffffu) x[k] &= 0x0000ffffu;
+                    }
+                    reinterpret_cast<uint4*>(dst)[i] = v;
+                }
+                for (uint32_t i = nv * 8 + tid; i < cnt_pos; i += kLinkThreads) dst[i] = hl[i] == 0xFFFFu ? 0 : hl[i];
             } else {  // the tile straddles the segment start: keep the links of earlier segments
-                for (uint32_t i = tid; i < cnt; i += kLinkThreads)
-                    if (base + i >= begin) dst[i] = lk[i];
+                for (uint32_t i = tid; i < cnt_pos; i += kLinkThreads)
+                    if (base + i >= begin) dst[i] = hl[i] == 0xFFFFu ? 0 : hl[i];
             }
         }
         if (t + 1 < last) {
@@ -683,45 +728,53 @@ match_search_roll_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_
 // From such an arrival at p the reference emits k literals p..p+k-1 (each displaced by a strictly
 // longer match one byte later) and then one match at p+k, or a single literal if nothing matches.
 // ------------------------------------------------------------------------------------------
-__global__ void lazy_step_kernel(const uint32_t* __restrict__ r_full, const uint32_t* __restrict__ r_quarter, uint32_t n,
-                                 LevelArgs lv, uint32_t* __restrict__ nx) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    uint32_t r = r_full[p];
-    uint32_t out = 0;
-    if (r != 0) {
-        uint32_t cur = p;
-        while (true) {
-            const uint32_t len = match_len_of(r);
-            if (len >= lv.lazy) break;  // deflate.zig:171
-            const uint32_t nxt = cur + 1;
-            if (nxt >= n) break;
-            const uint32_t r2 = (len >= lv.good) ? r_quarter[nxt] : r_full[nxt];  // deflate.zig:241-245
-            if (match_len_of(r2) > len) {  // better match one byte later: p becomes a literal
-                cur = nxt;
-                r = r2;
-            } else {
-                break;  // deflate.zig:182-184: emit the pending match
-            }
-        }
-        out = (cur - p) | ((match_len_of(r) - 3) << 8) | (match_dist_of(r) << 16);
-    }
-    nx[p] = out;
-}
-
 // ------------------------------------------------------------------------------------------
 // K3b: chunk exit tables by pointer jumping.  For every possible entry offset e < 516 of a chunk
 // of kChunk positions, the offset (into the next chunk) of the first arrival past the chunk end.
 // ------------------------------------------------------------------------------------------
+constexpr uint32_t kLazyHalo = 256;  // a lazy run looks at most 255 positions ahead of its arrival
 __global__ void __launch_bounds__(1024)
-chunk_exit_kernel(const uint32_t* __restrict__ nx, uint32_t n, uint16_t* __restrict__ exits) {
+lazy_exit_kernel(const uint32_t* __restrict__ r_full, const uint32_t* __restrict__ r_quarter, uint32_t n, LevelArgs lv,
+                 uint32_t* __restrict__ nx, uint16_t* __restrict__ exits) {
+    // K3a + K3b fused: the chunk's match tables are staged once in shared memory, every thread
+    // evaluates the lazy rule for 4 arrivals (deflate.zig:160-193), then the chunk's exit table is
+    // built by pointer jumping.
+    __shared__ uint32_t sf[kChunk + kLazyHalo];
+    __shared__ uint32_t sq[kChunk + kLazyHalo];
     __shared__ uint16_t nxt[kChunk];
     const uint32_t c = blockIdx.x;
     const uint32_t cs = c * kChunk;
+    for (uint32_t i = threadIdx.x; i < kChunk + kLazyHalo; i += blockDim.x) {
+        const uint32_t p = cs + i;
+        sf[i] = p < n ? r_full[p] : 0;
+        sq[i] = p < n ? r_quarter[p] : 0;
+    }
+    __syncthreads();
     for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
         const uint32_t p = cs + i;
         uint32_t t = kChunk;  // positions past the end of data exit immediately
-        if (p < n) t = i + nx_step(nx[p]);
+        if (p < n) {
+            uint32_t r = sf[i];
+            uint32_t out = 0;
+            if (r != 0) {
+                uint32_t cur = i;
+                while (true) {
+                    const uint32_t len = match_len_of(r);
+                    if (len >= lv.lazy) break;  // deflate.zig:171
+                    const uint32_t nb = cur + 1;  // stays inside the halo: at most 254 deferrals
+                    const uint32_t r2 = (len >= lv.good) ? sq[nb] : sf[nb];  // deflate.zig:241-245
+                    if (match_len_of(r2) > len) {  // better match one byte later: cur becomes a literal
+                        cur = nb;
+                        r = r2;
+                    } else {
+                        break;  // deflate.zig:182-184: emit the pending match
+                    }
+                }
+                out = (cur - i) | ((match_len_of(r) - 3) << 8) | (match_dist_of(r) << 16);
+            }
+            nx[p] = out;
+            t = i + nx_step(out);
+        }
         nxt[i] = (uint16_t)t;
     }
     __syncthreads();
@@ -778,8 +831,7 @@ constexpr uint32_t kMarkThreads = 128;
 __global__ void __launch_bounds__(kMarkThreads)
 orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* __restrict__ entry,
                   uint32_t* __restrict__ bitmap, uint32_t* __restrict__ chunk_tokens) {
-    __shared__ uint16_t step[kChunk];   // step | 0x8000.. no: plain step (<= 515)
-    __shared__ uint16_t ntok[kChunk];   // tokens emitted by an arrival here
+    __shared__ uint32_t sn[kChunk];  // step | tokens emitted by an arrival here << 16
     __shared__ uint32_t bits[kChunk / 32];
     const uint32_t c = blockIdx.x;
     const uint32_t cs = c * kChunk;
@@ -791,20 +843,26 @@ orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* _
             s = nx_step(v);
             t = (v >> 16) ? (v & 255u) + 1 : 1;
         }
-        step[i] = (uint16_t)s;
-        ntok[i] = (uint16_t)t;
+        sn[i] = s | (t << 16);
     }
     for (uint32_t i = threadIdx.x; i < kChunk / 32; i += kMarkThreads) bits[i] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {  // the orbit is sequential; many chunks walk concurrently
         uint32_t i = entry[c];
-        uint32_t total = 0;
+        uint32_t total = 0, word = 0xffffffffu, acc = 0;
         const uint32_t lim = min(kChunk, n > cs ? n - cs : 0u);
         while (i < lim) {
-            bits[i >> 5] |= 1u << (i & 31);
-            total += ntok[i];
-            i += step[i];
+            const uint32_t v = sn[i];
+            if ((i >> 5) != word) {
+                if (word != 0xffffffffu) bits[word] = acc;
+                word = i >> 5;
+                acc = 0;
+            }
+            acc |= 1u << (i & 31);
+            total += v >> 16;
+            i += v & 0xffffu;
         }
+        if (word != 0xffffffffu) bits[word] = acc;
         chunk_tokens[c] = total;
     }
     __syncthreads();
@@ -975,11 +1033,9 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t be
     // everything after the match search works in segment-relative positions
     const uint8_t* d_seg = d_in + begin;
     n -= begin;
-    lazy_step_kernel<<<(n + 255) / 256, 256, 0, st>>>(b.r_full, b.r_quarter, n, lv, b.nx);
-    pt->mark(st, kPhLazy);
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
     const uint32_t ngroups = (nchunks + kGroup - 1) / kGroup;
-    chunk_exit_kernel<<<nchunks, 1024, 0, st>>>(b.nx, n, b.exits);
+    lazy_exit_kernel<<<nchunks, 1024, 0, st>>>(b.r_full, b.r_quarter, n, lv, b.nx, b.exits);
     pt->mark(st, kPhChunkExit);
     group_exit_kernel<<<ngroups, 544, 0, st>>>(b.exits, nchunks, b.gexits);
     group_entry_kernel<<<1, 32, 0, st>>>(b.gexits, ngroups, b.gentry);
