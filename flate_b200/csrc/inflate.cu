@@ -250,8 +250,8 @@ __device__ uint32_t warp_adler32(const uint8_t* p, uint64_t n) {
 // shared memory.  Literals and match copies stay on the SM; the ring is drained to HBM in
 // 16-byte coalesced stores.  Ring slot of output position p is (p + A) mod kRing with
 // A = (address of out) mod 16, so ring and global alignment agree.
-constexpr uint32_t kRing = 32768;
-constexpr uint32_t kFlushAt = 8192;  // drain when this many bytes are pending
+constexpr uint32_t kRing = 16384;
+constexpr uint32_t kFlushAt = 4096;  // drain when this many bytes are pending
 
 struct OutWindow {
     uint8_t* ring;
@@ -298,6 +298,8 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
     W.A = (uint32_t)((uintptr_t)out & 15);
     W.flushed = 0;
 
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t lit_fast_addr = (uint32_t)__cvta_generic_to_shared(T.lit_fast);
     BitCursor bc;
     bc.next = d_in + md.in_off;
     bc.end = bc.next + md.in_len;
@@ -471,6 +473,24 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                 uint32_t ev_len = 0, ev_dist = 0;  // match event (len > 0); otherwise flush / end of block / error
                 if (lane == 0) {
                     for (;;) {
+                        {
+                            // fast path: literals whose code sits in the direct table, as long as neither a
+                            // drain nor the output capacity is due.  Everything else (long codes, matches,
+                            // end of block, short input, errors) leaves through the general path below, which
+                            // re-decodes the symbol with the reference's exact check order.
+                            const uint64_t stop = min(cap, W.flushed + kFlushAt);
+                            while (pos < stop) {
+                                if (bc.cnt <= 32) bc.refill();
+                                uint32_t e;
+                                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(lit_fast_addr + (((uint32_t)bc.buf & ((1u << kLitFast) - 1)) << 1)));
+                                const uint32_t nb = e & 15;
+                                if (nb == 0 || nb > bc.cnt || e >= (256u << 4)) break;
+                                bc.buf >>= nb;
+                                bc.cnt -= nb;
+                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_addr + (((uint32_t)pos + W.A) & (kRing - 1))), "r"(e >> 4));
+                                pos++;
+                            }
+                        }
                         if (pos - W.flushed >= kFlushAt) break;                    // drain request
                         if (bc.empty()) { status = FB200_END_OF_STREAM; break; }  // fill(15) / fill(7+2)
                         uint32_t sym, nb;
