@@ -22,9 +22,14 @@ __constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49
 constexpr uint32_t kLitFast = 10, kDistFast = 8;
 constexpr uint32_t kInflateWarps = 4;
 
+// direct-table entry: code length (4 bits, 0 = use the canonical fallback) | symbol << 4 (9 bits) |
+// extra-bit count << 13 (4 bits) | base value << 17 (length or distance base; 15 bits)
+constexpr uint32_t kQueue = 64;        // match descriptors per batch
+constexpr uint32_t kBatchSpan = 1024;  // output bytes lane 0 may run ahead of the warp's copies
 struct WarpTables {
-    uint16_t lit_fast[1 << kLitFast];    // len | sym << 4 ; 0 = use the canonical fallback
-    uint16_t dist_fast[1 << kDistFast];
+    uint32_t lit_fast[1 << kLitFast];
+    uint32_t dist_fast[1 << kDistFast];
+    uint32_t queue[2 * kQueue];          // (position, length << 16 | distance - 1)
     uint16_t lit_count[16], dist_count[16];
     uint16_t lit_sym[kNumLit + 2], dist_sym[kNumDist + 2];
     uint8_t lit_lens[kNumLit + 2], dist_lens[kNumDist + 2];
@@ -98,7 +103,7 @@ __device__ __forceinline__ int slow_find(const uint16_t* count, const uint16_t* 
 
 // huffman_decoder.zig:126-153 checkCompletnes + canonical tables.  Whole warp; returns status (uniform).
 __device__ int build_decoder(const uint8_t* lens, uint32_t n, bool is_lit, uint32_t max_code_bits, uint16_t* count,
-                             uint16_t* symbol, uint16_t* fast, uint32_t fast_bits) {
+                             uint16_t* symbol, uint32_t* fast, uint32_t fast_bits) {
     const uint32_t lane = threadIdx.x & 31;
     int status = FB200_OK;
     __shared__ uint16_t offs_all[kInflateWarps][17];
@@ -146,7 +151,18 @@ __device__ int build_decoder(const uint8_t* lens, uint32_t n, bool is_lit, uint3
         // symbols symbol[index .. index+cnt) have codes code .. code+cnt-1 (MSB-first)
         for (uint32_t k = lane; k < cnt; k += 32) {
             const uint32_t rev = __brev(code + k) >> (32 - len);
-            const uint16_t entry = (uint16_t)(len | (symbol[index + k] << 4));
+            const uint32_t sym = symbol[index + k];
+            uint32_t eb = 0, base_v = 0;
+            if (is_lit) {
+                if (sym >= 257 && sym <= 285) {
+                    eb = length_extra_bits(sym - 257);
+                    base_v = c_len_base[sym - 257];
+                }
+            } else if (sym <= 29) {
+                eb = distance_extra_bits(sym);
+                base_v = c_dist_base[sym];
+            }
+            const uint32_t entry = len | (sym << 4) | (eb << 13) | (base_v << 17);
             for (uint32_t e = rev; e < (1u << fast_bits); e += (1u << len)) fast[e] = entry;
         }
         code = (code + cnt) << 1;
@@ -300,6 +316,7 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
 
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t lit_fast_addr = (uint32_t)__cvta_generic_to_shared(T.lit_fast);
+    const uint32_t dist_fast_addr = (uint32_t)__cvta_generic_to_shared(T.dist_fast);
     BitCursor bc;
     bc.next = d_in + md.in_off;
     bc.end = bc.next + md.in_len;
@@ -470,33 +487,87 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
             // ---- symbol loop (inflate.zig:220-239 dynamicBlock / :104-124 fixedBlock) ----
             bool done = false;
             while (!done) {
+                // ---- batch: lane 0 decodes ahead.  Literals go straight into the ring, matches are queued
+                // (their bytes do not influence decoding) and resolved afterwards by the whole warp.  Only
+                // regular cases are committed here; anything else (codes outside the direct tables, end of
+                // block, short input, invalid symbols, capacity) is left to the exact general path below.
+                uint32_t nq = 0;
+                const uint64_t pos0 = pos;  // uniform here; lane 0 runs ahead from it
+                if (lane == 0) {
+                    const uint64_t stop = min(min(cap, W.flushed + kFlushAt), pos + kBatchSpan);
+                    while (pos < stop && nq < kQueue) {
+                        if (bc.cnt <= 32) bc.refill();
+                        uint32_t e;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_fast_addr + (((uint32_t)bc.buf & ((1u << kLitFast) - 1)) << 2)));
+                        const uint32_t nb = e & 15, sym = (e >> 4) & 511u;
+                        if (nb == 0 || nb > bc.cnt) break;
+                        if (sym < 256) {
+                            bc.buf >>= nb;
+                            bc.cnt -= nb;
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_addr + (((uint32_t)pos + W.A) & (kRing - 1))), "r"(sym));
+                            pos++;
+                            continue;
+                        }
+                        if (sym == 256 || sym > 285) break;
+                        // length + distance, on a copy of the cursor so that an irregular case leaves it untouched
+                        const uint32_t leb = (e >> 13) & 15;
+                        if (nb + leb > bc.cnt) break;
+                        BitCursor t = bc;
+                        const uint32_t length = (e >> 17) + (((uint32_t)(t.buf >> nb)) & ((1u << leb) - 1));
+                        t.buf >>= nb + leb;
+                        t.cnt -= nb + leb;
+                        if (t.cnt <= 32) t.refill();
+                        uint32_t de;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(de) : "r"(dist_fast_addr + (((uint32_t)t.buf & ((1u << kDistFast) - 1)) << 2)));
+                        const uint32_t dnb = de & 15, deb = (de >> 13) & 15;
+                        if (dnb == 0 || ((de >> 4) & 511u) > 29 || dnb + deb > t.cnt) break;
+                        const uint32_t distance = (de >> 17) + (((uint32_t)(t.buf >> dnb)) & ((1u << deb) - 1));
+                        if (md.hist + pos < distance || pos + length > cap) break;
+                        t.buf >>= dnb + deb;
+                        t.cnt -= dnb + deb;
+                        bc = t;
+                        T.queue[2 * nq] = (uint32_t)pos;
+                        T.queue[2 * nq + 1] = (length << 16) | (distance - 1);
+                        nq++;
+                        pos += length;
+                    }
+                }
+                __syncwarp();
+                nq = BCAST(nq);
+                if (nq) {
+                    for (uint32_t k = 0; k < nq; k++) {
+                        const uint32_t qlo = T.queue[2 * k], w1 = T.queue[2 * k + 1];
+                        const uint32_t q_len = w1 >> 16, q_dist = (w1 & 0xffffu) + 1;
+                        const uint64_t qpos = pos0 + (uint32_t)(qlo - (uint32_t)pos0);  // the batch spans < 4 GiB
+                        if (q_dist <= kRing - kBatchSpan - 512 && q_dist <= qpos) {
+                            const uint32_t from = (uint32_t)qpos - q_dist;
+                            if (q_dist >= q_len) {
+                                for (uint32_t i = lane; i < q_len; i += 32) W.ring[W.slot(qpos + i)] = W.ring[((from + i) + W.A) & (kRing - 1)];
+                            } else {
+                                for (uint32_t i = lane; i < q_len; i += 32)
+                                    W.ring[W.slot(qpos + i)] = W.ring[((from + i % q_dist) + W.A) & (kRing - 1)];
+                            }
+                        } else {
+                            for (uint32_t i = lane; i < q_len; i += 32) {
+                                const int64_t sp = (int64_t)qpos - q_dist + (q_dist >= q_len ? i : i % q_dist);
+                                uint8_t b;
+                                if (sp >= (int64_t)W.flushed) b = W.ring[W.slot((uint64_t)sp)];
+                                else b = __ldcg(out + sp);
+                                W.ring[W.slot(qpos + i)] = b;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
                 uint32_t ev_len = 0, ev_dist = 0;  // match event (len > 0); otherwise flush / end of block / error
                 if (lane == 0) {
                     for (;;) {
-                        {
-                            // fast path: literals whose code sits in the direct table, as long as neither a
-                            // drain nor the output capacity is due.  Everything else (long codes, matches,
-                            // end of block, short input, errors) leaves through the general path below, which
-                            // re-decodes the symbol with the reference's exact check order.
-                            const uint64_t stop = min(cap, W.flushed + kFlushAt);
-                            while (pos < stop) {
-                                if (bc.cnt <= 32) bc.refill();
-                                uint32_t e;
-                                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(lit_fast_addr + (((uint32_t)bc.buf & ((1u << kLitFast) - 1)) << 1)));
-                                const uint32_t nb = e & 15;
-                                if (nb == 0 || nb > bc.cnt || e >= (256u << 4)) break;
-                                bc.buf >>= nb;
-                                bc.cnt -= nb;
-                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_addr + (((uint32_t)pos + W.A) & (kRing - 1))), "r"(e >> 4));
-                                pos++;
-                            }
-                        }
                         if (pos - W.flushed >= kFlushAt) break;                    // drain request
                         if (bc.empty()) { status = FB200_END_OF_STREAM; break; }  // fill(15) / fill(7+2)
                         uint32_t sym, nb;
                         const uint32_t e = T.lit_fast[bc.peek(kLitFast)];
                         if (e & 15) {
-                            sym = e >> 4;
+                            sym = (e >> 4) & 511u;
                             nb = e & 15;
                         } else {
                             status = slow_find(T.lit_count, T.lit_sym, 15, bc.peek(15), sym, nb);
@@ -527,7 +598,7 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                         bc.refill();
                         const uint32_t de = T.dist_fast[bc.peek(kDistFast)];
                         if (de & 15) {
-                            dsym = de >> 4;
+                            dsym = (de >> 4) & 511u;
                             dnb = de & 15;
                         } else {
                             status = slow_find(T.dist_count, T.dist_sym, 15, bc.peek(15), dsym, dnb);
