@@ -325,6 +325,17 @@ def main():
                    "roofline": {"bound": "hbm", "achieved": round(algo / 1e9 / (kms / 1e3), 2), "peak": peak, "unit": "GB/s",
                                 "frac": round(algo / 1e9 / (kms / 1e3) / peak, 5), "traffic": None,
                                 "kernel": "inflate_members_kernel", "kernel_ms": round(kms, 3)}}
+        # CPU baseline of the inflate side: the oracle (port of inflate.zig) on one host core, 64 members
+        if rank == 0 and not args.skip_cpu:
+            from oracle import oracle as o
+            ksample = min(64, uniq)
+            t0 = time.perf_counter()
+            for i in range(ksample):
+                pl, _ = o.decompress(members[i], o.GZIP, cap=MEMBER_BYTES + 64)
+                assert len(pl) == MEMBER_BYTES
+            dt = time.perf_counter() - t0
+            inflate["cpu_baseline"] = {"value": round(ksample * MEMBER_BYTES / 1e6 / dt, 1), "unit": "MB/s", "cores": 1,
+                                       "kind": "port", "sample": "%d of the same members, oracle inflate, 1 thread" % ksample}
         del d_blob, d_plain
 
     if world > 1:
