@@ -35,6 +35,10 @@ namespace fb {
 // Four warm-up tiles (32768 positions) prime the table so runs are independent (links farther than
 // 32768 are dropped anyway, deflate.zig:250).
 // ------------------------------------------------------------------------------------------
+// link[p] = distance to the previous position with the same hash; kNoLink when there is none within
+// 32768 (or p was never inserted).  0xFFFF makes the walk's single bound test catch it: q - 65535 is
+// always below the lowest admissible candidate.
+constexpr uint16_t kNoLink = 0xFFFF;
 constexpr uint32_t kLinkTile = 8192;
 constexpr uint32_t kLinkWarm = kHist / kLinkTile;  // warm-up tiles
 constexpr uint32_t kLinkWarps = 16;
@@ -219,16 +223,16 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, uin
                     uint4 v = reinterpret_cast<const uint4*>(hl)[i];
                     uint32_t* x = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        if ((x[k] & 0xffffu) == 0xffffu) x[k] &= 0xffff0000u;
-                        if ((x[k] >> 16) == 0xffffu) x[k] &= 0x0000ffffu;
+                    for (int k = 0; k < 4; k++) {  // no predecessor (0) and never inserted (0xFFFF) both become kNoLink
+                        if ((x[k] & 0xffffu) == 0) x[k] |= 0x0000ffffu;
+                        if ((x[k] >> 16) == 0) x[k] |= 0xffff0000u;
                     }
                     reinterpret_cast<uint4*>(dst)[i] = v;
                 }
-                for (uint32_t i = nv * 8 + tid; i < cnt_pos; i += kLinkThreads) dst[i] = hl[i] == 0xFFFFu ? 0 : hl[i];
+                for (uint32_t i = nv * 8 + tid; i < cnt_pos; i += kLinkThreads) dst[i] = hl[i] == 0 ? kNoLink : hl[i];
             } else {  // the tile straddles the segment start: keep the links of earlier segments
                 for (uint32_t i = tid; i < cnt_pos; i += kLinkThreads)
-                    if (base + i >= begin) dst[i] = hl[i] == 0xFFFFu ? 0 : hl[i];
+                    if (base + i >= begin) dst[i] = hl[i] == 0 ? kNoLink : hl[i];
             }
         }
         if (t + 1 < last) {
@@ -288,8 +292,9 @@ match_search_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, 
                     LevelArgs lv, SearchTune tune, uint32_t* __restrict__ r_full, uint32_t* __restrict__ r_quarter) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t tile_next;
+    __shared__ __align__(8) uint64_t stage_bar;
     uint8_t* sb = smem_raw;                                                 // bytes, slot i+16 = position wb+i
-    uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + kSearchBytes);    // slot of the previous same-hash position, 0 = none
+    uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + kSearchBytes);    // link (distance, kNoLink = none) per slot
     const uint32_t s = (begin / kSearchTile + blockIdx.x) * kSearchTile;    // first new position (tiles are absolute)
     r_full -= begin;                                                        // result tables are segment relative
     r_quarter -= begin;
@@ -298,8 +303,35 @@ match_search_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, 
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t ltmask = (1u << lane) - 1;
 
-    // ---- stage window: bytes verbatim, links converted from distances to slots ----
-    {
+    // ---- stage window ----
+    // Interior tiles: two TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier)
+    // issued by one thread: 36 KiB of bytes and 72 KiB of links land in shared memory without passing
+    // through registers.  Edge tiles (stream start / end) use a guarded copy loop.
+    const bool tma_ok = wb >= 0 && (uint64_t)s + kSearchTile + 272 <= n && (((uintptr_t)in | (uintptr_t)link) & 15) == 0;
+    if (tma_ok) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+        constexpr uint32_t kBytesTx = kSearchBytes - kSearchOff, kLinksTx = (kSearchLinks - kSearchOff) * 2;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBytesTx + kLinksTx) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(sb + kSearchOff)), "l"(in + wb), "r"(kBytesTx), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(sl + kSearchOff)), "l"(link + wb), "r"(kLinksTx), "r"(bar) : "memory");
+            tile_next = kSearchThreads;  // the first kSearchThreads positions are pre-assigned
+        }
+        __syncthreads();  // barrier initialised and armed before anyone polls it
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_STAGE:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@p bra DONE_STAGE;\n"
+            "bra WAIT_STAGE;\n"
+            "DONE_STAGE:\n"
+            "}\n" ::"r"(bar) : "memory");
+    } else {
         const uint32_t byte_hi = (uint32_t)min((int64_t)(kSearchBytes - kSearchOff), (int64_t)n - wb);  // exclusive
         const bool aligned = ((uintptr_t)in & 15) == 0;  // wb is a multiple of 4096
         const uint32_t v_lo = lo / 16, v_hi = aligned ? byte_hi / 16 : v_lo;
@@ -309,30 +341,10 @@ match_search_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, 
         for (uint32_t i = max(lo, v_hi * 16) + threadIdx.x; i < byte_hi; i += kSearchThreads) sb[kSearchOff + i] = in[wb + i];
         for (uint32_t i = byte_hi + threadIdx.x; i < kSearchBytes - kSearchOff; i += kSearchThreads) sb[kSearchOff + i] = 0;
         const uint32_t link_hi = (uint32_t)min((int64_t)(kSearchLinks - kSearchOff), (int64_t)n - wb);
-        const uint32_t lv_lo = lo / 8, lv_hi = link_hi / 8;
-        const uint4* lsrc = reinterpret_cast<const uint4*>(link + wb);
-        for (uint32_t i = lv_lo + threadIdx.x; i < lv_hi; i += kSearchThreads) {
-            const uint4 v = lsrc[i];
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t o[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t slot0 = kSearchOff + i * 8 + 2 * k, slot1 = slot0 + 1;
-                const uint32_t l0 = w[k] & 0xffffu, l1 = w[k] >> 16;
-                // a link that leaves the window is farther than 32768 from every tile position: none
-                const uint32_t t0 = (l0 && l0 + kSearchOff <= slot0) ? slot0 - l0 : 0;
-                const uint32_t t1 = (l1 && l1 + kSearchOff <= slot1) ? slot1 - l1 : 0;
-                o[k] = t0 | (t1 << 16);
-            }
-            reinterpret_cast<uint4*>(sl + kSearchOff)[i] = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        for (uint32_t i = max(lo, lv_hi * 8) + threadIdx.x; i < link_hi; i += kSearchThreads) {
-            const uint32_t l = link[wb + i], slot = kSearchOff + i;
-            sl[slot] = (uint16_t)((l && l + kSearchOff <= slot) ? slot - l : 0);
-        }
-        if (threadIdx.x == 0) tile_next = kSearchThreads;  // the first kSearchThreads positions are pre-assigned
+        for (uint32_t i = lo + threadIdx.x; i < link_hi; i += kSearchThreads) sl[kSearchOff + i] = link[wb + i];
+        if (threadIdx.x == 0) tile_next = kSearchThreads;
+        __syncthreads();
     }
-    __syncthreads();
 
     const uint32_t tile_cnt = min(kSearchTile, n - s);  // positions of this tile that exist
     const uint32_t quarter = lv.chain >> 2;
@@ -396,8 +408,8 @@ match_search_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, 
 #pragma unroll
         for (int u = 0; u < kStepsPerRound; u++) {
             if (left) {
-                qi = lds_shared_u16(sl_addr + 2 * qi);
-                if (qi < lim) {  // end of chain, too far, or at/below the slide base
+                qi -= lds_shared_u16(sl_addr + 2 * qi);
+                if ((int32_t)qi < (int32_t)lim) {  // end of chain (kNoLink), too far, or at/below the slide base
                     st = kDone;
                     left = 0;
                 } else if (lds_shared_u8(ro_addr + qi) == cb) {  // may beat the best so far: needs the full compare
@@ -536,14 +548,9 @@ match_search_roll_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_
                 w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
             } else {
                 for (int k = 0; k < 4; k++) {
-                    const uint32_t l0 = p + 2 * k < n ? link[p + 2 * k] : 0u, l1 = p + 2 * k + 1 < n ? link[p + 2 * k + 1] : 0u;
+                    const uint32_t l0 = p + 2 * k < n ? link[p + 2 * k] : 0xffffu, l1 = p + 2 * k + 1 < n ? link[p + 2 * k + 1] : 0xffffu;
                     w[k] = l0 | (l1 << 16);
                 }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {  // distance 0 (none) -> 0xFFFF
-                const uint32_t lo16 = w[k] & 0xffffu, hi16 = w[k] >> 16;
-                w[k] = (lo16 ? lo16 : 0xffffu) | ((hi16 ? hi16 : 0xffffu) << 16);
             }
             *reinterpret_cast<uint4*>(sl + (p & (kRing - 1))) = make_uint4(w[0], w[1], w[2], w[3]);
         }
