@@ -87,6 +87,8 @@ struct DevBuf {
 struct fb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host-to-device slabs, overlapped with the search of earlier slabs
+    cudaEvent_t slab_ev[16] = {};
     uint64_t launches = 0;
     PhaseTimer timer;
     // LZ77 workspace
@@ -155,6 +157,8 @@ int fb200_ctx_create(int device, fb200_ctx** out) {
     if (!c) return FB200_INVALID_ARGUMENT;
     c->device = device;
     FB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : c->slab_ev) FB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     FB_CUDA_CHECK(cudaMalloc(&c->d_scalars, 128));
     FB_CUDA_CHECK(cudaMallocHost(&c->h_scalars, 64));
     *out = c;
@@ -171,6 +175,9 @@ void fb200_ctx_destroy(fb200_ctx* c) {
     c->lit_freq.release(); c->dist_freq.release(); c->d_in.release(); c->d_out.release(); c->m_desc.release();
     if (c->d_scalars) cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    for (auto& e : c->slab_ev)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -229,7 +236,10 @@ static inline size_t footer_size(int container) { return container == FB200_GZIP
 // written bytes (from d_out start).  The checksum of d_in[0..n) is left in c->h_scalars[1].
 static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint8_t* d_in, size_t begin, size_t n,
                                const uint32_t* d_skip, uint32_t nskip, uint8_t* d_out, size_t cap, size_t* end_bytes,
-                               bool final_flush, bool with_header, cudaStream_t st) {
+                               bool final_flush, bool with_header, cudaStream_t st, const uint8_t* h_src = nullptr) {
+    // h_src != nullptr: the bytes [begin, n) still live in (pinned or pageable) host memory at h_src and are
+    // copied to d_in + begin here, in slabs, so that hash links and match search of slab k run while slab k+1
+    // is still crossing PCIe.
     if (container < 0 || container > 2 || begin > n) return FB200_INVALID_ARGUMENT;
     if (((uintptr_t)d_out & 15) != 0) return FB200_INVALID_ARGUMENT;
     const size_t hdr = with_header ? header_size(container) : 0;
@@ -248,8 +258,34 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         if ((rc = ensure_blocks(c, max_blocks))) return rc;
         Lz77Buffers b = lz77_view(c);
         c->timer.begin(st);
-        FB_CUDA_CHECK(lz77_tokenize(b, d_in, (uint32_t)begin, (uint32_t)n, d_skip, nskip, lv, st, &c->timer));
-        c->launches += n > begin ? 9 : 0;
+        constexpr size_t kSlab = 32u << 20, kLag = 8192;  // the search of a slab lags one hash tile behind its copy
+        if (h_src && n - begin > kSlab + kLag) {
+            const size_t first_end = (begin / kSlab + 1) * kSlab;
+            size_t copied = begin, searched = begin;
+            int k = 0;
+            while (copied < n) {
+                const size_t slab_end = copied == begin ? (first_end < n ? first_end : n) : (copied + kSlab < n ? copied + kSlab : n);
+                cudaEvent_t ev = c->slab_ev[k % 16];
+                if (k >= 16) FB_CUDA_CHECK(cudaEventSynchronize(ev));
+                FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in) + copied, h_src + (copied - begin), slab_end - copied,
+                                              cudaMemcpyHostToDevice, c->copy_stream));
+                FB_CUDA_CHECK(cudaEventRecord(ev, c->copy_stream));
+                FB_CUDA_CHECK(cudaStreamWaitEvent(st, ev, 0));
+                const size_t range_end = slab_end == n ? n : slab_end - kLag;
+                FB_CUDA_CHECK(lz77_search_range(b, d_in, (uint32_t)begin, (uint32_t)searched, (uint32_t)range_end, (uint32_t)n, d_skip,
+                                                nskip, lv, st, &c->timer));
+                c->launches += 2;
+                searched = range_end;
+                copied = slab_end;
+                k++;
+            }
+            FB_CUDA_CHECK(lz77_parse(b, d_in, (uint32_t)begin, (uint32_t)n, lv, st, &c->timer));
+            c->launches += 7;
+        } else {
+            if (h_src && n > begin) FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in) + begin, h_src, n - begin, cudaMemcpyHostToDevice, st));
+            FB_CUDA_CHECK(lz77_tokenize(b, d_in, (uint32_t)begin, (uint32_t)n, d_skip, nskip, lv, st, &c->timer));
+            c->launches += n > begin ? 9 : 0;
+        }
         FB_CUDA_CHECK(plan_level_blocks(b.total_tokens, b.cut_rp, (uint32_t)begin, (uint32_t)n, max_blocks,
                                         final_flush ? 1 : 0, c->plans.p, nblocks_dev, st));
         FB_CUDA_CHECK(histogram_tokens(b.tokens, c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, st));
@@ -263,6 +299,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         max_blocks = nslices + (final_flush ? 0 : 1);
         int rc = ensure_blocks(c, max_blocks);
         if (rc) return rc;
+        if (h_src && n > begin) FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in) + begin, h_src, n - begin, cudaMemcpyHostToDevice, st));
         c->timer.begin(st);
         plan_simple_blocks_kernel<<<(max_blocks + 255) / 256, 256, 0, st>>>(begin, n, nslices,
                                                                             mode == FB200_MODE_HUFFMAN ? kHuffmanBlock : 3u,
@@ -348,9 +385,8 @@ int fb200_compress(fb200_ctx* c, int container, int mode, const uint8_t* in, siz
     FB_CUDA_CHECK(c->d_in.ensure(n + 512));
     FB_CUDA_CHECK(c->d_out.ensure(round_up(bound, 16)));
     cudaStream_t st = c->stream;
-    if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
     size_t end = 0;
-    int rc = deflate_body_device(c, container, mode, c->d_in.p, 0, n, nullptr, 0, c->d_out.p, c->d_out.cap, &end, true, true, st);
+    int rc = deflate_body_device(c, container, mode, c->d_in.p, 0, n, nullptr, 0, c->d_out.p, c->d_out.cap, &end, true, true, st, in);
     if (rc) return rc;
     uint8_t footer[8];
     const size_t flen = make_footer(container, (uint32_t)c->h_scalars[1], n, footer);

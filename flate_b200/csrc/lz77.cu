@@ -65,8 +65,8 @@ __device__ __forceinline__ uint32_t part_peers(uint32_t part) {
 }
 
 __global__ void __launch_bounds__(kLinkThreads, 2)
-hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, uint32_t run, const uint32_t* __restrict__ skip,
-                 uint32_t nskip, uint16_t* __restrict__ link) {
+hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_end, uint32_t n, uint32_t run,
+                 const uint32_t* __restrict__ skip, uint32_t nskip, uint16_t* __restrict__ link) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint16_t* head = reinterpret_cast<uint16_t*>(smem_raw);
     uint16_t* lists = reinterpret_cast<uint16_t*>(smem_raw + 65536);          // tile offsets grouped by owner warp, in position order
@@ -78,7 +78,9 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, uin
     // [begin, n) is the segment being compressed (begin > 0 after a sync flush); earlier positions are
     // history: hashed again to prime the table, never re-linked.  `skip` lists history positions that
     // the reference never inserted (the last 3 bytes before each flush point, Lookup.zig:24).
-    const uint32_t ntiles = (n + kLinkTile - 1) / kLinkTile;
+    // links are produced for positions [begin, range_end) (range_end is tile aligned or n); validity of a
+    // position is judged against the stream end n
+    const uint32_t ntiles = (range_end + kLinkTile - 1) / kLinkTile;
     const uint32_t first = begin / kLinkTile + blockIdx.x * run;
     if (first >= ntiles) return;
     const uint32_t last = min(first + run, ntiles);
@@ -288,16 +290,17 @@ enum : uint32_t { kIdle = 0, kStepping = 1, kPending = 2, kDone = 3 };
 
 template <int kStepsPerRound>
 __global__ void __launch_bounds__(kSearchThreads, 2)
-match_search_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, const uint16_t* __restrict__ link,
-                    LevelArgs lv, SearchTune tune, uint32_t* __restrict__ r_full, uint32_t* __restrict__ r_quarter) {
+match_search_kernel(const uint8_t* __restrict__ in, uint32_t seg_begin, uint32_t begin, uint32_t range_end, uint32_t n,
+                    const uint16_t* __restrict__ link, LevelArgs lv, SearchTune tune, uint32_t* __restrict__ r_full,
+                    uint32_t* __restrict__ r_quarter) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t tile_next;
     __shared__ __align__(8) uint64_t stage_bar;
     uint8_t* sb = smem_raw;                                                 // bytes, slot i+16 = position wb+i
     uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + kSearchBytes);    // link (distance, kNoLink = none) per slot
     const uint32_t s = (begin / kSearchTile + blockIdx.x) * kSearchTile;    // first new position (tiles are absolute)
-    r_full -= begin;                                                        // result tables are segment relative
-    r_quarter -= begin;
+    r_full -= seg_begin;                                                    // result tables are segment relative
+    r_quarter -= seg_begin;
     const int64_t wb = (int64_t)s - kHist;                                  // window base (may be < 0)
     const uint32_t lo = wb < 0 ? (uint32_t)(-wb) : 0;                       // first valid window index
     const uint32_t lane = threadIdx.x & 31;
@@ -346,7 +349,7 @@ match_search_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t n, 
         __syncthreads();
     }
 
-    const uint32_t tile_cnt = min(kSearchTile, n - s);  // positions of this tile that exist
+    const uint32_t tile_cnt = min(kSearchTile, range_end - s);  // positions of this tile that are searched in this launch
     const uint32_t quarter = lv.chain >> 2;
     // 32-bit shared-window addresses: explicit ld.shared keeps the address arithmetic out of the hot loop
     uint32_t sb_addr = (uint32_t)__cvta_generic_to_shared(sb);
@@ -973,70 +976,80 @@ emit_tokens_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // host-side launcher
 // ------------------------------------------------------------------------------------------
-cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const uint32_t* d_skip,
-                          uint32_t nskip, const LevelArgs& lv, cudaStream_t st, PhaseTimer* pt) {
+static int g_num_sms = 148;
+static int g_search_steps = 8;
+static SearchTune g_tune{3, 8};
+static int g_use_roll = 0;
+static void lz77_init_once() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    cudaFuncSetAttribute(hash_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinkSmem);
+    cudaFuncSetAttribute(match_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
+    cudaFuncSetAttribute(match_search_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
+    cudaFuncSetAttribute(match_search_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
+    cudaFuncSetAttribute(match_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
+    cudaFuncSetAttribute(match_search_roll_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
+    cudaFuncSetAttribute(match_search_roll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    // development knobs: FB200_TUNE="steps,pend_at,refill_at", FB200_SEARCH=roll (persistent rolling-window kernel)
+    if (const char* e = getenv("FB200_TUNE")) {
+        int a = 0, p = 0, r = 0;
+        if (sscanf(e, "%d,%d,%d", &a, &p, &r) == 3) {
+            g_search_steps = a;
+            g_tune.pend_at = (uint32_t)p;
+            g_tune.refill_at = (uint32_t)r;
+        }
+    }
+    const char* e = getenv("FB200_SEARCH");
+    g_use_roll = (e && e[0] == 'r') ? 1 : 0;
+}
+
+// K1 + K2 for stream positions [from, range_end) of the segment that starts at seg_begin.  `from` and
+// `range_end` must be multiples of 8192 unless they are seg_begin / n.  Lets the caller overlap the
+// host-to-device copy of later parts of the input with the search of earlier parts.
+cudaError_t lz77_search_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t seg_begin, uint32_t from, uint32_t range_end,
+                              uint32_t n, const uint32_t* d_skip, uint32_t nskip, const LevelArgs& lv, cudaStream_t st,
+                              PhaseTimer* pt) {
+    lz77_init_once();
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(hash_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinkSmem);
-        cudaFuncSetAttribute(match_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
-        cudaFuncSetAttribute(match_search_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
-        cudaFuncSetAttribute(match_search_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
-        cudaFuncSetAttribute(match_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
-        attr_set = true;
+    if (range_end <= from) return cudaSuccess;
+    const uint32_t ntiles = (range_end + kLinkTile - 1) / kLinkTile - from / kLinkTile;
+    // run length: long enough to amortise the 4 warm-up tiles, short enough to fill the GPU
+    const uint32_t run = ntiles >= 32 * 600 ? 32 : ntiles >= 8 * 600 ? 16 : 8;
+    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, from, range_end, n, run, d_skip, nskip, b.link);
+    pt->mark(st, kPhLink);
+    if (g_use_roll && from == seg_begin && range_end == n) {
+        const uint32_t epochs = (n + kEpoch - 1) / kEpoch - from / kEpoch;
+        const uint32_t run_epochs = (epochs + g_num_sms - 1) / g_num_sms;
+        const uint32_t rgrid = (epochs + run_epochs - 1) / run_epochs;
+        if (g_search_steps == 4) match_search_roll_kernel<4><<<rgrid, kRollThreads, kRollSmem, st>>>(d_in, from, n, b.link, lv, g_tune, run_epochs, b.r_full, b.r_quarter);
+        else match_search_roll_kernel<8><<<rgrid, kRollThreads, kRollSmem, st>>>(d_in, from, n, b.link, lv, g_tune, run_epochs, b.r_full, b.r_quarter);
+    } else {
+        const uint32_t grid = (range_end + kSearchTile - 1) / kSearchTile - from / kSearchTile;
+#define FB_LAUNCH_SEARCH(K) match_search_kernel<K><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, seg_begin, from, range_end, n, b.link, lv, g_tune, b.r_full, b.r_quarter)
+        if (g_search_steps == 2) FB_LAUNCH_SEARCH(2);
+        else if (g_search_steps == 4) FB_LAUNCH_SEARCH(4);
+        else if (g_search_steps == 16) FB_LAUNCH_SEARCH(16);
+        else FB_LAUNCH_SEARCH(8);
+#undef FB_LAUNCH_SEARCH
     }
+    pt->mark(st, kPhSearch);
+    return cudaGetLastError();
+}
+
+// K3: lazy parse + token emission of the segment [begin, n) from the match tables.
+cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const LevelArgs& lv,
+                       cudaStream_t st, PhaseTimer* pt) {
+    PhaseTimer dummy;
+    if (!pt) pt = &dummy;
     if (n == begin) {
         cudaMemsetAsync(b.total_tokens, 0, sizeof(uint32_t), st);
         return cudaGetLastError();
     }
-    const uint32_t ntiles = (n + kLinkTile - 1) / kLinkTile - begin / kLinkTile;
-    // run length: long enough to amortise the 4 warm-up tiles, short enough to fill the GPU
-    const uint32_t run = ntiles >= 32 * 600 ? 32 : ntiles >= 8 * 600 ? 16 : 8;
-    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, begin, n, run, d_skip, nskip, b.link);
-    pt->mark(st, kPhLink);
-    {
-        // development knob: FB200_TUNE="steps,pend_at,refill_at"
-        static int steps = 8;
-        static SearchTune tune{3, 8};
-        static bool tune_read = false;
-        if (!tune_read) {
-            tune_read = true;
-            if (const char* e = getenv("FB200_TUNE")) {
-                int a = 0, p = 0, r = 0;
-                if (sscanf(e, "%d,%d,%d", &a, &p, &r) == 3) {
-                    steps = a;
-                    tune.pend_at = (uint32_t)p;
-                    tune.refill_at = (uint32_t)r;
-                }
-            }
-        }
-        static int use_roll = -1;
-        static int num_sms = 148;
-        if (use_roll < 0) {
-            const char* e = getenv("FB200_SEARCH");
-            use_roll = (e && e[0] == 'r') ? 1 : 0;  // FB200_SEARCH=roll selects the persistent rolling-window kernel
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaFuncSetAttribute(match_search_roll_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
-            cudaFuncSetAttribute(match_search_roll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
-        }
-        if (use_roll) {
-            const uint32_t epochs = (n + kEpoch - 1) / kEpoch - begin / kEpoch;
-            const uint32_t run_epochs = (epochs + num_sms - 1) / num_sms;
-            const uint32_t rgrid = (epochs + run_epochs - 1) / run_epochs;
-            if (steps == 4) match_search_roll_kernel<4><<<rgrid, kRollThreads, kRollSmem, st>>>(d_in, begin, n, b.link, lv, tune, run_epochs, b.r_full, b.r_quarter);
-            else match_search_roll_kernel<8><<<rgrid, kRollThreads, kRollSmem, st>>>(d_in, begin, n, b.link, lv, tune, run_epochs, b.r_full, b.r_quarter);
-        } else {
-        const uint32_t grid = (n + kSearchTile - 1) / kSearchTile - begin / kSearchTile;
-        if (steps == 2) match_search_kernel<2><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
-        else if (steps == 16) match_search_kernel<16><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
-        else if (steps == 8) match_search_kernel<8><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
-        else match_search_kernel<4><<<grid, kSearchThreads, kSearchSmem, st>>>(d_in, begin, n, b.link, lv, tune, b.r_full, b.r_quarter);
-        }
-    }
-    pt->mark(st, kPhSearch);
     // everything after the match search works in segment-relative positions
     const uint8_t* d_seg = d_in + begin;
     n -= begin;
@@ -1055,6 +1068,13 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t be
     emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_seg, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp);
     pt->mark(st, kPhEmit);
     return cudaGetLastError();
+}
+
+cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const uint32_t* d_skip,
+                          uint32_t nskip, const LevelArgs& lv, cudaStream_t st, PhaseTimer* pt) {
+    cudaError_t e = lz77_search_range(b, d_in, begin, begin, n, n, d_skip, nskip, lv, st, pt);
+    if (e != cudaSuccess) return e;
+    return lz77_parse(b, d_in, begin, n, lv, st, pt);
 }
 
 }  // namespace fb

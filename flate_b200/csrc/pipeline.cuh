@@ -75,6 +75,13 @@ struct Lz77Buffers {
 cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const uint32_t* d_skip,
                           uint32_t nskip, const LevelArgs& lv, cudaStream_t st, PhaseTimer* pt = nullptr);
 
+// the two halves of lz77_tokenize, for callers that overlap the input copy with the search
+cudaError_t lz77_search_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t seg_begin, uint32_t from, uint32_t range_end,
+                              uint32_t n, const uint32_t* d_skip, uint32_t nskip, const LevelArgs& lv, cudaStream_t st,
+                              PhaseTimer* pt = nullptr);
+cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const LevelArgs& lv,
+                       cudaStream_t st, PhaseTimer* pt = nullptr);
+
 // ---- block writer ----
 enum WriteKind : uint32_t { kWrite = 0, kDynamicBlock = 1, kHuffmanBlock = 2 };  // block_writer.zig:307,395,524
 

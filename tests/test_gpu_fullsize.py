@@ -54,6 +54,14 @@ def test_c2_gzip_footer_at_full_size(ctx, text256):
     assert int.from_bytes(out[-4:], "little") == 128 * MIB
 
 
+def test_host_path_slab_overlap_equals_device_path(ctx, text256):
+    """fb200_compress copies the input in 32 MiB slabs and searches slab k while slab k+1 is in flight;
+    the result must not depend on that."""
+    n = 96 * MIB + 12345
+    data = text256[:n]
+    assert ctx.compress(data, 0, 6) == _device_compress(ctx, data, 6)
+
+
 def test_c5_huffman_only_1GiB_roundtrip(ctx):
     """configs[4] shape (random + zeros mix, stored and dynamic blocks alternating), 1 GiB per GPU."""
     from flate_b200 import synth
