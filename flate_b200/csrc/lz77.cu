@@ -350,6 +350,7 @@ match_search_kernel(const uint8_t* __restrict__ in, uint32_t seg_begin, uint32_t
     }
 
     const uint32_t tile_cnt = min(kSearchTile, range_end - s);  // positions of this tile that are searched in this launch
+    const uint32_t slide_J = max(n >> 15, 1u) - 1;             // slides that ever happen for a stream of n bytes
     const uint32_t quarter = lv.chain >> 2;
     // 32-bit shared-window addresses: explicit ld.shared keeps the address arithmetic out of the hot loop
     uint32_t sb_addr = (uint32_t)__cvta_generic_to_shared(sb);
@@ -384,8 +385,10 @@ match_search_kernel(const uint8_t* __restrict__ in, uint32_t seg_begin, uint32_t
         max_len = min(remaining, kMaxMatch);  // SlidingWindow.zig:82
         qi = pi;
         // candidates must satisfy  p - q <= 32768 (deflate.zig:250)  and  q > slide base (:248, pos 0 = none)
-        const int64_t base_slot = (int64_t)slide_base(p, n) - wb + kSearchOff;
-        lim = (uint32_t)max((int64_t)pi - (int64_t)kMaxDist, base_slot + 1);
+        // slide_base(p, n) in 32-bit arithmetic (p, n < 2^31): 32768 * min(max((p + 262) >> 15, 1) - 1, J)
+        const uint32_t jj = max((p + kMinLookahead) >> 15, 1u) - 1;
+        const int32_t base_slot = (int32_t)(min(jj, slide_J) << 15) - (int32_t)wb + (int32_t)kSearchOff;
+        lim = (uint32_t)max((int32_t)pi - (int32_t)kMaxDist, base_slot + 1);
         left = quarter;  // first budget event: the quarter snapshot (deflate.zig:241-245)
         first4 = lds_u32_unaligned(sb, pi);
         ro_addr = sb_addr + 3;  // a useful candidate agrees on byte `ro` = max(best_len, 3)
@@ -837,12 +840,21 @@ __global__ void chunk_entry_kernel(const uint16_t* __restrict__ exits, const uin
 // K3d: walk the orbit of each chunk from its true entry; record arrivals in a bitmap and count
 // the tokens they emit (k literals + 1 match, or 1 literal).
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kMarkThreads = 128;
+constexpr uint32_t kMarkThreads = 256;
+constexpr uint32_t kSub = 256;                    // sub-chunk walked by one lane
+constexpr uint32_t kSubs = kChunk / kSub;         // 16 walkers per chunk
 __global__ void __launch_bounds__(kMarkThreads)
 orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* __restrict__ entry,
                   uint32_t* __restrict__ bitmap, uint32_t* __restrict__ chunk_tokens) {
-    __shared__ uint32_t sn[kChunk];  // step | tokens emitted by an arrival here << 16
+    // The orbit inside a chunk is sequential, but once the first arrival in every 256-position
+    // sub-chunk is known the 16 sub-chunks can be walked at the same time.  Those arrivals come from
+    // pointer jumping restricted to sub-chunks (jump[i] = first arrival at or past the end of i's
+    // sub-chunk), chained from the chunk's true entry.
+    __shared__ uint32_t sn[kChunk];    // step | tokens emitted by an arrival here << 16
+    __shared__ uint16_t jump[kChunk];
     __shared__ uint32_t bits[kChunk / 32];
+    __shared__ uint32_t sub_entry[kSubs];
+    __shared__ uint32_t sub_tokens[kSubs];
     const uint32_t c = blockIdx.x;
     const uint32_t cs = c * kChunk;
     for (uint32_t i = threadIdx.x; i < kChunk; i += kMarkThreads) {
@@ -854,17 +866,38 @@ orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* _
             t = (v >> 16) ? (v & 255u) + 1 : 1;
         }
         sn[i] = s | (t << 16);
+        jump[i] = (uint16_t)(i + s);  // <= 4095 + 515
     }
     for (uint32_t i = threadIdx.x; i < kChunk / 32; i += kMarkThreads) bits[i] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {  // the orbit is sequential; many chunks walk concurrently
-        uint32_t i = entry[c];
+    while (true) {
+        bool pending = false;
+        for (uint32_t i = threadIdx.x; i < kChunk; i += kMarkThreads) {
+            const uint32_t t = jump[i];
+            if (t < (i | (kSub - 1)) + 1) {  // still inside i's sub-chunk
+                jump[i] = jump[t];           // racing reads see some power of f: still correct
+                pending = true;
+            }
+        }
+        if (!__syncthreads_or(pending)) break;
+    }
+    if (threadIdx.x == 0) {
+        uint32_t e = entry[c];
+        for (uint32_t k = 0; k < kSubs; k++) {
+            sub_entry[k] = e;
+            if (e < (k + 1) * kSub) e = jump[e];  // else: a long match jumps over this sub-chunk entirely
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kSubs) {
+        const uint32_t k = threadIdx.x;
+        const uint32_t lim = min(min((k + 1) * kSub, kChunk), n > cs ? n - cs : 0u);
+        uint32_t i = sub_entry[k];
         uint32_t total = 0, word = 0xffffffffu, acc = 0;
-        const uint32_t lim = min(kChunk, n > cs ? n - cs : 0u);
         while (i < lim) {
             const uint32_t v = sn[i];
             if ((i >> 5) != word) {
-                if (word != 0xffffffffu) bits[word] = acc;
+                if (word != 0xffffffffu) bits[word] = acc;  // words belong to exactly one sub-chunk
                 word = i >> 5;
                 acc = 0;
             }
@@ -873,9 +906,14 @@ orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* _
             i += v & 0xffffu;
         }
         if (word != 0xffffffffu) bits[word] = acc;
-        chunk_tokens[c] = total;
+        sub_tokens[k] = total;
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (uint32_t k = 0; k < kSubs; k++) total += sub_tokens[k];
+        chunk_tokens[c] = total;
+    }
     for (uint32_t i = threadIdx.x; i < kChunk / 32; i += kMarkThreads) bitmap[(size_t)c * (kChunk / 32) + i] = bits[i];
 }
 

@@ -1045,7 +1045,9 @@ static inline uint32_t br_peek(const BitReader* r, unsigned nb) {
     uint64_t v = 0;
     size_t byte = (size_t)(r->bitpos >> 3);
     unsigned off = (unsigned)(r->bitpos & 7);
-    for (unsigned i = 0; i < 6 && byte + i < r->n; i++) v |= (uint64_t)r->p[byte + i] << (8 * i);
+    if (byte + 8 <= r->n) memcpy(&v, r->p + byte, 8); /* little-endian host */
+    else
+        for (unsigned i = 0; i < 6 && byte + i < r->n; i++) v |= (uint64_t)r->p[byte + i] << (8 * i);
     v >>= off;
     return (uint32_t)(v & ((nb >= 32) ? 0xffffffffu : ((1u << nb) - 1)));
 }
@@ -1075,6 +1077,7 @@ static inline uint32_t rev_bits(uint32_t v, unsigned n) {
     return o;
 }
 
+static inline uint32_t rev_bits(uint32_t v, unsigned n);
 /* huffman_decoder.zig: canonical code over (code_bits, alphabet index); the 9-bit table + linked
  * lists (:64-118) are not observable, only code assignment order, completeness rules and the
  * InvalidCode-on-miss behaviour of find (:156-175). */
@@ -1082,6 +1085,9 @@ typedef struct {
     uint16_t count[16];
     uint16_t symbol[NUM_LIT];
     int max_bits;
+    /* direct table over the first 9 stream bits (the reference uses lookup_bits = 9 for the literal and
+     * distance decoders, huffman_decoder.zig:31-33): symbol << 4 | code length, 0 = longer code / no code */
+    uint16_t fast[512];
 } HuffDec;
 
 /* huffman_decoder.zig:126-153 checkCompletnes; alphabet 286 => lit, max_code_bits 15 or 7 */
@@ -1111,10 +1117,28 @@ static int hd_generate(HuffDec* h, const uint8_t* lens, int n, int alphabet, int
     for (int len = 1; len < 16; len++) offs[len + 1] = (uint16_t)(offs[len] + h->count[len]);
     for (int i = 0; i < n; i++)
         if (lens[i]) h->symbol[offs[lens[i]]++] = (uint16_t)i;
+    memset(h->fast, 0, sizeof h->fast);
+    {
+        unsigned code = 0, index = 0;
+        for (int len = 1; len <= 9 && len <= max_code_bits; len++) {
+            for (unsigned k = 0; k < h->count[len]; k++) {
+                unsigned rev = rev_bits(code + k, (unsigned)len);
+                for (unsigned e = rev; e < 512; e += 1u << len) h->fast[e] = (uint16_t)((h->symbol[index + k] << 4) | len);
+            }
+            code = (code + h->count[len]) << 1;
+            index += h->count[len];
+        }
+    }
     return FO_OK;
 }
 /* find on the zero-padded peek; returns symbol index and code length, or InvalidCode */
 static int hd_find(const HuffDec* h, uint32_t peek_lsb_first, int* sym, int* nbits) {
+    const uint16_t e = h->fast[peek_lsb_first & 511];
+    if (e) {
+        *sym = e >> 4;
+        *nbits = e & 15;
+        return FO_OK;
+    }
     int code = 0, first = 0, index = 0;
     for (int len = 1; len <= h->max_bits; len++) {
         code |= (int)(peek_lsb_first & 1);
