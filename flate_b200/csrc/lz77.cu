@@ -52,16 +52,16 @@ __device__ __forceinline__ uint32_t hash_be(uint32_t le32) {
     return (__byte_perm(le32, 0, 0x0123) * 0x9E3779B1u) >> 17;
 }
 
-// lanes of the warp whose `part` (0..15) equals mine; 16 ballots pipeline far better than MATCH.ANY,
-// whose latency grows with the number of distinct values
+// lanes of the warp whose `part` (0..15) equals mine, from one ballot per bit of `part` (MATCH.ANY's
+// latency grows with the number of distinct values; 16 per-value ballots cost 3x the instructions)
 __device__ __forceinline__ uint32_t part_peers(uint32_t part) {
-    uint32_t mine = 0;
+    uint32_t peers = __ballot_sync(0xffffffffu, part < kLinkWarps);
 #pragma unroll
-    for (uint32_t k = 0; k < kLinkWarps; k++) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, part == k);
-        if (part == k) mine = bal;
+    for (uint32_t b = 0; b < 4; b++) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (part >> b) & 1u);
+        peers &= ((part >> b) & 1u) ? bal : ~bal;
     }
-    return mine;
+    return peers;
 }
 
 __global__ void __launch_bounds__(kLinkThreads, 2)
@@ -1056,8 +1056,11 @@ cudaError_t lz77_search_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_
     if (!pt) pt = &dummy;
     if (range_end <= from) return cudaSuccess;
     const uint32_t ntiles = (range_end + kLinkTile - 1) / kLinkTile - from / kLinkTile;
-    // run length: long enough to amortise the 4 warm-up tiles, short enough to fill the GPU
-    const uint32_t run = ntiles >= 32 * 600 ? 32 : ntiles >= 8 * 600 ? 16 : 8;
+    // run length: long enough to amortise the 4 warm-up tiles (<= 32 tiles), and chosen so that the grid is
+    // close to a whole number of waves of 2 CTAs per SM
+    const uint32_t slots = 2 * (uint32_t)g_num_sms;
+    const uint32_t waves = (ntiles + slots * 32 - 1) / (slots * 32);
+    const uint32_t run = max(1u, (ntiles + slots * waves - 1) / (slots * waves));
     hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, from, range_end, n, run, d_skip, nskip, b.link);
     pt->mark(st, kPhLink);
     if (g_use_roll && from == seg_begin && range_end == n) {
