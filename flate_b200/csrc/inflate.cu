@@ -494,43 +494,81 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                 uint32_t nq = 0;
                 const uint64_t pos0 = pos;  // uniform here; lane 0 runs ahead from it
                 if (lane == 0) {
+                    // local, 32-bit state: every instruction here is on the member's critical path
                     const uint64_t stop = min(min(cap, W.flushed + kFlushAt), pos + kBatchSpan);
-                    while (pos < stop && nq < kQueue) {
-                        if (bc.cnt <= 32) bc.refill();
+                    const uint32_t stop32 = (uint32_t)(stop - pos0);          // < 2^13
+                    const uint32_t room32 = (uint32_t)min(cap - pos0, (uint64_t)0x7fffffffu);
+                    const uint32_t slot0 = (uint32_t)pos0 + W.A;
+                    const uint64_t reach = md.hist + pos0;                     // bytes a match may reach back from pos0
+                    uint64_t buf = bc.buf;
+                    uint32_t cnt = bc.cnt;
+                    const uint8_t* nxp = bc.next;
+                    const uint8_t* const endp = bc.end;
+                    uint32_t p32 = 0;
+                    while (p32 < stop32 && nq < kQueue) {
+                        if (cnt <= 32) {
+                            if ((((uintptr_t)nxp) & 3) == 0 && nxp + 4 <= endp) {
+                                buf |= (uint64_t)__ldg(reinterpret_cast<const uint32_t*>(nxp)) << cnt;
+                                nxp += 4;
+                                cnt += 32;
+                            } else {
+                                while (cnt <= 56 && nxp < endp) {
+                                    buf |= (uint64_t)(*nxp++) << cnt;
+                                    cnt += 8;
+                                }
+                            }
+                        }
                         uint32_t e;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_fast_addr + (((uint32_t)bc.buf & ((1u << kLitFast) - 1)) << 2)));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_fast_addr + (((uint32_t)buf & ((1u << kLitFast) - 1)) << 2)));
                         const uint32_t nb = e & 15, sym = (e >> 4) & 511u;
-                        if (nb == 0 || nb > bc.cnt) break;
+                        if (nb == 0 || nb > cnt) break;
                         if (sym < 256) {
-                            bc.buf >>= nb;
-                            bc.cnt -= nb;
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_addr + (((uint32_t)pos + W.A) & (kRing - 1))), "r"(sym));
-                            pos++;
+                            buf >>= nb;
+                            cnt -= nb;
+                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_addr + ((slot0 + p32) & (kRing - 1))), "r"(sym));
+                            p32++;
                             continue;
                         }
                         if (sym == 256 || sym > 285) break;
-                        // length + distance, on a copy of the cursor so that an irregular case leaves it untouched
+                        // length + distance on copies, so that an irregular case leaves the cursor untouched
                         const uint32_t leb = (e >> 13) & 15;
-                        if (nb + leb > bc.cnt) break;
-                        BitCursor t = bc;
-                        const uint32_t length = (e >> 17) + (((uint32_t)(t.buf >> nb)) & ((1u << leb) - 1));
-                        t.buf >>= nb + leb;
-                        t.cnt -= nb + leb;
-                        if (t.cnt <= 32) t.refill();
+                        if (nb + leb > cnt) break;
+                        uint64_t tbuf = buf >> nb;
+                        const uint32_t length = (e >> 17) + ((uint32_t)tbuf & ((1u << leb) - 1));
+                        tbuf >>= leb;
+                        uint32_t tcnt = cnt - nb - leb;
+                        const uint8_t* tnx = nxp;
+                        if (tcnt <= 32) {
+                            if ((((uintptr_t)tnx) & 3) == 0 && tnx + 4 <= endp) {
+                                tbuf |= (uint64_t)__ldg(reinterpret_cast<const uint32_t*>(tnx)) << tcnt;
+                                tnx += 4;
+                                tcnt += 32;
+                            } else {
+                                while (tcnt <= 56 && tnx < endp) {
+                                    tbuf |= (uint64_t)(*tnx++) << tcnt;
+                                    tcnt += 8;
+                                }
+                            }
+                        }
                         uint32_t de;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(de) : "r"(dist_fast_addr + (((uint32_t)t.buf & ((1u << kDistFast) - 1)) << 2)));
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(de) : "r"(dist_fast_addr + (((uint32_t)tbuf & ((1u << kDistFast) - 1)) << 2)));
                         const uint32_t dnb = de & 15, deb = (de >> 13) & 15;
-                        if (dnb == 0 || ((de >> 4) & 511u) > 29 || dnb + deb > t.cnt) break;
-                        const uint32_t distance = (de >> 17) + (((uint32_t)(t.buf >> dnb)) & ((1u << deb) - 1));
-                        if (md.hist + pos < distance || pos + length > cap) break;
-                        t.buf >>= dnb + deb;
-                        t.cnt -= dnb + deb;
-                        bc = t;
-                        T.queue[2 * nq] = (uint32_t)pos;
+                        if (dnb == 0 || ((de >> 4) & 511u) > 29 || dnb + deb > tcnt) break;
+                        tbuf >>= dnb;
+                        const uint32_t distance = (de >> 17) + ((uint32_t)tbuf & ((1u << deb) - 1));
+                        if (reach + p32 < distance || p32 + length > room32) break;
+                        buf = tbuf >> deb;
+                        cnt = tcnt - dnb - deb;
+                        nxp = tnx;
+                        T.queue[2 * nq] = p32;
                         T.queue[2 * nq + 1] = (length << 16) | (distance - 1);
                         nq++;
-                        pos += length;
+                        p32 += length;
                     }
+                    bc.buf = buf;
+                    bc.cnt = cnt;
+                    bc.next = nxp;
+                    pos = pos0 + p32;
                 }
                 __syncwarp();
                 nq = BCAST(nq);
@@ -538,7 +576,7 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                     for (uint32_t k = 0; k < nq; k++) {
                         const uint32_t qlo = T.queue[2 * k], w1 = T.queue[2 * k + 1];
                         const uint32_t q_len = w1 >> 16, q_dist = (w1 & 0xffffu) + 1;
-                        const uint64_t qpos = pos0 + (uint32_t)(qlo - (uint32_t)pos0);  // the batch spans < 4 GiB
+                        const uint64_t qpos = pos0 + qlo;  // queue positions are relative to the batch start
                         if (q_dist <= kRing - kBatchSpan - 512 && q_dist <= qpos) {
                             const uint32_t from = (uint32_t)qpos - q_dist;
                             if (q_dist >= q_len) {

@@ -13,7 +13,7 @@ from flate_b200 import synth  # noqa: E402
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 level = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 ctx = flate_b200.Context(0)
-d = synth.enwik_like(mib << 20, seed=19)
+d = synth.enwik_like(mib << 20, seed=19) if level >= 4 else synth.random_zero_mix(mib << 20)
 t_in = torch.from_numpy(d).cuda()
 cap = ctx.lib.fb200_compress_bound(d.size, level) + 64
 t_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
