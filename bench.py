@@ -18,7 +18,6 @@ inflate side (config C3 shape: 1 MiB gzip members, 1 GiB of plain output at N = 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -44,51 +43,53 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~5 ms)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
         self.index = index
-        self.rows = []
-        self.proc = None
-
-    def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.sm = []
+        self.mask = 0
+        self.max_mhz = None
+        self.stop_flag = False
+        self.thread = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for nm, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        sm = sorted(self.sm)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
                 "samples": len(sm)}
 
 
