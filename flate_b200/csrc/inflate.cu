@@ -572,21 +572,39 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                 }
                 __syncwarp();
                 nq = BCAST(nq);
-                if (nq) {
-                    for (uint32_t k = 0; k < nq; k++) {
-                        const uint32_t qlo = T.queue[2 * k], w1 = T.queue[2 * k + 1];
-                        const uint32_t q_len = w1 >> 16, q_dist = (w1 & 0xffffu) + 1;
+                // Resolve the queue: four matches at a time, eight lanes each.  A match may only run together
+                // with earlier ones of its group if its source ends before the group's first destination
+                // (conservative); otherwise it starts the next group.
+                for (uint32_t k = 0; k < nq;) {
+                    const uint32_t g = lane >> 3, sub = lane & 7;
+                    const bool valid = k + g < nq;
+                    uint32_t qlo = 0, q_len = 0, q_dist = 1;
+                    if (valid) {
+                        qlo = T.queue[2 * (k + g)];
+                        const uint32_t w1 = T.queue[2 * (k + g) + 1];
+                        q_len = w1 >> 16;
+                        q_dist = (w1 & 0xffffu) + 1;
+                    }
+                    const uint32_t first_lo = __shfl_sync(0xffffffffu, qlo, 0);
+                    // source bytes actually read: [qpos - dist, qpos - dist + min(len, dist))
+                    const int64_t src_end = (int64_t)qlo - q_dist + min(q_len, q_dist);
+                    const bool conflict = valid && g > 0 && src_end > (int64_t)first_lo;
+                    const uint32_t cmask = __ballot_sync(0xffffffffu, conflict);
+                    const uint32_t take = cmask ? (uint32_t)(__ffs(cmask) - 1) >> 3 : min(4u, nq - k);
+                    if (valid && g < take) {
                         const uint64_t qpos = pos0 + qlo;  // queue positions are relative to the batch start
                         if (q_dist <= kRing - kBatchSpan - 512 && q_dist <= qpos) {
-                            const uint32_t from = (uint32_t)qpos - q_dist;
+                            const uint32_t from = (uint32_t)qpos - q_dist + W.A, to = (uint32_t)qpos + W.A;
                             if (q_dist >= q_len) {
-                                for (uint32_t i = lane; i < q_len; i += 32) W.ring[W.slot(qpos + i)] = W.ring[((from + i) + W.A) & (kRing - 1)];
+                                for (uint32_t i = sub; i < q_len; i += 8) W.ring[(to + i) & (kRing - 1)] = W.ring[(from + i) & (kRing - 1)];
                             } else {
-                                for (uint32_t i = lane; i < q_len; i += 32)
-                                    W.ring[W.slot(qpos + i)] = W.ring[((from + i % q_dist) + W.A) & (kRing - 1)];
+                                for (uint32_t i = sub; i < q_len; i += 8)
+                                    W.ring[(to + i) & (kRing - 1)] = W.ring[(from + i % q_dist) & (kRing - 1)];
                             }
                         } else {
-                            for (uint32_t i = lane; i < q_len; i += 32) {
+                            // far match, or one that reaches into an earlier member's output: the source left the ring
+                            // but was drained to HBM long ago (pending <= kFlushAt + kBatchSpan + 258)
+                            for (uint32_t i = sub; i < q_len; i += 8) {
                                 const int64_t sp = (int64_t)qpos - q_dist + (q_dist >= q_len ? i : i % q_dist);
                                 uint8_t b;
                                 if (sp >= (int64_t)W.flushed) b = W.ring[W.slot((uint64_t)sp)];
@@ -594,8 +612,9 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                                 W.ring[W.slot(qpos + i)] = b;
                             }
                         }
-                        __syncwarp();
                     }
+                    __syncwarp();
+                    k += take;
                 }
                 uint32_t ev_len = 0, ev_dist = 0;  // match event (len > 0); otherwise flush / end of block / error
                 if (lane == 0) {
