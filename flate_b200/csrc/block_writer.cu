@@ -493,7 +493,12 @@ __global__ void scan_block_offsets_kernel(BlockDesc* __restrict__ descs, const u
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const uint32_t nb = *nblocks_dev;
     uint64_t off = start_bits;
+    // total_bits[1] = number of blocks, total_bits[2 + i] = start bit of block nb * (i + 1) / kPackParts
+    // (lets the host overlap the device-to-host copy of finished parts with the packing of later ones)
+    total_bits[1] = nb;
     for (uint32_t b = 0; b < nb; b++) {
+        for (uint32_t i = 0; i + 1 < kPackParts; i++)
+            if (b == (uint32_t)(((uint64_t)nb * (i + 1)) / kPackParts)) total_bits[2 + i] = off;
         descs[b].bit_offset = off;
         if (descs[b].type == kStored) {
             off = (off + 3 + 7) & ~(uint64_t)7;
@@ -549,11 +554,11 @@ __device__ __forceinline__ uint32_t token_bits(uint32_t t, const uint32_t* lit, 
 
 __global__ void __launch_bounds__(kPackThreads)
 pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tokens, const BlockDesc* __restrict__ descs,
-                   const uint32_t* __restrict__ nblocks_dev, uint32_t* __restrict__ out) {
+                   const uint32_t* __restrict__ nblocks_dev, uint32_t first_block, uint32_t* __restrict__ out) {
     __shared__ uint32_t lit[kNumLit];
     __shared__ uint32_t dist[kNumDist];
     __shared__ uint32_t warp_sums[kPackThreads / 32];
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = first_block + blockIdx.x;
     if (b >= *nblocks_dev) return;
     const BlockDesc& d = descs[b];
     const uint64_t o = d.bit_offset;
@@ -691,7 +696,13 @@ cudaError_t scan_block_offsets(BlockDesc* descs, const uint32_t* nblocks_dev, ui
 }
 cudaError_t pack_blocks(const uint8_t* in, const uint32_t* tokens, const BlockDesc* descs, const uint32_t* nblocks_dev,
                         uint32_t max_blocks, uint32_t* out_words, cudaStream_t st) {
-    pack_blocks_kernel<<<max_blocks, kPackThreads, 0, st>>>(in, tokens, descs, nblocks_dev, out_words);
+    pack_blocks_kernel<<<max_blocks, kPackThreads, 0, st>>>(in, tokens, descs, nblocks_dev, 0, out_words);
+    return cudaGetLastError();
+}
+cudaError_t pack_blocks_range(const uint8_t* in, const uint32_t* tokens, const BlockDesc* descs, const uint32_t* nblocks_dev,
+                              uint32_t first_block, uint32_t count, uint32_t* out_words, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    pack_blocks_kernel<<<count, kPackThreads, 0, st>>>(in, tokens, descs, nblocks_dev, first_block, out_words);
     return cudaGetLastError();
 }
 

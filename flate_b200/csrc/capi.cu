@@ -100,8 +100,10 @@ struct fb200_ctx {
     DevBuf<uint32_t> lit_freq, dist_freq;
     // staging
     DevBuf<uint8_t> d_in, d_out;
-    uint32_t* d_scalars = nullptr;  // [0] total_tokens [1] nblocks ; +8: total_bits (u64)
-    uint64_t* h_scalars = nullptr;  // pinned: [0] total_bits [1] total_tokens | nblocks<<32
+    // device scalars: u32[0] total_tokens, u32[1] nblocks; u64 at byte 8: total_bits, nblocks, kPackParts-1 part
+    // offsets (written by scan_block_offsets); u32 at byte 64: container checksum; u64[2] at byte 96: Adler scratch
+    uint32_t* d_scalars = nullptr;
+    uint64_t* h_scalars = nullptr;  // pinned: [0] total_bits [1] nblocks [2..] part offsets; [8] checksum
     // inflate workspace
     DevBuf<uint64_t> m_desc;        // member descriptors / results
     std::vector<uint64_t> h_members;
@@ -159,8 +161,8 @@ int fb200_ctx_create(int device, fb200_ctx** out) {
     FB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     FB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& e : c->slab_ev) FB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    FB_CUDA_CHECK(cudaMalloc(&c->d_scalars, 128));
-    FB_CUDA_CHECK(cudaMallocHost(&c->h_scalars, 64));
+    FB_CUDA_CHECK(cudaMalloc(&c->d_scalars, 256));
+    FB_CUDA_CHECK(cudaMallocHost(&c->h_scalars, 128));
     *out = c;
     return FB200_OK;
 }
@@ -236,7 +238,10 @@ static inline size_t footer_size(int container) { return container == FB200_GZIP
 // written bytes (from d_out start).  The checksum of d_in[0..n) is left in c->h_scalars[1].
 static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint8_t* d_in, size_t begin, size_t n,
                                const uint32_t* d_skip, uint32_t nskip, uint8_t* d_out, size_t cap, size_t* end_bytes,
-                               bool final_flush, bool with_header, cudaStream_t st, const uint8_t* h_src = nullptr) {
+                               bool final_flush, bool with_header, cudaStream_t st, const uint8_t* h_src = nullptr,
+                               uint8_t* h_dst = nullptr, size_t h_cap = 0) {
+    // h_dst != nullptr: the packed bytes are also copied to host memory at h_dst, part by part, while later
+    // blocks are still being packed (the caller must not copy them again).
     // h_src != nullptr: the bytes [begin, n) still live in (pinned or pageable) host memory at h_src and are
     // copied to d_in + begin here, in slabs, so that hash links and match search of slab k run while slab k+1
     // is still crossing PCIe.
@@ -258,9 +263,9 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         if ((rc = ensure_blocks(c, max_blocks))) return rc;
         Lz77Buffers b = lz77_view(c);
         c->timer.begin(st);
-        constexpr size_t kSlab = 32u << 20, kLag = 8192;  // the search of a slab lags one hash tile behind its copy
+        constexpr size_t kSlab = 32u << 20, kFirst = 8u << 20, kLag = 8192;  // the search of a slab lags one hash tile behind its copy
         if (h_src && n - begin > kSlab + kLag) {
-            const size_t first_end = (begin / kSlab + 1) * kSlab;
+            const size_t first_end = (begin / kFirst + 1) * kFirst;  // a small first slab shortens the initial wait
             size_t copied = begin, searched = begin;
             int k = 0;
             while (copied < n) {
@@ -322,23 +327,48 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     if (hdr && container == FB200_GZIP) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kGzipHeader, 10, cudaMemcpyHostToDevice, st));
     if (hdr && container == FB200_ZLIB) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kZlibHeader, 2, cudaMemcpyHostToDevice, st));
     c->timer.mark(st, kPhOffsets);
-    FB_CUDA_CHECK(pack_blocks(d_in, tokens, c->descs.p, nblocks_dev, max_blocks, reinterpret_cast<uint32_t*>(d_out), st));
+    bool copied_out = false;
+    if (h_dst) {
+        // one small read-back tells the host the block count, the total size and the part boundaries
+        FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8 * (2 + kPackParts - 1), cudaMemcpyDeviceToHost, st));
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        const uint64_t total_bits = c->h_scalars[0];
+        const uint32_t nb = (uint32_t)c->h_scalars[1];
+        const size_t out_bytes = (size_t)((total_bits + 7) >> 3);
+        if (out_bytes + footer_size(container) > h_cap) return FB200_NO_SPACE_LEFT;
+        size_t byte_lo = 0;
+        for (uint32_t i = 0; i < kPackParts; i++) {
+            const uint32_t b_lo = (uint32_t)(((uint64_t)nb * i) / kPackParts), b_hi = (uint32_t)(((uint64_t)nb * (i + 1)) / kPackParts);
+            FB_CUDA_CHECK(pack_blocks_range(d_in, tokens, c->descs.p, nblocks_dev, b_lo, b_hi - b_lo, reinterpret_cast<uint32_t*>(d_out), st));
+            // bytes below the next part's first bit are final once this part is packed (a shared byte goes with the next part)
+            const size_t byte_hi = i + 1 == kPackParts ? out_bytes : (size_t)(c->h_scalars[2 + i] >> 3);
+            FB_CUDA_CHECK(cudaEventRecord(c->slab_ev[i], st));
+            FB_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->slab_ev[i], 0));
+            if (byte_hi > byte_lo)
+                FB_CUDA_CHECK(cudaMemcpyAsync(h_dst + byte_lo, d_out + byte_lo, byte_hi - byte_lo, cudaMemcpyDeviceToHost, c->copy_stream));
+            byte_lo = byte_hi > byte_lo ? byte_hi : byte_lo;
+        }
+        copied_out = true;
+    } else {
+        FB_CUDA_CHECK(pack_blocks(d_in, tokens, c->descs.p, nblocks_dev, max_blocks, reinterpret_cast<uint32_t*>(d_out), st));
+    }
     c->timer.mark(st, kPhPack);
     c->launches += 4;
     // container checksum of the plain bytes on the device (container.zig:168-206), SURVEY.md §8(f) rank 1
-    uint32_t* sum_dev = c->d_scalars + 4;
+    uint32_t* sum_dev = c->d_scalars + 16;
     if (!final_flush) {
         // the footer is only written by finish()
     } else if (container == FB200_GZIP) {
         FB_CUDA_CHECK(crc32_device(d_in, n, sum_dev, st));
         c->launches += n ? 1 : 0;
     } else if (container == FB200_ZLIB) {
-        FB_CUDA_CHECK(adler32_device(d_in, n, sum_dev, reinterpret_cast<uint64_t*>(c->d_scalars + 8), st));
+        FB_CUDA_CHECK(adler32_device(d_in, n, sum_dev, reinterpret_cast<uint64_t*>(c->d_scalars + 24), st));
         c->launches += n ? 2 : 1;
     }
-    if (container != FB200_RAW && final_flush) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 1, sum_dev, 4, cudaMemcpyDeviceToHost, st));
+    if (container != FB200_RAW && final_flush) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 8, sum_dev, 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (copied_out) FB_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
     c->timer.collect();
     *end_bytes = (size_t)((c->h_scalars[0] + 7) >> 3);
     return FB200_OK;
@@ -370,7 +400,7 @@ int fb200_compress_device(fb200_ctx* c, int container, int mode, const void* d_i
     int rc = deflate_body_device(c, container, mode, (const uint8_t*)d_in, 0, n, nullptr, 0, (uint8_t*)d_out, cap, &end, true, true, st);
     if (rc) return rc;
     uint8_t footer[8];
-    const size_t flen = make_footer(container, (uint32_t)c->h_scalars[1], n, footer);
+    const size_t flen = make_footer(container, (uint32_t)c->h_scalars[8], n, footer);
     if (flen) FB_CUDA_CHECK(cudaMemcpyAsync((uint8_t*)d_out + end, footer, flen, cudaMemcpyHostToDevice, st));
     if (flen) FB_CUDA_CHECK(cudaStreamSynchronize(st));
     *out_len = end + flen;
@@ -386,13 +416,12 @@ int fb200_compress(fb200_ctx* c, int container, int mode, const uint8_t* in, siz
     FB_CUDA_CHECK(c->d_out.ensure(round_up(bound, 16)));
     cudaStream_t st = c->stream;
     size_t end = 0;
-    int rc = deflate_body_device(c, container, mode, c->d_in.p, 0, n, nullptr, 0, c->d_out.p, c->d_out.cap, &end, true, true, st, in);
+    int rc = deflate_body_device(c, container, mode, c->d_in.p, 0, n, nullptr, 0, c->d_out.p, c->d_out.cap, &end, true, true, st, in,
+                                 out, cap);
     if (rc) return rc;
     uint8_t footer[8];
-    const size_t flen = make_footer(container, (uint32_t)c->h_scalars[1], n, footer);
+    const size_t flen = make_footer(container, (uint32_t)c->h_scalars[8], n, footer);
     if (end + flen > cap) return FB200_NO_SPACE_LEFT;
-    FB_CUDA_CHECK(cudaMemcpyAsync(out, c->d_out.p, end, cudaMemcpyDeviceToHost, st));
-    FB_CUDA_CHECK(cudaStreamSynchronize(st));
     memcpy(out + end, footer, flen);
     *out_len = end + flen;
     return FB200_OK;
@@ -663,7 +692,7 @@ static int deflate_emit_segment(fb200_deflate* d, bool final_flush) {
     std::vector<uint8_t> out(out_end + 8);
     if (out_end) FB_CUDA_CHECK(cudaMemcpy(out.data(), c->d_out.p, out_end, cudaMemcpyDeviceToHost));
     size_t total = out_end;
-    if (final_flush) total += make_footer(d->container, (uint32_t)c->h_scalars[1], end, out.data() + out_end);
+    if (final_flush) total += make_footer(d->container, (uint32_t)c->h_scalars[8], end, out.data() + out_end);
     if (total && d->writer(d->user, out.data(), total)) return FB200_NO_SPACE_LEFT;
     // positions with fewer than 4 bytes before the flush point were never hashed (Lookup.zig:24) and
     // stay that way for later segments

@@ -109,5 +109,8 @@ cudaError_t scan_block_offsets(BlockDesc* descs, const uint32_t* nblocks_dev, ui
                                cudaStream_t st);
 cudaError_t pack_blocks(const uint8_t* in, const uint32_t* tokens, const BlockDesc* descs, const uint32_t* nblocks_dev,
                         uint32_t max_blocks, uint32_t* out_words, cudaStream_t st);
+constexpr uint32_t kPackParts = 4;  // scan_block_offsets reports kPackParts-1 interior part boundaries after total_bits
+cudaError_t pack_blocks_range(const uint8_t* in, const uint32_t* tokens, const BlockDesc* descs, const uint32_t* nblocks_dev,
+                              uint32_t first_block, uint32_t count, uint32_t* out_words, cudaStream_t st);
 
 }  // namespace fb
