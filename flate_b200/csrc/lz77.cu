@@ -94,11 +94,16 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
         // ---- 1. hashes of the tile (0xFFFF = not insertable) ----
         if (aligned) {
             const uint32_t* words = reinterpret_cast<const uint32_t*>(in + base);
-            const uint32_t nwords_total = (n - base + 3) / 4;  // readable words from base
+            const uint32_t nwords_total = (n - base + 3) / 4, nwords_full = (n - base) / 4;
             for (uint32_t i = tid; i < kLinkTile / 4; i += kLinkThreads) {
+                // whole words inside the stream; the last, partial word is assembled from its valid bytes
                 uint32_t w0 = 0, w1 = 0;
-                if (i < nwords_total) w0 = words[i];
-                if (i + 1 < nwords_total) w1 = words[i + 1];
+                if (i < nwords_full) w0 = words[i];
+                else if (i < nwords_total)
+                    for (uint32_t j = 0; i * 4 + j < n - base; j++) w0 |= (uint32_t)in[base + i * 4 + j] << (8 * j);
+                if (i + 1 < nwords_full) w1 = words[i + 1];
+                else if (i + 1 < nwords_total)
+                    for (uint32_t j = 0; (i + 1) * 4 + j < n - base; j++) w1 |= (uint32_t)in[base + (i + 1) * 4 + j] << (8 * j);
                 uint32_t hh[4];
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++) {
@@ -190,10 +195,9 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
                 // with the same hash, and only then is the group ordered with MATCH.ANY.
                 const uint32_t code = off + kHist + 1;
                 uint32_t e = 0;
-                if (have) {
-                    e = head[h];
-                    head[h] = (uint16_t)code;
-                }
+                if (have) e = head[h];
+                __syncwarp();  // every lane has the old head before anybody publishes
+                if (have) head[h] = (uint16_t)code;  // same-hash lanes race on purpose: any winner exposes the conflict
                 __syncwarp();
                 const bool lost = have && head[h] != code;
                 uint32_t d = 0;
