@@ -124,7 +124,7 @@ histogram_bytes_kernel(const uint8_t* __restrict__ in, const BlockPlan* __restri
 // sequential parts (the algorithm is a literal restatement of the Go-lineage bitCounts and must
 // stay bit-exact), all lanes share the rank sort.
 // ------------------------------------------------------------------------------------------
-struct LevelInfo {
+struct __align__(16) LevelInfo {
     uint32_t last_freq, next_char_freq, next_pair_freq, needed;
 };
 struct HuffScratch {
@@ -139,28 +139,30 @@ struct HuffScratch {
 
 __device__ __forceinline__ uint32_t bit_reverse(uint32_t v, uint32_t nbits) { return __brev(v) >> (32 - nbits); }
 
-// huffman_encoder.zig:122-247.  list = s.s_freq[0..n) ascending; n >= 3.  Lane 0 only.
-__device__ uint32_t bit_counts_serial(HuffScratch& s, uint32_t n, uint32_t max_bits) {
+// huffman_encoder.zig:122-247.  list = s.s_freq[0..n) ascending; n >= 3.
+// The algorithm is inherently sequential (and must stay a literal restatement to be bit-exact), so
+// the whole warp executes it redundantly on broadcast shared-memory reads; the one O(level) step --
+// copying a row of leaf counts when a pair is taken (:199) -- is spread over the lanes.  Element
+// (l, j < l) of leaf_counts is only ever written and read by lane j, the diagonal and the level
+// records are written identically by every lane, so no synchronisation is needed inside the loop.
+__device__ uint32_t bit_counts_warp(HuffScratch& s, uint32_t n, uint32_t max_bits) {
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t kMaxI32 = 0x7fffffffu;
     if (max_bits > n - 1) max_bits = n - 1;  // :131
-    for (uint32_t l = 0; l < 17; l++) {
-        s.levels[l] = LevelInfo{0, 0, 0, 0};
-        for (uint32_t j = 0; j < 16; j++) s.leaf_counts[l][j] = 0;
-    }
+    for (uint32_t i = lane; i < 17 * 16; i += 32) (&s.leaf_counts[0][0])[i] = 0;
+    for (uint32_t l = lane; l < 17; l += 32) s.levels[l] = LevelInfo{0, 0, 0, 0};
+    __syncwarp();
+    const uint32_t f0 = s.s_freq[0], f1 = s.s_freq[1], f2 = s.s_freq[2];
     for (uint32_t level = 1; level <= max_bits; level++) {  // :144-161
-        s.levels[level].last_freq = s.s_freq[1];
-        s.levels[level].next_char_freq = s.s_freq[2];
-        s.levels[level].next_pair_freq = (uint32_t)s.s_freq[0] + (uint32_t)s.s_freq[1];
-        s.levels[level].needed = 0;
+        s.levels[level] = LevelInfo{f1, f2, level == 1 ? kMaxI32 : f0 + f1, 0};
         s.leaf_counts[level][level] = 2;
-        if (level == 1) s.levels[level].next_pair_freq = kMaxI32;
     }
     s.levels[max_bits].needed = 2 * n - 4;  // :164
     uint32_t level = max_bits;
     while (true) {  // :168-224
-        LevelInfo& l = s.levels[level];
+        LevelInfo l = s.levels[level];
         if (l.next_pair_freq == kMaxI32 && l.next_char_freq == kMaxI32) {  // :170 (leaf sentinel is 65535: not taken)
-            l.needed = 0;
+            s.levels[level].needed = 0;
             s.levels[level + 1].next_pair_freq = kMaxI32;
             level += 1;
             continue;
@@ -173,10 +175,11 @@ __device__ uint32_t bit_counts_serial(HuffScratch& s, uint32_t n, uint32_t max_b
             l.next_char_freq = (next >= n) ? 65535u : (uint32_t)s.s_freq[next];  // :188-192, maxNode :282
         } else {  // :193 next item is a pair from the level below
             l.last_freq = l.next_pair_freq;
-            for (uint32_t j = 0; j < level; j++) s.leaf_counts[level][j] = s.leaf_counts[level - 1][j];
+            if (lane < level) s.leaf_counts[level][lane] = s.leaf_counts[level - 1][lane];  // :199
             s.levels[level - 1].needed = 2;
         }
         l.needed -= 1;
+        s.levels[level] = l;
         if (l.needed == 0) {  // :204
             if (level == max_bits) break;
             s.levels[level + 1].next_pair_freq = prev_freq + l.last_freq;
@@ -188,11 +191,15 @@ __device__ uint32_t bit_counts_serial(HuffScratch& s, uint32_t n, uint32_t max_b
             }
         }
     }
-    uint32_t bits = 1;
-    for (uint32_t lv = max_bits; lv > 0; lv--) {  // :235-245
-        s.bit_count[bits] = s.leaf_counts[max_bits][lv] - s.leaf_counts[max_bits][lv - 1];
-        bits++;
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t bits = 1;
+        for (uint32_t lv = max_bits; lv > 0; lv--) {  // :235-245
+            s.bit_count[bits] = s.leaf_counts[max_bits][lv] - s.leaf_counts[max_bits][lv - 1];
+            bits++;
+        }
     }
+    __syncwarp();
     return max_bits;
 }
 
@@ -229,8 +236,8 @@ __device__ void huff_generate_warp(HuffScratch& s, const uint16_t* freq, uint32_
         s.s_freq[rank] = s.t_freq[i];
     }
     __syncwarp();
+    const uint32_t mb = bit_counts_warp(s, count, max_bits);
     if (lane == 0) {
-        const uint32_t mb = bit_counts_serial(s, count, max_bits);
         // lengths: the last bit_count[1] symbols of the sorted list get 1 bit, the next bit_count[2] get 2, ...
         uint32_t remaining = count, code = 0;
         for (uint32_t nb = 1; nb <= mb; nb++) {
@@ -490,24 +497,51 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
 // ------------------------------------------------------------------------------------------
 __global__ void scan_block_offsets_kernel(BlockDesc* __restrict__ descs, const uint32_t* __restrict__ nblocks_dev,
                                           uint64_t start_bits, uint64_t* __restrict__ total_bits) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const uint32_t nb = *nblocks_dev;
-    uint64_t off = start_bits;
+    // One warp: descriptors are fetched 32 at a time (the loads overlap), the recurrence itself is run
+    // redundantly by all lanes on shuffled values.
     // total_bits[1] = number of blocks, total_bits[2 + i] = start bit of block nb * (i + 1) / kPackParts
     // (lets the host overlap the device-to-host copy of finished parts with the packing of later ones)
-    total_bits[1] = nb;
-    for (uint32_t b = 0; b < nb; b++) {
-        for (uint32_t i = 0; i + 1 < kPackParts; i++)
-            if (b == (uint32_t)(((uint64_t)nb * (i + 1)) / kPackParts)) total_bits[2 + i] = off;
-        descs[b].bit_offset = off;
-        if (descs[b].type == kStored) {
-            off = (off + 3 + 7) & ~(uint64_t)7;
-            off += 32 + 8ull * descs[b].in_len;
-        } else {
-            off += descs[b].hdr_bits + descs[b].body_bits;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t nb = *nblocks_dev;
+    uint32_t mark[kPackParts - 1];
+#pragma unroll
+    for (uint32_t i = 0; i + 1 < kPackParts; i++) mark[i] = (uint32_t)(((uint64_t)nb * (i + 1)) / kPackParts);
+    uint64_t off = start_bits;
+    for (uint32_t base = 0; base < nb; base += 32) {
+        const uint32_t b = base + lane;
+        uint32_t type = kFixed, in_len = 0;
+        uint64_t bits = 0;
+        if (b < nb) {
+            type = descs[b].type;
+            in_len = descs[b].in_len;
+            bits = descs[b].hdr_bits + descs[b].body_bits;
+        }
+        const uint32_t cnt = min(32u, nb - base);
+        uint64_t my_off = 0;
+        for (uint32_t j = 0; j < cnt; j++) {
+            const uint32_t t = __shfl_sync(0xffffffffu, type, j);
+            const uint32_t len_j = __shfl_sync(0xffffffffu, in_len, j);
+            const uint64_t bits_j = __shfl_sync(0xffffffffu, (unsigned long long)bits, j);
+            if (j == lane) my_off = off;
+            if (t == kStored) {
+                off = (off + 3 + 7) & ~(uint64_t)7;
+                off += 32 + 8ull * len_j;
+            } else {
+                off += bits_j;
+            }
+        }
+        if (b < nb) {
+            descs[b].bit_offset = my_off;
+#pragma unroll
+            for (uint32_t i = 0; i + 1 < kPackParts; i++)
+                if (b == mark[i]) total_bits[2 + i] = my_off;
         }
     }
-    *total_bits = off;
+    if (lane == 0) {
+        total_bits[0] = off;
+        total_bits[1] = nb;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -573,6 +607,17 @@ pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
         const uint8_t* src = in + d.in_begin;
         const uint64_t w0 = a >> 2, w1 = (a + total + 3) >> 2;
         for (uint64_t w = w0 + threadIdx.x; w < w1; w += kPackThreads) {
+            const int64_t s0 = (int64_t)(w * 4) - (int64_t)a;  // stream index of the word's first byte
+            if (s0 >= 4 && s0 + 4 <= (int64_t)total) {
+                // interior word: four payload bytes from an arbitrarily aligned source (two aligned loads + funnel shift)
+                const uint8_t* p = src + (s0 - 4);
+                const uint32_t* pw = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+                const uint32_t sh = (uint32_t)((uintptr_t)p & 3) * 8;
+                const uint32_t lo = pw[0];
+                const uint32_t hi = sh ? pw[1] : 0;  // when aligned the second word may lie past the buffer
+                out[w] = __funnelshift_r(lo, hi, sh);
+                continue;
+            }
             uint32_t v = 0;
             bool full = true;
             for (uint32_t j = 0; j < 4; j++) {
