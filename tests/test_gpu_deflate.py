@@ -304,3 +304,55 @@ def test_gzip_zlib_footer_from_device_checksum(ctx, o):
         for container in (1, 2):
             got = ctx.compress(d, container, 6)
             assert got[-8:] == o.compress(d, container, 6)[-8:], (n, container)
+
+
+def _structured(rng, n, kind):
+    if kind == 0:      # tiny alphabet: long hash chains, many equal-length candidates (tie-break order matters)
+        return rng.integers(0, 2, n, dtype=np.uint8).tobytes()
+    if kind == 1:      # periodic with noise: overlapping matches, distance < length
+        period = int(rng.integers(1, 40))
+        base = rng.integers(97, 123, period, dtype=np.uint8)
+        a = np.tile(base, n // period + 1)[:n].copy()
+        flips = rng.integers(0, n, max(1, n // 97))
+        a[flips] = rng.integers(0, 256, flips.size, dtype=np.uint8)
+        return a.tobytes()
+    if kind == 2:      # words from a small dictionary
+        words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(50)]
+        out = bytearray()
+        while len(out) < n:
+            out += words[int(rng.integers(0, 50))] + b" "
+        return bytes(out[:n])
+    from flate_b200 import synth
+    return synth.mixed_small(n, seed=int(rng.integers(1, 1 << 20))).tobytes()
+
+
+def test_differential_around_window_boundaries(ctx, o):
+    """Sizes straddling every special position of the reference's schedule: the 64 KiB fill, the
+    32768-byte slides, the 262-byte look-ahead reserve (SlidingWindow.zig:13), 65535-byte stored/huffman
+    slices and the 32768-token block cut."""
+    rng = np.random.default_rng(2024)
+    specials = [32768, 65274, 65535, 65536, 98042, 98304, 131072]
+    sizes = sorted({max(0, s + d) for s in specials for d in (-263, -4, -1, 0, 1, 3, 262)})
+    picked = [sizes[i] for i in rng.permutation(len(sizes))[:18]]
+    for i, n in enumerate(picked):
+        d = _structured(rng, n, i % 4)
+        for mode in (4, 6, 9, 1):
+            if mode == 9 and i % 4 == 0 and n > 70000:
+                continue  # binary alphabet at level 9: the oracle walks 4096-deep chains
+            got = ctx.compress(d, 0, mode)
+            want = o.compress(d, 0, mode)
+            assert got == want, (n, i % 4, mode, first_diff(got, want))
+
+
+def test_differential_small_random(ctx, o):
+    rng = np.random.default_rng(77)
+    for i in range(60):
+        n = int(rng.integers(0, 3000))
+        d = _structured(rng, n, i % 4)
+        for mode in (4, 5, 6, 7, 8, 9, 1, 0):
+            got = ctx.compress(d, i % 3, mode)
+            want = o.compress(d, i % 3, mode)
+            assert got == want, (n, i % 4, mode, i % 3, first_diff(got, want))
+        if n:
+            # and the token seam
+            assert ctx.debug_tokens(d, 6).tolist() == o.tokenize(d, 6).tolist()

@@ -189,3 +189,45 @@ def test_puff_cross_check(ctx, o):
         except o.OracleError as e:
             assert not ok
             assert err_name(ctx, b) == e.name
+
+
+def test_differential_corruptions_all_containers(ctx, o):
+    """Random bit flips, truncations and insertions on valid raw/gzip/zlib streams: the error class (or
+    the output) must equal the oracle's for every mutated stream."""
+    import flate_b200
+    rng = np.random.default_rng(99)
+    base_plain = read_golden("rfc1951.txt")[:6000]
+    n_err = n_ok = 0
+    for trial in range(240):
+        container = trial % 3
+        mode = (0, 1, 4, 6, 9)[trial % 5]
+        b = bytearray(o.compress(base_plain[: 500 + (trial * 37) % 5000], container, mode))
+        kind = trial % 4
+        if kind == 0:
+            for _ in range(1 + trial % 3):
+                b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:
+            del b[int(rng.integers(1, len(b))):]
+        elif kind == 2:
+            b.insert(int(rng.integers(0, len(b))), int(rng.integers(0, 256)))
+        else:
+            i = int(rng.integers(0, len(b)))
+            b[i] = int(rng.integers(0, 256))
+        data = bytes(b)
+        try:
+            want, want_used = o.decompress(data, container, cap=1 << 20)
+            want_err = None
+        except o.OracleError as e:
+            want_err = e.name
+        try:
+            got, used = ctx.decompress(data, container, cap=1 << 20)
+            got_err = None
+        except flate_b200.FlateError as e:
+            got_err = type(e).__name__
+        assert got_err == want_err, (trial, container, mode, kind, got_err, want_err)
+        if want_err is None:
+            assert got == want and used == want_used, trial
+            n_ok += 1
+        else:
+            n_err += 1
+    assert n_err > 100 and n_ok > 5
