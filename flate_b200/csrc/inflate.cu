@@ -819,11 +819,13 @@ __global__ void adler32_finish_kernel(const unsigned long long* __restrict__ acc
 cudaError_t inflate_members(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
                             MemberResult* d_res, cudaStream_t st) {
     if (k == 0) return cudaSuccess;
-    static bool attr_set = false;
+    static bool attr_set[64] = {};  // per device
     const size_t smem = kRing + sizeof(WarpTables);
-    if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaFuncSetAttribute(inflate_members_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     inflate_members_kernel<<<k, 32, smem, st>>>(container, d_in, d_desc, k, d_out, d_res);
     return cudaGetLastError();

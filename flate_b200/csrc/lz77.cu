@@ -1023,9 +1023,13 @@ static int g_search_steps = 8;
 static SearchTune g_tune{3, 8};
 static int g_use_roll = 0;
 static void lz77_init_once() {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    // function attributes are per device: a process may hold contexts on several GPUs
+    static bool done[64] = {};
+    static bool knobs_read = false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return;
+    if (dev >= 0 && dev < 64) done[dev] = true;
     cudaFuncSetAttribute(hash_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinkSmem);
     cudaFuncSetAttribute(match_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
     cudaFuncSetAttribute(match_search_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
@@ -1033,9 +1037,9 @@ static void lz77_init_once() {
     cudaFuncSetAttribute(match_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
     cudaFuncSetAttribute(match_search_roll_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
     cudaFuncSetAttribute(match_search_roll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (knobs_read) return;
+    knobs_read = true;
     // development knobs: FB200_TUNE="steps,pend_at,refill_at", FB200_SEARCH=roll (persistent rolling-window kernel)
     if (const char* e = getenv("FB200_TUNE")) {
         int a = 0, p = 0, r = 0;
