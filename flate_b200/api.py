@@ -151,6 +151,16 @@ class Context:
                                                       used.ctypes.data, st.ctypes.data, stream)
         return rc, ol, used, st
 
+    # ---- one stream sharded by position over several GPUs ----
+    def shard_search(self, d_in, n, lo, hi, d_nx, level=Level.default, stream=None):
+        _check(self.lib.fb200_deflate_shard_search(self.h, level, d_in, n, lo, hi, d_nx, stream))
+
+    def shard_finish(self, d_in, n, d_nx, d_out, cap, level=Level.default, container=RAW, stream=None):
+        out_len = C.c_size_t(0)
+        _check(self.lib.fb200_deflate_shard_finish(self.h, container, level, d_in, n, d_nx, d_out, cap, C.byref(out_len),
+                                                   stream))
+        return out_len.value
+
     # ---- test seams ----
     def debug_tokens(self, data, level=Level.default):
         a = _as_u8(data)

@@ -239,7 +239,9 @@ static inline size_t footer_size(int container) { return container == FB200_GZIP
 static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint8_t* d_in, size_t begin, size_t n,
                                const uint32_t* d_skip, uint32_t nskip, uint8_t* d_out, size_t cap, size_t* end_bytes,
                                bool final_flush, bool with_header, cudaStream_t st, const uint8_t* h_src = nullptr,
-                               uint8_t* h_dst = nullptr, size_t h_cap = 0) {
+                               uint8_t* h_dst = nullptr, size_t h_cap = 0, const uint32_t* d_nx_given = nullptr) {
+    // d_nx_given != nullptr: the lazy-step table of the whole stream was produced elsewhere (position-sharded
+    // search on several GPUs); only the parse and the block writer run here.
     // h_dst != nullptr: the packed bytes are also copied to host memory at h_dst, part by part, while later
     // blocks are still being packed (the caller must not copy them again).
     // h_src != nullptr: the bytes [begin, n) still live in (pinned or pageable) host memory at h_src and are
@@ -264,7 +266,11 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         Lz77Buffers b = lz77_view(c);
         c->timer.begin(st);
         constexpr size_t kSlab = 32u << 20, kFirst = 8u << 20, kLag = 8192;  // the search of a slab lags one hash tile behind its copy
-        if (h_src && n - begin > kSlab + kLag) {
+        if (d_nx_given) {
+            b.nx = const_cast<uint32_t*>(d_nx_given);
+            FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer));
+            c->launches += n ? 7 : 0;
+        } else if (h_src && n - begin > kSlab + kLag) {
             const size_t first_end = (begin / kFirst + 1) * kFirst;  // a small first slab shortens the initial wait
             size_t copied = begin, searched = begin;
             int k = 0;
@@ -423,6 +429,48 @@ int fb200_compress(fb200_ctx* c, int container, int mode, const uint8_t* in, siz
     const size_t flen = make_footer(container, (uint32_t)c->h_scalars[8], n, footer);
     if (end + flen > cap) return FB200_NO_SPACE_LEFT;
     memcpy(out + end, footer, flen);
+    *out_len = end + flen;
+    return FB200_OK;
+}
+
+// ---- position-sharded single stream ----
+int fb200_deflate_shard_search(fb200_ctx* c, int level, const void* d_in, size_t n, size_t from, size_t to, void* d_nx,
+                               void* stream) {
+    LevelArgs lv;
+    if (!c || !level_args(level, lv) || !d_nx || n > (1ull << 31) || from > to || to > n || (from % 8192) != 0)
+        return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (to == from) return FB200_OK;
+    const size_t span = to - from + 256 + 8192 + 64;
+    FB_CUDA_CHECK(c->link.ensure(n + 64));
+    FB_CUDA_CHECK(c->r_full.ensure(span));
+    FB_CUDA_CHECK(c->r_quarter.ensure(span));
+    Lz77Buffers b = lz77_view(c);
+    c->timer.begin(st);
+    FB_CUDA_CHECK(lz77_shard_search(b, (const uint8_t*)d_in, (uint32_t)from, (uint32_t)to, (uint32_t)n, lv,
+                                    reinterpret_cast<uint32_t*>(d_nx) + from, st, &c->timer));
+    c->launches += 3;
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    c->timer.collect();
+    return FB200_OK;
+}
+
+int fb200_deflate_shard_finish(fb200_ctx* c, int container, int level, const void* d_in, size_t n, const void* d_nx,
+                               void* d_out, size_t cap, size_t* out_len, void* stream) {
+    LevelArgs lv;
+    if (!c || !level_args(level, lv) || !out_len || (!d_nx && n) || n > (1ull << 31)) return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    size_t end = 0;
+    static const uint32_t dummy_nx = 0;
+    int rc = deflate_body_device(c, container, level, (const uint8_t*)d_in, 0, n, nullptr, 0, (uint8_t*)d_out, cap, &end, true, true,
+                                 st, nullptr, nullptr, 0, n ? (const uint32_t*)d_nx : &dummy_nx);
+    if (rc) return rc;
+    uint8_t footer[8];
+    const size_t flen = make_footer(container, (uint32_t)c->h_scalars[8], n, footer);
+    if (flen) FB_CUDA_CHECK(cudaMemcpyAsync((uint8_t*)d_out + end, footer, flen, cudaMemcpyHostToDevice, st));
+    if (flen) FB_CUDA_CHECK(cudaStreamSynchronize(st));
     *out_len = end + flen;
     return FB200_OK;
 }

@@ -809,6 +809,60 @@ lazy_exit_kernel(const uint32_t* __restrict__ r_full, const uint32_t* __restrict
     for (uint32_t i = threadIdx.x; i < kEntries; i += blockDim.x) exits[(size_t)c * kEntries + i] = nxt[i] - kChunk;
 }
 
+// K3a alone, for a range of positions whose match tables start at `r_base` (used when a stream is
+// sharded by position over several GPUs: every rank produces nx for its own range).
+__global__ void lazy_step_range_kernel(const uint32_t* __restrict__ r_full, const uint32_t* __restrict__ r_quarter,
+                                       uint32_t count, uint32_t avail, LevelArgs lv, uint32_t* __restrict__ nx) {
+    // r_full / r_quarter / nx are indexed from the range start; `avail` (>= count) entries of the tables are valid
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t r = r_full[i];
+    uint32_t out = 0;
+    if (r != 0) {
+        uint32_t cur = i;
+        while (true) {
+            const uint32_t len = match_len_of(r);
+            if (len >= lv.lazy) break;  // deflate.zig:171
+            const uint32_t nb = cur + 1;
+            if (nb >= avail) break;     // only at the end of the stream (the caller provides 256 positions of slack)
+            const uint32_t r2 = (len >= lv.good) ? r_quarter[nb] : r_full[nb];  // deflate.zig:241-245
+            if (match_len_of(r2) > len) {
+                cur = nb;
+                r = r2;
+            } else {
+                break;
+            }
+        }
+        out = (cur - i) | ((match_len_of(r) - 3) << 8) | (match_dist_of(r) << 16);
+    }
+    nx[i] = out;
+}
+
+// K3b alone: exit tables from nx.
+__global__ void __launch_bounds__(1024)
+chunk_exit_kernel(const uint32_t* __restrict__ nx, uint32_t n, uint16_t* __restrict__ exits) {
+    __shared__ uint16_t nxt[kChunk];
+    const uint32_t c = blockIdx.x;
+    const uint32_t cs = c * kChunk;
+    for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
+        const uint32_t p = cs + i;
+        nxt[i] = (uint16_t)(p < n ? i + nx_step(nx[p]) : kChunk);
+    }
+    __syncthreads();
+    while (true) {
+        bool pending = false;
+        for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
+            const uint32_t t = nxt[i];
+            if (t < kChunk) {
+                nxt[i] = nxt[t];
+                pending = true;
+            }
+        }
+        if (!__syncthreads_or(pending)) break;
+    }
+    for (uint32_t i = threadIdx.x; i < kEntries; i += blockDim.x) exits[(size_t)c * kEntries + i] = nxt[i] - kChunk;
+}
+
 // K3c: resolve the true entry offset of every chunk.  Two-level: groups of kGroup chunks.
 __global__ void group_exit_kernel(const uint16_t* __restrict__ exits, uint32_t nchunks, uint16_t* __restrict__ gexits) {
     const uint32_t g = blockIdx.x;
@@ -1115,6 +1169,50 @@ cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin
     scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
     pt->mark(st, kPhScan);
     emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_seg, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp);
+    pt->mark(st, kPhEmit);
+    return cudaGetLastError();
+}
+
+// Position-sharded single stream.  Stage 1 on every rank: links, match search
+// and lazy step for stream positions [from, to); nx_out[0 .. to-from) receives the packed lazy steps.
+// `from` must be 0 or a multiple of 8192.  d_in must be readable from max(0, from - 32768) to
+// min(n, to + 8192 + 272).
+cudaError_t lz77_shard_search(const Lz77Buffers& b, const uint8_t* d_in, uint32_t from, uint32_t to, uint32_t n,
+                              const LevelArgs& lv, uint32_t* nx_out, cudaStream_t st, PhaseTimer* pt) {
+    PhaseTimer dummy;
+    if (!pt) pt = &dummy;
+    if (to <= from) return cudaSuccess;
+    // the lazy rule looks up to 255 positions past its arrival: search one extra hash tile
+    const uint32_t range_end = (uint32_t)min((uint64_t)n, ((uint64_t)to + 256 + kLinkTile - 1) / kLinkTile * kLinkTile);
+    cudaError_t e = lz77_search_range(b, d_in, from, from, range_end, n, nullptr, 0, lv, st, pt);
+    if (e != cudaSuccess) return e;
+    lazy_step_range_kernel<<<(to - from + 255) / 256, 256, 0, st>>>(b.r_full, b.r_quarter, to - from, range_end - from, lv, nx_out);
+    pt->mark(st, kPhLazy);
+    return cudaGetLastError();
+}
+
+// Stage 2 on one rank: parse + token emission from a complete nx table (b.nx).
+cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
+                               PhaseTimer* pt) {
+    PhaseTimer dummy;
+    if (!pt) pt = &dummy;
+    if (n == 0) {
+        cudaMemsetAsync(b.total_tokens, 0, sizeof(uint32_t), st);
+        return cudaGetLastError();
+    }
+    const uint32_t nchunks = (n + kChunk - 1) / kChunk;
+    const uint32_t ngroups = (nchunks + kGroup - 1) / kGroup;
+    chunk_exit_kernel<<<nchunks, 1024, 0, st>>>(b.nx, n, b.exits);
+    pt->mark(st, kPhChunkExit);
+    group_exit_kernel<<<ngroups, 544, 0, st>>>(b.exits, nchunks, b.gexits);
+    group_entry_kernel<<<1, 32, 0, st>>>(b.gexits, ngroups, b.gentry);
+    chunk_entry_kernel<<<(ngroups + 127) / 128, 128, 0, st>>>(b.exits, b.gentry, nchunks, b.entry);
+    pt->mark(st, kPhResolve);
+    orbit_mark_kernel<<<nchunks, kMarkThreads, 0, st>>>(b.nx, n, b.entry, b.bitmap, b.chunk_tokens);
+    pt->mark(st, kPhMark);
+    scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
+    pt->mark(st, kPhScan);
+    emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_in, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp);
     pt->mark(st, kPhEmit);
     return cudaGetLastError();
 }

@@ -82,6 +82,12 @@ cudaError_t lz77_search_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_
 cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const LevelArgs& lv,
                        cudaStream_t st, PhaseTimer* pt = nullptr);
 
+// position-sharded single stream: stage 1 (every rank) and stage 2 (one rank, complete nx in b.nx)
+cudaError_t lz77_shard_search(const Lz77Buffers& b, const uint8_t* d_in, uint32_t from, uint32_t to, uint32_t n,
+                              const LevelArgs& lv, uint32_t* nx_out, cudaStream_t st, PhaseTimer* pt = nullptr);
+cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
+                               PhaseTimer* pt = nullptr);
+
 // ---- block writer ----
 enum WriteKind : uint32_t { kWrite = 0, kDynamicBlock = 1, kHuffmanBlock = 2 };  // block_writer.zig:307,395,524
 

@@ -40,3 +40,25 @@ def all_gather_ragged(shard, size, pad_to=None, out=None):
 def concat_ragged(buffer, sizes, pad):
     """Byte-exact concatenation of the gathered payloads (host bytes)."""
     return b"".join(buffer[r * pad: r * pad + sizes[r]].cpu().numpy().tobytes() for r in range(len(sizes)))
+
+
+def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0):
+    """One deflate stream of n bytes (resident at torch uint8 tensor d_in on every rank) compressed by all
+    ranks together: every rank searches its own position range, the lazy-step tables are all-gathered
+    over NCCL, rank `root` runs the (cheap, sequential-in-nature) parse + block writer.  Returns the
+    compressed size on `root` (0 elsewhere).  Output is byte-identical to Context.compress_device."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    tile = 8192
+    per = ((n + world - 1) // world + tile - 1) // tile * tile if n else tile
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    nx = torch.empty(world * per, dtype=torch.int32, device=d_in.device)
+    sp = torch.cuda.current_stream().cuda_stream
+    ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level, stream=sp)
+    if world > 1:
+        dist.all_gather_into_tensor(nx, nx[rank * per:(rank + 1) * per])
+    if rank != root:
+        return 0
+    cap = d_out.numel()
+    return ctx.shard_finish(d_in.data_ptr(), n, nx.data_ptr(), d_out.data_ptr(), cap, level=level, container=container,
+                            stream=sp)

@@ -107,6 +107,19 @@ int fb200_decompress_members(fb200_ctx* ctx, int container, const uint8_t* in, c
                              const uint64_t* in_len, size_t k, uint8_t* out, const uint64_t* out_off,
                              const uint64_t* out_cap, uint64_t* out_len, uint64_t* consumed, int* status);
 
+/* ---- one stream sharded by position over several GPUs ----
+ * Match candidates do not depend on the parse, so any range of positions can be searched given a
+ * 32 KiB + 258 B halo of input.  Stage 1 runs on every rank for its own range [from, to) (`from` a
+ * multiple of 8192) and writes the packed lazy-parse steps into d_nx[from .. to) (uint32 per position;
+ * d_nx holds n entries; d_in must be readable on [max(0, from - 32768), min(n, to + 8464))).  The
+ * ranks exchange their d_nx ranges (NCCL all-gather) and stage 2 runs on one rank over the complete
+ * table: lazy-parse orbit, block cut, Huffman construction, bit-pack.  The result is byte-identical
+ * to fb200_compress_device on the same stream.  Replaces deflate.zig:304-347 for one large stream. */
+int fb200_deflate_shard_search(fb200_ctx* ctx, int level, const void* d_in, size_t n, size_t from, size_t to, void* d_nx,
+                               void* stream);
+int fb200_deflate_shard_finish(fb200_ctx* ctx, int container, int level, const void* d_in, size_t n, const void* d_nx,
+                               void* d_out, size_t cap, size_t* out_len, void* stream);
+
 /* ---- streaming compressor (Compressor / SimpleCompressor) ---- */
 typedef struct fb200_deflate fb200_deflate;
 typedef int (*fb200_write_fn)(void* user, const uint8_t* data, size_t len); /* the `writer`; non-zero = error */
