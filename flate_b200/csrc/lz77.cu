@@ -1112,18 +1112,22 @@ static void lz77_init_once() {
 // host-to-device copy of later parts of the input with the search of earlier parts.
 cudaError_t lz77_search_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t seg_begin, uint32_t from, uint32_t range_end,
                               uint32_t n, const uint32_t* d_skip, uint32_t nskip, const LevelArgs& lv, cudaStream_t st,
-                              PhaseTimer* pt) {
+                              PhaseTimer* pt, uint32_t link_from) {
+    // link_from (<= from, default = from): first position whose link is (re)computed.  A caller that has not
+    // linked the 32 KiB of history before `from` (a rank searching the middle of a sharded stream) passes
+    // from - 32768.
     lz77_init_once();
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
     if (range_end <= from) return cudaSuccess;
-    const uint32_t ntiles = (range_end + kLinkTile - 1) / kLinkTile - from / kLinkTile;
+    if (link_from > from) link_from = from;
+    const uint32_t ntiles = (range_end + kLinkTile - 1) / kLinkTile - link_from / kLinkTile;
     // run length: long enough to amortise the 4 warm-up tiles (<= 32 tiles), and chosen so that the grid is
     // close to a whole number of waves of 2 CTAs per SM
     const uint32_t slots = 2 * (uint32_t)g_num_sms;
     const uint32_t waves = (ntiles + slots * 32 - 1) / (slots * 32);
     const uint32_t run = max(1u, (ntiles + slots * waves - 1) / (slots * waves));
-    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, from, range_end, n, run, d_skip, nskip, b.link);
+    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, link_from, range_end, n, run, d_skip, nskip, b.link);
     pt->mark(st, kPhLink);
     if (g_use_roll && from == seg_begin && range_end == n) {
         const uint32_t epochs = (n + kEpoch - 1) / kEpoch - from / kEpoch;
@@ -1184,7 +1188,7 @@ cudaError_t lz77_shard_search(const Lz77Buffers& b, const uint8_t* d_in, uint32_
     if (to <= from) return cudaSuccess;
     // the lazy rule looks up to 255 positions past its arrival: search one extra hash tile
     const uint32_t range_end = (uint32_t)min((uint64_t)n, ((uint64_t)to + 256 + kLinkTile - 1) / kLinkTile * kLinkTile);
-    cudaError_t e = lz77_search_range(b, d_in, from, from, range_end, n, nullptr, 0, lv, st, pt);
+    cudaError_t e = lz77_search_range(b, d_in, from, from, range_end, n, nullptr, 0, lv, st, pt, from >= kHist ? from - kHist : 0);
     if (e != cudaSuccess) return e;
     lazy_step_range_kernel<<<(to - from + 255) / 256, 256, 0, st>>>(b.r_full, b.r_quarter, to - from, range_end - from, lv, nx_out);
     pt->mark(st, kPhLazy);
@@ -1219,7 +1223,7 @@ cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32
 
 cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const uint32_t* d_skip,
                           uint32_t nskip, const LevelArgs& lv, cudaStream_t st, PhaseTimer* pt) {
-    cudaError_t e = lz77_search_range(b, d_in, begin, begin, n, n, d_skip, nskip, lv, st, pt);
+    cudaError_t e = lz77_search_range(b, d_in, begin, begin, n, n, d_skip, nskip, lv, st, pt, begin);
     if (e != cudaSuccess) return e;
     return lz77_parse(b, d_in, begin, n, lv, st, pt);
 }

@@ -78,7 +78,7 @@ cudaError_t lz77_tokenize(const Lz77Buffers& b, const uint8_t* d_in, uint32_t be
 // the two halves of lz77_tokenize, for callers that overlap the input copy with the search
 cudaError_t lz77_search_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t seg_begin, uint32_t from, uint32_t range_end,
                               uint32_t n, const uint32_t* d_skip, uint32_t nskip, const LevelArgs& lv, cudaStream_t st,
-                              PhaseTimer* pt = nullptr);
+                              PhaseTimer* pt = nullptr, uint32_t link_from = 0xffffffffu);
 cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const LevelArgs& lv,
                        cudaStream_t st, PhaseTimer* pt = nullptr);
 

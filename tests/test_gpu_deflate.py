@@ -370,12 +370,16 @@ def test_position_sharded_stream_equals_whole(ctx, o, level):
     cap = ctx.lib.fb200_compress_bound(n, level) + 64
     d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
     want = o.compress(data.tobytes(), 1, level)
+    import flate_b200
     for parts in (1, 2, 3, 5):
         per = ((n + parts - 1) // parts + 8191) // 8192 * 8192
         nx = torch.full((parts * per,), -1, dtype=torch.int32, device="cuda")
-        for r in reversed(range(parts)):  # any order: ranges are independent
+        for r in reversed(range(parts)):
+            # a fresh context per range, like a separate GPU: nothing (links of the history!) is inherited
+            c = flate_b200.Context(0)
             lo, hi = min(n, r * per), min(n, (r + 1) * per)
-            ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level)
+            c.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level)
+            c.close()
         m = ctx.shard_finish(d_in.data_ptr(), n, nx.data_ptr(), d_out.data_ptr(), cap, level=level, container=1)
         got = d_out[:m].cpu().numpy().tobytes()
         assert got == want, (level, parts, first_diff(got, want))
