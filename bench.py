@@ -323,45 +323,48 @@ def main():
                     continue
             members.append(m)
             plains.append(sl)
-        blob = b"".join(members[i % uniq] for i in range(nmem))
-        lens = np.array([len(members[i % uniq]) for i in range(nmem)], dtype=np.uint64)
-        offs = np.zeros(nmem, dtype=np.uint64)
-        offs[1:] = np.cumsum(lens)[:-1]
-        d_blob = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).cuda()
-        d_plain = torch.empty(nmem * MEMBER_BYTES + 64, dtype=torch.uint8, device="cuda")
-        ooff = np.arange(nmem, dtype=np.uint64) * np.uint64(MEMBER_BYTES)
-        ocap = np.full(nmem, MEMBER_BYTES, dtype=np.uint64)
+        def time_inflate(nmem):
+            blob = b"".join(members[i % uniq] for i in range(nmem))
+            lens = np.array([len(members[i % uniq]) for i in range(nmem)], dtype=np.uint64)
+            offs = np.zeros(nmem, dtype=np.uint64)
+            offs[1:] = np.cumsum(lens)[:-1]
+            d_blob = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8).copy()).cuda()
+            d_plain = torch.empty(nmem * MEMBER_BYTES + 64, dtype=torch.uint8, device="cuda")
+            ooff = np.arange(nmem, dtype=np.uint64) * np.uint64(MEMBER_BYTES)
+            ocap = np.full(nmem, MEMBER_BYTES, dtype=np.uint64)
 
-        def inflate_step():
-            rc, ol, used, st = ctx.decompress_members_device(d_blob.data_ptr(), offs, lens, d_plain.data_ptr(), ooff, ocap,
-                                                             flate_b200.GZIP, stream=sp)
-            if rc:
-                raise RuntimeError("inflate failed: %d" % rc)
-            return int(ol.sum())
+            def inflate_step():
+                rc, ol, used, st = ctx.decompress_members_device(d_blob.data_ptr(), offs, lens, d_plain.data_ptr(), ooff,
+                                                                 ocap, flate_b200.GZIP, stream=sp)
+                if rc:
+                    raise RuntimeError("inflate failed: %d" % rc)
+                return int(ol.sum())
 
-        for _ in range(2):
-            plain_bytes = inflate_step()
-        ctx.profile(True)
-        barrier()
-        isteps = max(2, args.steps // 2)
-        e0.record(stream)
-        for _ in range(isteps):
-            plain_bytes = inflate_step()
-        e1.record(stream)
-        barrier()
-        ims = e0.elapsed_time(e1) / isteps
-        iph = ctx.profile_read()
-        ctx.profile(False)
-        t = torch.tensor([ims], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ims = float(t.item())
+            for _ in range(2):
+                plain_bytes = inflate_step()
+            ctx.profile(True)
+            barrier()
+            isteps = max(2, args.steps // 2)
+            e0.record(stream)
+            for _ in range(isteps):
+                plain_bytes = inflate_step()
+            e1.record(stream)
+            barrier()
+            ims = e0.elapsed_time(e1) / isteps
+            iph = ctx.profile_read()
+            ctx.profile(False)
+            t = torch.tensor([ims], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            chk = d_plain[:MEMBER_BYTES].cpu().numpy()
+            kms = iph["inflate_members"][0] / max(1, iph["inflate_members"][1])
+            return float(t.item()), plain_bytes, len(blob), kms, chk
+
+        ims, plain_bytes, blob_len, kms, chk = time_inflate(nmem)
         # parity: a member's plain bytes equal the text it was made from
-        chk = d_plain[:MEMBER_BYTES].cpu().numpy()
         assert (chk == plains[0]).all(), "inflate output differs from the original text"
-        kms = iph["inflate_members"][0] / max(1, iph["inflate_members"][1])
         peak, src = peaks()
-        algo = float(len(blob) + plain_bytes)
+        algo = float(blob_len + plain_bytes)
         inflate = {"metric": "inflate MB/s out", "value": round(world * plain_bytes / 1e6 / (ims / 1e3), 1), "unit": "MB/s",
                    "ms_per_step": round(ims, 3), "scaling": "strong",
                    "workload": "%d gzip members x 1 MiB plain (level 6 text) per GPU, %d MiB plain over %d GPU(s)"
@@ -380,7 +383,15 @@ def main():
             dt = time.perf_counter() - t0
             inflate["cpu_baseline"] = {"value": round(ksample * MEMBER_BYTES / 1e6 / dt, 1), "unit": "MB/s", "cores": 1,
                                        "kind": "port", "sample": "%d of the same members, oracle inflate, 1 thread" % ksample}
-        del d_blob, d_plain
+        if world > 1:
+            # the same members, 1 GiB of plain output PER GPU: one warp decodes one member, so a GPU needs
+            # about a thousand members in flight; the strong-scaling leg above leaves 1024 / N per GPU
+            wn = max(1, INFLATE_TOTAL // MEMBER_BYTES)
+            wms, wplain, _, wk, wchk = time_inflate(wn)
+            assert (wchk == plains[0]).all()
+            inflate["weak"] = {"value": round(world * wplain / 1e6 / (wms / 1e3), 1), "unit": "MB/s",
+                               "ms_per_step": round(wms, 3), "scaling": "weak", "kernel_ms": round(wk, 3),
+                               "workload": "%d gzip members x 1 MiB plain per GPU" % wn}
 
     if world > 1:
         dist.barrier()
