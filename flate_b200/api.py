@@ -80,6 +80,14 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.fb200_kernel_launches(self.h))
 
+    def set_parse_mode(self, mode):
+        """0 = speculative sparse parse with automatic dense redo (default), 1 = dense match tables always."""
+        _check(self.lib.fb200_ctx_set_parse_mode(self.h, int(mode)))
+
+    @property
+    def sparse_fallbacks(self):
+        return int(self.lib.fb200_sparse_fallbacks(self.h))
+
     def profile(self, on=True):
         self.lib.fb200_profile_enable(self.h, int(on))
 

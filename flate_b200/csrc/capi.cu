@@ -91,6 +91,8 @@ struct fb200_ctx {
     cudaEvent_t slab_ev[16] = {};
     uint64_t launches = 0;
     PhaseTimer timer;
+    int parse_mode = 0;              // 0 = sparse parse with dense fallback, 1 = dense tables always
+    uint64_t sparse_fallbacks = 0;   // streams redone with the dense tables
     // LZ77 workspace
     DevBuf<uint16_t> link, exits, gexits, gentry, entry;
     DevBuf<uint32_t> r_full, r_quarter, nx, bitmap, chunk_tokens, tok_offset, tokens, cut_rp;
@@ -128,6 +130,12 @@ const char* fb200_strerror(int code) {
     if (code < 0 || code > 20) return "Unknown";
     return names[code];
 }
+int fb200_ctx_set_parse_mode(fb200_ctx* ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 1) return FB200_INVALID_ARGUMENT;
+    ctx->parse_mode = mode;
+    return FB200_OK;
+}
+uint64_t fb200_sparse_fallbacks(const fb200_ctx* ctx) { return ctx ? ctx->sparse_fallbacks : 0; }
 uint64_t fb200_kernel_launches(const fb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int fb200_profile_enable(fb200_ctx* ctx, int on) {
     if (!ctx) return FB200_INVALID_ARGUMENT;
@@ -139,7 +147,7 @@ int fb200_profile_phases(void) { return kPhCount; }
 const char* fb200_profile_phase_name(int i) {
     static const char* names[] = {"hash_link", "match_search", "lazy_step(fused)", "lazy+chunk_exit", "resolve_entries", "orbit_mark",
                                   "scan_tokens", "emit_tokens", "plan+histogram", "build_blocks", "offsets+zero", "pack_blocks",
-                                  "inflate_members"};
+                                  "inflate_members", "sparse_parse"};
     return (i >= 0 && i < kPhCount) ? names[i] : "?";
 }
 int fb200_profile_read(const fb200_ctx* ctx, double* ms, uint64_t* count, int n) {
@@ -232,6 +240,30 @@ static const uint8_t kZlibHeader[2] = {0x78, 0x9c};                             
 static inline size_t header_size(int container) { return container == FB200_GZIP ? 10 : container == FB200_ZLIB ? 2 : 0; }
 static inline size_t footer_size(int container) { return container == FB200_GZIP ? 8 : container == FB200_ZLIB ? 4 : 0; }
 
+// Device flags of the sparse parse (u32 index 20 of d_scalars): bit 0 = an orbit left its span unjoined,
+// bit 1 = the token emitter met an entry that was never evaluated.  Non-zero => redo with dense tables.
+constexpr int kSparseFlagIdx = 20;
+static int sparse_begin(fb200_ctx* c, const Lz77Buffers& b, size_t n, cudaStream_t st) {
+    FB_CUDA_CHECK(cudaMemsetAsync(b.nx, 0xFF, n * sizeof(uint32_t), st));
+    FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
+    return FB200_OK;
+}
+// whole stream already on the device
+static int sparse_tokenize(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in, size_t n, const LevelArgs& lv, cudaStream_t st) {
+    if (n == 0) {
+        FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, 0, lv, st, &c->timer));
+        return FB200_OK;
+    }
+    int rc = sparse_begin(c, b, n, st);
+    if (rc) return rc;
+    const uint32_t T = lz77_sparse_chunk();
+    FB_CUDA_CHECK(lz77_link_range(b, d_in, 0, (uint32_t)n, (uint32_t)n, st, &c->timer));
+    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, 0, (uint32_t)((n + T - 1) / T), (uint32_t)n, lv, c->d_scalars + kSparseFlagIdx, st, &c->timer));
+    FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
+    c->launches += 9;
+    return FB200_OK;
+}
+
 // Runs the deflate body of stream positions [begin, n) on the device.  One-shot calls pass begin = 0
 // and get the container header in front; the streaming compressor passes the flush point and gets
 // just the blocks of the segment (plus the sync marker when !final_flush).  Returns the end of the
@@ -239,7 +271,8 @@ static inline size_t footer_size(int container) { return container == FB200_GZIP
 static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint8_t* d_in, size_t begin, size_t n,
                                const uint32_t* d_skip, uint32_t nskip, uint8_t* d_out, size_t cap, size_t* end_bytes,
                                bool final_flush, bool with_header, cudaStream_t st, const uint8_t* h_src = nullptr,
-                               uint8_t* h_dst = nullptr, size_t h_cap = 0, const uint32_t* d_nx_given = nullptr) {
+                               uint8_t* h_dst = nullptr, size_t h_cap = 0, const uint32_t* d_nx_given = nullptr,
+                               bool force_dense = false) {
     // d_nx_given != nullptr: the lazy-step table of the whole stream was produced elsewhere (position-sharded
     // search on several GPUs); only the parse and the block writer run here.
     // h_dst != nullptr: the packed bytes are also copied to host memory at h_dst, part by part, while later
@@ -257,6 +290,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     uint32_t max_blocks;
     const uint32_t* tokens = nullptr;
     LevelArgs lv;
+    bool sparse = false;
     if (level_args(mode, lv)) {
         if (n > (1ull << 31)) return FB200_INVALID_ARGUMENT;  // single-stream position space is 32-bit
         int rc = ensure_lz77(c, n);
@@ -270,6 +304,40 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
             b.nx = const_cast<uint32_t*>(d_nx_given);
             FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer));
             c->launches += n ? 7 : 0;
+        } else if ((sparse = (begin == 0 && nskip == 0 && n > 0 && !force_dense && c->parse_mode == 0)) && !(h_src && n > kSlab + kLag)) {
+            if (h_src) FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in), h_src, n, cudaMemcpyHostToDevice, st));
+            if ((rc = sparse_tokenize(c, b, d_in, n, lv, st))) return rc;
+        } else if (sparse) {
+            // slab-overlapped copy: links follow the copy front one hash tile behind, the sparse parse follows the
+            // links by its look-ahead
+            if ((rc = sparse_begin(c, b, n, st))) return rc;
+            const uint32_t T = lz77_sparse_chunk(), ahead = lz77_sparse_lookahead();
+            size_t copied = 0, linked = 0;
+            uint32_t chunks_done = 0;
+            int k = 0;
+            while (copied < n) {
+                const size_t slab_end = copied == 0 ? (kFirst < n ? kFirst : n) : (copied + kSlab < n ? copied + kSlab : n);
+                cudaEvent_t ev = c->slab_ev[k % 16];
+                if (k >= 16) FB_CUDA_CHECK(cudaEventSynchronize(ev));
+                FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in) + copied, h_src + copied, slab_end - copied,
+                                              cudaMemcpyHostToDevice, c->copy_stream));
+                FB_CUDA_CHECK(cudaEventRecord(ev, c->copy_stream));
+                FB_CUDA_CHECK(cudaStreamWaitEvent(st, ev, 0));
+                const size_t range_end = slab_end == n ? n : slab_end - kLag;
+                FB_CUDA_CHECK(lz77_link_range(b, d_in, (uint32_t)linked, (uint32_t)range_end, (uint32_t)n, st, &c->timer));
+                const uint32_t chunks_end = range_end == n ? (uint32_t)((n + T - 1) / T)
+                                                           : (uint32_t)(range_end > ahead ? (range_end - ahead) / T : 0);
+                if (chunks_end > chunks_done) {
+                    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, chunks_done, chunks_end, (uint32_t)n, lv, c->d_scalars + kSparseFlagIdx, st, &c->timer));
+                    chunks_done = chunks_end;
+                }
+                c->launches += 2;
+                linked = range_end;
+                copied = slab_end;
+                k++;
+            }
+            FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
+            c->launches += 7;
         } else if (h_src && n - begin > kSlab + kLag) {
             const size_t first_end = (begin / kFirst + 1) * kFirst;  // a small first slab shortens the initial wait
             size_t copied = begin, searched = begin;
@@ -373,9 +441,17 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     }
     if (container != FB200_RAW && final_flush) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 8, sum_dev, 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8, cudaMemcpyDeviceToHost, st));
+    if (sparse) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 9, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
     if (copied_out) FB_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
     c->timer.collect();
+    if (sparse && (uint32_t)c->h_scalars[9] != 0) {
+        // the speculation did not cover the true orbit (e.g. long periodic data, where parses started at
+        // different positions never fall into step): redo the stream with the dense match tables
+        c->sparse_fallbacks++;
+        return deflate_body_device(c, container, mode, d_in, begin, n, d_skip, nskip, d_out, cap, end_bytes, final_flush, with_header,
+                                   st, nullptr, h_dst, h_cap, nullptr, true);
+    }
     *end_bytes = (size_t)((c->h_scalars[0] + 7) >> 3);
     return FB200_OK;
 }
@@ -486,9 +562,17 @@ int fb200_debug_tokens(fb200_ctx* c, int level, const uint8_t* in, size_t n, uin
     cudaStream_t st = c->stream;
     if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
     Lz77Buffers b = lz77_view(c);
-    FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, 0, (uint32_t)n, nullptr, 0, lv, st));
-    c->launches += n ? 9 : 0;
-    uint32_t total = 0;
+    uint32_t total = 0, bad = 0;
+    if (c->parse_mode == 0 && n) {
+        if ((rc = sparse_tokenize(c, b, c->d_in.p, n, lv, st))) return rc;
+        FB_CUDA_CHECK(cudaMemcpyAsync(&bad, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (bad) c->sparse_fallbacks++;
+    }
+    if (c->parse_mode != 0 || n == 0 || bad) {
+        FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, 0, (uint32_t)n, nullptr, 0, lv, st));
+        c->launches += n ? 9 : 0;
+    }
     FB_CUDA_CHECK(cudaMemcpyAsync(&total, b.total_tokens, 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
     *ntok = total;

@@ -61,6 +61,8 @@ __host__ __device__ inline uint32_t match_dist_of(uint32_t r) { return (r >> 9) 
 
 // Packed lazy-parse step for a clean arrival at p (see deflate.cu lazy_step_kernel):
 //   k (deferred literals before the match) | (len-3) << 8 | dist << 16 ; dist == 0 => plain literal
+constexpr uint32_t kNxInvalid = 0xFFFFFFFFu;  // entry never evaluated by the sparse parse (distance 0xFFFF cannot occur)
+__host__ __device__ inline uint32_t nx_clean(uint32_t nx) { return nx == kNxInvalid ? 0u : nx; }
 __host__ __device__ inline uint32_t nx_step(uint32_t nx) { return (nx >> 16) ? (nx & 255u) + ((nx >> 8) & 255u) + 3u : 1u; }
 
 // ---- Token.zig:58-103 code tables, in arithmetic form (RFC 1951 3.2.5) ----

@@ -741,6 +741,341 @@ match_search_roll_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_
 }
 
 // ------------------------------------------------------------------------------------------
+// K2s: speculative sparse parse (findMatch + the lazy rule, only where a parse can arrive).
+//
+// The step f(p) of the lazy parse from a clean arrival p (deflate.zig:160-193: k deferred literals,
+// then one match, or one literal) is a pure function of p, and the reference only ever evaluates it
+// on the orbit of 0.  Parses started at different positions fall into step after a few tokens, so it
+// is enough to evaluate f on the orbits of many seeds: a CTA owns kT positions plus an overlap of kW
+// positions of the next CTA's range, puts a seed every kG positions, and every lane follows one
+// seed's orbit, searching on demand (with the real min_len and the real budget of deflate.zig:241-245)
+// and claiming each arrival in a bitmap.  A lane stops when it reaches an arrival somebody else has
+// claimed: that lane carries the orbit on.  So the set of evaluated arrivals is closed under f up to
+// the end of the span, every seed is in it, and position 0 is a seed: the true orbit stays inside it
+// as long as every orbit that started in a CTA's own range has joined the orbit of one of the overlap
+// seeds (which the next CTA evaluates as well) before the span ends.  That is checked exactly (`safe`
+// bitmap); if it ever fails the host falls back to the dense tables (match_search_kernel), so the
+// result never depends on the speculation.  nx[] is pre-filled with kNxInvalid by the caller; the
+// token emitter reports any invalid entry it meets on the true orbit as a second line of defence.
+// On text this evaluates ~8x fewer chain candidates than searching every position.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kSpHalo = 256;  // a lazy run searches up to 255 positions past its arrival
+struct SparseTune {
+    uint32_t pend_at;    // run the batched full compares once this many lanes wait for one
+    uint32_t done_at;    // run the lazy decisions once this many lanes finished a walk
+    uint32_t refill_at;  // hand out new seeds once this many lanes are idle
+    uint32_t levels;     // levels of split seeds handed out after the regular ones (0 = none)
+};
+template <uint32_t kT, uint32_t kW>
+struct SparseCfg {
+    static constexpr uint32_t kSpan = kT + kW;
+    static constexpr uint32_t kBytes = kSearchOff + kHist + kSpan + kSpHalo + 272;
+    static constexpr uint32_t kLinks = kSearchOff + kHist + kSpan + kSpHalo;
+    static constexpr uint32_t kWords = kSpan / 32;
+    static constexpr uint32_t kSmem = kBytes + kLinks * 2 + kWords * 8;
+};
+enum : uint32_t { kSearchDone = 4, kArrive = 5, kStart = 6 };
+constexpr uint32_t kMaxCross = 32;
+
+template <uint32_t kT, uint32_t kW, uint32_t kG, uint32_t kThreads, int kMinBlocks, int kSteps>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, uint32_t n, const uint16_t* __restrict__ link,
+                    LevelArgs lv, SparseTune tune, uint32_t* __restrict__ nx, uint32_t* __restrict__ flags) {
+    using C = SparseCfg<kT, kW>;
+    static_assert(C::kBytes % 16 == 0 && (C::kLinks * 2) % 16 == 0 && kT % kG == 0 && kW % kG == 0, "layout");
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint32_t seed_next, cross_cnt;
+    __shared__ uint32_t cross[kMaxCross];
+    __shared__ __align__(8) uint64_t stage_bar;
+    uint8_t* sb = smem_raw;                                               // bytes, slot i+16 = position wb+i
+    uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + C::kBytes);     // link (distance, kNoLink = none) per slot
+    uint32_t* valid = reinterpret_cast<uint32_t*>(smem_raw + C::kBytes + C::kLinks * 2);  // arrivals claimed by some lane
+    uint32_t* safe = valid + C::kWords;                                   // arrivals on the orbit of an overlap seed
+    const uint32_t s = (first_chunk + blockIdx.x) * kT;                   // first own position
+    const int64_t wb = (int64_t)s - kHist;
+    const uint32_t lo = wb < 0 ? (uint32_t)(-wb) : 0;
+    const uint32_t span_len = min(C::kSpan, n - s);                       // arrivals evaluated here: offsets < span_len
+    const bool open_end = (uint64_t)s + C::kSpan < n;                     // the stream goes on past the span
+    const uint32_t nseeds = (span_len + kG - 1) / kG;
+    const uint32_t total_seeds = nseeds << min(tune.levels, kG == 32 ? 3u : 2u);  // levels of split seeds: n, n, 2n, 4n
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ltmask = (1u << lane) - 1;
+
+    for (uint32_t i = threadIdx.x; i < 2 * C::kWords; i += kThreads) valid[i] = 0;
+    if (threadIdx.x == 0) {
+        seed_next = 0;
+        cross_cnt = 0;
+    }
+    // ---- stage window (same scheme as match_search_kernel) ----
+    constexpr uint32_t kBytesTx = C::kBytes - kSearchOff, kLinksTx = (C::kLinks - kSearchOff) * 2;
+    const bool tma_ok = wb >= 0 && (uint64_t)s + C::kSpan + kSpHalo + 272 <= n && (((uintptr_t)in | (uintptr_t)link) & 15) == 0;
+    if (tma_ok) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBytesTx + kLinksTx) : "memory");
+            constexpr uint32_t kPiece = 32768;  // bulk copies in pieces of at most 32 KiB
+            for (uint32_t o = 0; o < kBytesTx; o += kPiece) {
+                const uint32_t len = min(kPiece, kBytesTx - o);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(sb + kSearchOff + o)), "l"(in + wb + o), "r"(len), "r"(bar) : "memory");
+            }
+            const uint8_t* lsrc = reinterpret_cast<const uint8_t*>(link + wb);
+            uint8_t* ldst = reinterpret_cast<uint8_t*>(sl + kSearchOff);
+            for (uint32_t o = 0; o < kLinksTx; o += kPiece) {
+                const uint32_t len = min(kPiece, kLinksTx - o);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(ldst + o)), "l"(lsrc + o), "r"(len), "r"(bar) : "memory");
+            }
+        }
+        __syncthreads();
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_SP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@p bra DONE_SP;\n"
+            "bra WAIT_SP;\n"
+            "DONE_SP:\n"
+            "}\n" ::"r"(bar) : "memory");
+    } else {
+        const uint32_t byte_hi = (uint32_t)min((int64_t)kBytesTx, (int64_t)n - wb);  // exclusive
+        const bool aligned = ((uintptr_t)in & 15) == 0;
+        const uint32_t v_lo = (lo + 15) / 16, v_hi = aligned ? byte_hi / 16 : v_lo;
+        const uint4* src = reinterpret_cast<const uint4*>(in + wb);
+        uint4* dst = reinterpret_cast<uint4*>(sb + kSearchOff);
+        for (uint32_t i = v_lo + threadIdx.x; i < v_hi; i += kThreads) dst[i] = src[i];
+        for (uint32_t i = lo + threadIdx.x; i < min(v_lo * 16, byte_hi); i += kThreads) sb[kSearchOff + i] = in[wb + i];
+        for (uint32_t i = max(lo, v_hi * 16) + threadIdx.x; i < byte_hi; i += kThreads) sb[kSearchOff + i] = in[wb + i];
+        for (uint32_t i = byte_hi + threadIdx.x; i < kBytesTx; i += kThreads) sb[kSearchOff + i] = 0;
+        const uint32_t link_hi = (uint32_t)min((int64_t)(C::kLinks - kSearchOff), (int64_t)n - wb);
+        for (uint32_t i = lo + threadIdx.x; i < link_hi; i += kThreads) sl[kSearchOff + i] = link[wb + i];
+        __syncthreads();
+    }
+
+    const uint32_t slide_J = max(n >> 15, 1u) - 1;
+    const uint32_t quarter = lv.chain >> 2;
+    uint32_t sb_addr = (uint32_t)__cvta_generic_to_shared(sb);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sb_addr));
+    const uint32_t sl_addr = sb_addr + C::kBytes;
+
+    uint32_t st = kIdle, left = 0, saved = 0;
+    uint32_t pi = 0, qi = 0, lim = 0, best_len = 0, best_dist = 0, ro_addr = 0, cb = 0, first4 = 0, max_len = 0;
+    uint32_t p0 = 0, curk = 0, cur_len = 0, cur_dist = 0;  // the arrival being evaluated and its pending match
+    bool from_overlap = false;
+
+    // Lane states beyond the walk itself: kSearchDone (walk ended, lazy rule pending), kArrive (the orbit
+    // reaches the clean arrival a_rel), kStart (findMatch at a_rel with min_len = best_len and `saved`
+    // candidates is about to begin).  Every transition has exactly one copy of its code in the loop below.
+    uint32_t a_rel = 0;
+    // findMatch(pos = s + a_rel, min_len = best_len) with `saved` candidates (deflate.zig:233-266)
+    auto start_search = [&]() {
+        const uint32_t rel = a_rel, min_len = best_len, budget = saved;
+        best_dist = 0;
+        left = 0;
+        st = kSearchDone;
+        const uint32_t p = s + rel;
+        if (p >= n) return;
+        const uint32_t remaining = n - p;
+        if (remaining < kMinMatch) return;     // Lookup.zig:24
+        max_len = min(remaining, kMaxMatch);   // SlidingWindow.zig:82
+        if (min_len >= max_len || budget == 0) return;
+        pi = kSearchOff + kHist + rel;
+        qi = pi;
+        const uint32_t jj = max((p + kMinLookahead) >> 15, 1u) - 1;
+        const int32_t base_slot = (int32_t)(min(jj, slide_J) << 15) - (int32_t)wb + (int32_t)kSearchOff;
+        lim = (uint32_t)max((int32_t)pi - (int32_t)kMaxDist, base_slot + 1);
+        left = budget;
+        first4 = lds_u32_unaligned(sb, pi);
+        const uint32_t ro = max(min_len, 3u);  // a longer match agrees on byte max(best_len, 3)
+        ro_addr = sb_addr + ro;
+        cb = sb[pi + ro];
+        st = kStepping;
+    };
+    // the orbit reaches the clean arrival s + a_rel (p0 still holds the previous arrival)
+    auto arrive = [&]() {
+        const uint32_t rel = a_rel;
+        st = kIdle;
+        if (rel >= span_len) {
+            if (!from_overlap && open_end) {  // must have joined an overlap seed's orbit: checked after the loop
+                const uint32_t idx = atomicAdd(&cross_cnt, 1u);
+                if (idx < kMaxCross) cross[idx] = p0;
+            }
+            return;
+        }
+        const uint32_t w = rel >> 5, bit = 1u << (rel & 31);
+        const uint32_t old = atomicOr(&valid[w], bit);
+        if (from_overlap) {
+            if (atomicOr(&safe[w], bit) & bit) return;  // another overlap seed's lane carries on from here
+        } else if (old & bit) {
+            return;                                      // somebody carries on from here
+        }
+        p0 = rel;
+        curk = 0;
+        cur_len = 0;
+        cur_dist = 0;
+        best_len = 0;
+        saved = lv.chain;
+        st = kStart;
+    };
+    // a walk ended: apply the lazy rule (deflate.zig:166-190)
+    auto decide = [&]() {
+        const bool found = best_dist != 0;
+        bool fin = false;
+        if (cur_len == 0) {
+            if (found) {
+                cur_len = best_len;
+                cur_dist = best_dist;
+            } else {
+                fin = true;  // plain literal
+            }
+        } else if (found) {  // better match one byte later: the pending one becomes a literal
+            curk++;
+            cur_len = best_len;
+            cur_dist = best_dist;
+        } else {
+            fin = true;      // emit the pending match
+        }
+        if (!fin && cur_len >= lv.lazy) fin = true;  // deflate.zig:171
+        if (!fin) {
+            a_rel = p0 + curk + 1;
+            best_len = cur_len;
+            saved = cur_len >= lv.good ? quarter : lv.chain;  // deflate.zig:241-245
+            st = kStart;
+        } else {
+            uint32_t out = 0, step = 1;
+            if (cur_len) {
+                out = curk | ((cur_len - 3) << 8) | (cur_dist << 16);
+                step = curk + cur_len;
+            }
+            nx[s + p0] = out;
+            a_rel = p0 + step;
+            st = kArrive;
+        }
+    };
+
+    bool exhausted = false;
+    while (true) {
+        // ---- phase A: chain steps (deflate.zig:248 "Hot path loop!") ----
+#pragma unroll
+        for (int u = 0; u < kSteps; u++) {
+            if (left) {
+                qi -= lds_shared_u16(sl_addr + 2 * qi);
+                if ((int32_t)qi < (int32_t)lim) {  // end of chain, too far, or at/below the slide base
+                    st = kSearchDone;
+                    left = 0;
+                } else if (lds_shared_u8(ro_addr + qi) == cb) {
+                    st = kPending;
+                    saved = left;
+                    left = 0;
+                } else {
+                    left--;
+                }
+            }
+        }
+        if (st == kStepping && left == 0) st = kSearchDone;
+        // ---- phase B: full compares ----
+        const uint32_t pend = __ballot_sync(0xffffffffu, st == kPending);
+        if (pend) {
+            const uint32_t stepping = __ballot_sync(0xffffffffu, st == kStepping);
+            if (__popc(pend) >= tune.pend_at || stepping == 0) {
+                if (st == kPending) {
+                    st = kStepping;
+                    left = saved - 1;
+                    if (lds_u32_unaligned(sb, qi) == first4) {
+                        uint32_t i = 4;
+                        while (i < max_len) {
+                            const uint32_t x = lds_u32_unaligned(sb, qi + i) ^ lds_u32_unaligned(sb, pi + i);
+                            if (x) {
+                                i += (__ffs(x) - 1) >> 3;
+                                break;
+                            }
+                            i += 4;
+                        }
+                        if (i > max_len) i = max_len;
+                        if (i > best_len) {
+                            best_len = i;
+                            best_dist = pi - qi;
+                            if (i >= lv.nice || i >= max_len) {  // deflate.zig:256-259, or nothing can be longer
+                                st = kSearchDone;
+                                left = 0;
+                            } else {
+                                ro_addr = sb_addr + i;
+                                cb = sb[pi + i];
+                            }
+                        }
+                    }
+                    if (st == kStepping && left == 0) st = kSearchDone;
+                }
+            }
+        }
+        // ---- phase C: lazy decisions of finished walks, next arrival of the orbit ----
+        const uint32_t done = __ballot_sync(0xffffffffu, st == kSearchDone);
+        if (done) {
+            const uint32_t busy = __ballot_sync(0xffffffffu, st == kStepping || st == kPending);
+            if (__popc(done) >= tune.done_at || busy == 0) {
+                if (st == kSearchDone) decide();
+            }
+        }
+        // ---- phase D: new seeds for idle lanes ----
+        // Level 0: every kG positions, last segment first (so a lane soon meets the trail of the segment
+        // ahead).  When those run out, idle lanes split the work of the slow ones: level l >= 1 puts seeds
+        // half-way between the seeds of the levels above (spacing kG >> (l-1)); such a seed is only worth
+        // starting where no arrival has been claimed right behind it (the orbit through that segment is
+        // still on its way), and whoever comes from behind stops at its trail.
+        const uint32_t idle = __ballot_sync(0xffffffffu, st == kIdle);
+        if (idle) {
+            if (!exhausted && (__popc(idle) >= tune.refill_at || idle == 0xffffffffu)) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&seed_next, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= total_seeds) {
+                    exhausted = true;
+                } else if (st == kIdle) {
+                    const uint32_t t = base + __popc(idle & ltmask);
+                    if (t < nseeds) {
+                        a_rel = (nseeds - 1 - t) * kG;
+                        from_overlap = a_rel >= kT;
+                        st = kArrive;
+                    } else if (t < total_seeds) {
+                        const uint32_t u = t - nseeds;
+                        const uint32_t lvl = 32 - __clz(u / nseeds + 1);           // 1, 2, 2, 3, 3, 3, 3, ...
+                        const uint32_t first = ((1u << (lvl - 1)) - 1) * nseeds;
+                        const uint32_t sp = kG >> (lvl - 1);
+                        const uint32_t idx = (nseeds << (lvl - 1)) - 1 - (u - first);
+                        const uint32_t rel = idx * sp + sp / 2;
+                        const uint32_t mask = ((1u << (sp / 2)) - 1) << (rel & 31);
+                        if (rel < kT && rel < span_len && (valid[rel >> 5] & mask) == 0) {  // own range only: room to join
+                            from_overlap = false;
+                            a_rel = rel;
+                            st = kArrive;
+                        }
+                    }
+                }
+            }
+        }
+        // ---- phase E: arrivals (claim, or stop at somebody's trail), phase F: walks begin ----
+        if (__any_sync(0xffffffffu, st == kArrive)) {
+            if (st == kArrive) arrive();
+        }
+        if (__any_sync(0xffffffffu, st == kStart)) {
+            if (st == kStart) start_search();
+        }
+        if (exhausted && __ballot_sync(0xffffffffu, st != kIdle) == 0) break;
+    }
+    __syncthreads();
+    if (open_end) {
+        const uint32_t cnt = cross_cnt;
+        if (threadIdx.x < min(cnt, kMaxCross)) {
+            const uint32_t r = cross[threadIdx.x];
+            if (!((safe[r >> 5] >> (r & 31)) & 1u)) atomicOr(flags, 1u);
+        }
+        if (threadIdx.x == 0 && cnt > kMaxCross) atomicOr(flags, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K3a: lazy step.  deflate.zig:160-193 restricted to arrivals with no pending match.
 // From such an arrival at p the reference emits k literals p..p+k-1 (each displaced by a strictly
 // longer match one byte later) and then one match at p+k, or a single literal if nothing matches.
@@ -846,7 +1181,7 @@ chunk_exit_kernel(const uint32_t* __restrict__ nx, uint32_t n, uint16_t* __restr
     const uint32_t cs = c * kChunk;
     for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
         const uint32_t p = cs + i;
-        nxt[i] = (uint16_t)(p < n ? i + nx_step(nx[p]) : kChunk);
+        nxt[i] = (uint16_t)(p < n ? i + nx_step(nx_clean(nx[p])) : kChunk);
     }
     __syncthreads();
     while (true) {
@@ -919,7 +1254,7 @@ orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* _
         const uint32_t p = cs + i;
         uint32_t s = 1, t = 0;
         if (p < n) {
-            const uint32_t v = nx[p];
+            const uint32_t v = nx_clean(nx[p]);
             s = nx_step(v);
             t = (v >> 16) ? (v & 255u) + 1 : 1;
         }
@@ -1022,7 +1357,8 @@ constexpr uint32_t kEmitThreads = 256;
 __global__ void __launch_bounds__(kEmitThreads)
 emit_tokens_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ nx, uint32_t n,
                    const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ tok_offset, LevelArgs lv,
-                   uint32_t* __restrict__ tokens, uint32_t* __restrict__ cut_rp) {
+                   uint32_t* __restrict__ tokens, uint32_t* __restrict__ cut_rp, uint32_t* __restrict__ flags) {
+    // flags (may be null): bit 1 is set when the orbit meets an entry the sparse parse never evaluated
     __shared__ uint32_t warp_sums[kEmitThreads / 32];
     const uint32_t c = blockIdx.x;
     const uint32_t cs = c * kChunk;
@@ -1033,7 +1369,7 @@ emit_tokens_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
     // tokens of my arrivals
     uint32_t mine = 0;
     for (uint32_t m = mask; m; m &= m - 1) {
-        const uint32_t v = nx[cs + i0 + (__ffs(m) - 1)];
+        const uint32_t v = nx_clean(nx[cs + i0 + (__ffs(m) - 1)]);
         mine += (v >> 16) ? (v & 255u) + 1 : 1;
     }
     uint32_t x = mine;
@@ -1048,7 +1384,11 @@ emit_tokens_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
     uint32_t t = tok_offset[c] + wprefix + x - mine;
     for (uint32_t m = mask; m; m &= m - 1) {
         const uint32_t p = cs + i0 + (__ffs(m) - 1);
-        const uint32_t v = nx[p];
+        uint32_t v = nx[p];
+        if (v == kNxInvalid) {
+            if (flags) atomicOr(flags, 2u);
+            v = 0;
+        }
         if ((v >> 16) == 0) {
             tokens[t] = in[p];
             if ((t & (kTokensPerBlock - 1)) == kTokensPerBlock - 1) cut_rp[t >> 15] = p + 1;
@@ -1076,6 +1416,9 @@ static int g_num_sms = 148;
 static int g_search_steps = 8;
 static SearchTune g_tune{3, 8};
 static int g_use_roll = 0;
+constexpr uint32_t kSparseT = 4096, kSparseWideT = 32768, kSparseW = 512;
+static int g_sparse_variant = 0;  // see lz77_sparse_range
+static SparseTune g_sparse_tune{2, 4, 4, 0};
 static void lz77_init_once() {
     // function attributes are per device: a process may hold contexts on several GPUs
     static bool done[64] = {};
@@ -1091,6 +1434,14 @@ static void lz77_init_once() {
     cudaFuncSetAttribute(match_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
     cudaFuncSetAttribute(match_search_roll_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
     cudaFuncSetAttribute(match_search_roll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
+#define FB_SPARSE_ATTR(T, G, TH, MB) cudaFuncSetAttribute(sparse_parse_kernel<T, kSparseW, G, TH, MB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SparseCfg<T, kSparseW>::kSmem)
+    FB_SPARSE_ATTR(kSparseWideT, 32, 1024, 1);
+    FB_SPARSE_ATTR(kSparseWideT, 32, 512, 1);
+    FB_SPARSE_ATTR(kSparseWideT, 32, 256, 1);
+    FB_SPARSE_ATTR(kSparseWideT, 16, 1024, 1);
+    FB_SPARSE_ATTR(kSparseWideT, 16, 512, 1);
+    FB_SPARSE_ATTR(kSparseT, 16, 256, 2);
+#undef FB_SPARSE_ATTR
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (knobs_read) return;
     knobs_read = true;
@@ -1105,6 +1456,13 @@ static void lz77_init_once() {
     }
     const char* e = getenv("FB200_SEARCH");
     g_use_roll = (e && e[0] == 'r') ? 1 : 0;
+    // FB200_SPARSE="variant[,pend_at,done_at,refill_at,levels]": shape and pacing of the sparse parse kernel
+    if (const char* sp = getenv("FB200_SPARSE")) {
+        int v = 0, p = 0, d = 0, r = 0, l = 0;
+        const int got = sscanf(sp, "%d,%d,%d,%d,%d", &v, &p, &d, &r, &l);
+        if (got >= 1) g_sparse_variant = v;
+        if (got == 5) g_sparse_tune = SparseTune{(uint32_t)p, (uint32_t)d, (uint32_t)r, (uint32_t)l};
+    }
 }
 
 // K1 + K2 for stream positions [from, range_end) of the segment that starts at seg_begin.  `from` and
@@ -1148,6 +1506,47 @@ cudaError_t lz77_search_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_
     return cudaGetLastError();
 }
 
+// K1 alone for positions [link_from, range_end).
+cudaError_t lz77_link_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t link_from, uint32_t range_end, uint32_t n,
+                            cudaStream_t st, PhaseTimer* pt) {
+    lz77_init_once();
+    PhaseTimer dummy;
+    if (!pt) pt = &dummy;
+    if (range_end <= link_from) return cudaSuccess;
+    const uint32_t ntiles = (range_end + kLinkTile - 1) / kLinkTile - link_from / kLinkTile;
+    const uint32_t slots = 2 * (uint32_t)g_num_sms;
+    const uint32_t waves = (ntiles + slots * 32 - 1) / (slots * 32);
+    const uint32_t run = max(1u, (ntiles + slots * waves - 1) / (slots * waves));
+    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, link_from, range_end, n, run, nullptr, 0, b.link);
+    pt->mark(st, kPhLink);
+    return cudaGetLastError();
+}
+
+// K2s for the sparse-parse chunks [first_chunk, end_chunk) of a stream of n positions (begin = 0, no skip list).
+// b.link must be complete up to min(n, end_chunk * T + W + 256); b.nx must have been filled with kNxInvalid.
+uint32_t lz77_sparse_chunk() { lz77_init_once(); return g_sparse_variant == 5 ? kSparseT : kSparseWideT; }
+uint32_t lz77_sparse_lookahead() { return kSparseW + kSpHalo + 272; }
+cudaError_t lz77_sparse_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t first_chunk, uint32_t end_chunk, uint32_t n,
+                              const LevelArgs& lv, uint32_t* flags, cudaStream_t st, PhaseTimer* pt) {
+    lz77_init_once();
+    PhaseTimer dummy;
+    if (!pt) pt = &dummy;
+    if (end_chunk <= first_chunk) return cudaSuccess;
+    const uint32_t grid = end_chunk - first_chunk;
+#define FB_SPARSE(T, G, TH, MB) sparse_parse_kernel<T, kSparseW, G, TH, MB, 4><<<grid, TH, SparseCfg<T, kSparseW>::kSmem, st>>>(d_in, first_chunk, n, b.link, lv, g_sparse_tune, b.nx, flags)
+    switch (g_sparse_variant) {
+        case 1: FB_SPARSE(kSparseWideT, 32, 512, 1); break;
+        case 2: FB_SPARSE(kSparseWideT, 32, 256, 1); break;
+        case 3: FB_SPARSE(kSparseWideT, 16, 1024, 1); break;
+        case 4: FB_SPARSE(kSparseWideT, 16, 512, 1); break;
+        case 5: FB_SPARSE(kSparseT, 16, 256, 2); break;
+        default: FB_SPARSE(kSparseWideT, 32, 1024, 1); break;
+    }
+#undef FB_SPARSE
+    pt->mark(st, kPhSparse);
+    return cudaGetLastError();
+}
+
 // K3: lazy parse + token emission of the segment [begin, n) from the match tables.
 cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin, uint32_t n, const LevelArgs& lv,
                        cudaStream_t st, PhaseTimer* pt) {
@@ -1172,7 +1571,7 @@ cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin
     pt->mark(st, kPhMark);
     scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
     pt->mark(st, kPhScan);
-    emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_seg, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp);
+    emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_seg, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp, nullptr);
     pt->mark(st, kPhEmit);
     return cudaGetLastError();
 }
@@ -1197,7 +1596,7 @@ cudaError_t lz77_shard_search(const Lz77Buffers& b, const uint8_t* d_in, uint32_
 
 // Stage 2 on one rank: parse + token emission from a complete nx table (b.nx).
 cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
-                               PhaseTimer* pt) {
+                               PhaseTimer* pt, uint32_t* flags) {
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
     if (n == 0) {
@@ -1216,7 +1615,7 @@ cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32
     pt->mark(st, kPhMark);
     scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
     pt->mark(st, kPhScan);
-    emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_in, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp);
+    emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_in, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp, flags);
     pt->mark(st, kPhEmit);
     return cudaGetLastError();
 }

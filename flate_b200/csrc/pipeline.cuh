@@ -8,7 +8,7 @@ namespace fb {
 // the dominant kernel's duration live.  Off by default: mark() is then a no-op.
 enum Phase : int {
     kPhLink = 0, kPhSearch, kPhLazy, kPhChunkExit, kPhResolve, kPhMark, kPhScan, kPhEmit, kPhHist, kPhBuild,
-    kPhOffsets, kPhPack, kPhInflate, kPhCount
+    kPhOffsets, kPhPack, kPhInflate, kPhSparse, kPhCount
 };
 struct PhaseTimer {
     static constexpr int kMaxMarks = 64;
@@ -86,7 +86,17 @@ cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin
 cudaError_t lz77_shard_search(const Lz77Buffers& b, const uint8_t* d_in, uint32_t from, uint32_t to, uint32_t n,
                               const LevelArgs& lv, uint32_t* nx_out, cudaStream_t st, PhaseTimer* pt = nullptr);
 cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
-                               PhaseTimer* pt = nullptr);
+                               PhaseTimer* pt = nullptr, uint32_t* flags = nullptr);
+
+// sparse parse (whole streams, begin = 0): links, then the speculative sparse kernel writes nx directly;
+// lz77_parse_from_nx finishes.  *flags != 0 afterwards means the speculation did not cover the true
+// orbit and the caller must redo the stream with lz77_tokenize (dense tables).
+cudaError_t lz77_link_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t link_from, uint32_t range_end, uint32_t n,
+                            cudaStream_t st, PhaseTimer* pt = nullptr);
+uint32_t lz77_sparse_chunk();      // positions per sparse-parse CTA
+uint32_t lz77_sparse_lookahead();  // positions past a chunk's end that must be linked and resident
+cudaError_t lz77_sparse_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t first_chunk, uint32_t end_chunk, uint32_t n,
+                              const LevelArgs& lv, uint32_t* flags, cudaStream_t st, PhaseTimer* pt = nullptr);
 
 // ---- block writer ----
 enum WriteKind : uint32_t { kWrite = 0, kDynamicBlock = 1, kHuffmanBlock = 2 };  // block_writer.zig:307,395,524

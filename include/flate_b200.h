@@ -76,6 +76,13 @@ const char* fb200_strerror(int code);
 const char* fb200_last_cuda_error(void);
 /* number of this library's kernels launched by ctx since creation (bench.py's gpu_launches) */
 uint64_t fb200_kernel_launches(const fb200_ctx* ctx);
+/* Parse strategy of the level modes.  0 (default): f(p), the lazy-parse step of deflate.zig:160-193, is
+ * evaluated only on the orbits of seeds placed every few positions (speculative sparse parse), with an exact
+ * coverage check and an automatic redo with mode 1 when the check fails; 1: match tables for every position
+ * (findMatch deflate.zig:233-266 under both budgets).  Both give the reference's bytes; mode 1 exists for
+ * tests and for inputs known to be periodic.  fb200_sparse_fallbacks counts the automatic redos. */
+int fb200_ctx_set_parse_mode(fb200_ctx* ctx, int mode);
+uint64_t fb200_sparse_fallbacks(const fb200_ctx* ctx);
 /* optional per-phase device timing with CUDA events on the launching stream (for bench.py's roofline) */
 int fb200_profile_enable(fb200_ctx* ctx, int on); /* also clears the accumulated times */
 int fb200_profile_phases(void);
