@@ -21,6 +21,7 @@ SIGNATURES = {
     "fb200_kernel_launches": (C.c_uint64, [_P]),
     "fb200_ctx_set_parse_mode": (_I, [_P, _I]),
     "fb200_sparse_fallbacks": (C.c_uint64, [_P]),
+    "fb200_sparse_repairs": (C.c_uint64, [_P]),
     "fb200_profile_enable": (_I, [_P, _I]),
     "fb200_profile_phases": (_I, []),
     "fb200_profile_phase_name": (C.c_char_p, [_I]),

@@ -88,6 +88,10 @@ class Context:
     def sparse_fallbacks(self):
         return int(self.lib.fb200_sparse_fallbacks(self.h))
 
+    @property
+    def sparse_repairs(self):
+        return int(self.lib.fb200_sparse_repairs(self.h))
+
     def profile(self, on=True):
         self.lib.fb200_profile_enable(self.h, int(on))
 

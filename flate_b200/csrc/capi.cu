@@ -93,9 +93,11 @@ struct fb200_ctx {
     PhaseTimer timer;
     int parse_mode = 0;              // 0 = sparse parse with dense fallback, 1 = dense tables always
     uint64_t sparse_fallbacks = 0;   // streams redone with the dense tables
+    uint64_t sparse_repairs = 0;     // streams whose sparse parse was completed by evaluating some chunks densely
     // LZ77 workspace
     DevBuf<uint16_t> link, exits, gexits, gentry, entry;
     DevBuf<uint32_t> r_full, r_quarter, nx, bitmap, chunk_tokens, tok_offset, tokens, cut_rp;
+    DevBuf<uint32_t> chunk_fail, chunk_list;  // sparse parse: coverage check per chunk, chunks to repair
     // block writer workspace
     DevBuf<BlockPlan> plans;
     DevBuf<BlockDesc> descs;
@@ -136,6 +138,7 @@ int fb200_ctx_set_parse_mode(fb200_ctx* ctx, int mode) {
     return FB200_OK;
 }
 uint64_t fb200_sparse_fallbacks(const fb200_ctx* ctx) { return ctx ? ctx->sparse_fallbacks : 0; }
+uint64_t fb200_sparse_repairs(const fb200_ctx* ctx) { return ctx ? ctx->sparse_repairs : 0; }
 uint64_t fb200_kernel_launches(const fb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int fb200_profile_enable(fb200_ctx* ctx, int on) {
     if (!ctx) return FB200_INVALID_ARGUMENT;
@@ -217,6 +220,8 @@ static int ensure_lz77(fb200_ctx* c, size_t n) {
     FB_CUDA_CHECK(c->tok_offset.ensure(nchunks));
     FB_CUDA_CHECK(c->tokens.ensure(n + 64));
     FB_CUDA_CHECK(c->cut_rp.ensure(n / kTokensPerBlock + 4));
+    FB_CUDA_CHECK(c->chunk_fail.ensure(n / lz77_sparse_chunk() + 2));
+    FB_CUDA_CHECK(c->chunk_list.ensure(n / lz77_sparse_chunk() + 2));
     return FB200_OK;
 }
 static int ensure_blocks(fb200_ctx* c, size_t max_blocks) {
@@ -258,9 +263,44 @@ static int sparse_tokenize(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_
     if (rc) return rc;
     const uint32_t T = lz77_sparse_chunk();
     FB_CUDA_CHECK(lz77_link_range(b, d_in, 0, (uint32_t)n, (uint32_t)n, st, &c->timer));
-    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, 0, (uint32_t)((n + T - 1) / T), (uint32_t)n, lv, c->d_scalars + kSparseFlagIdx, st, &c->timer));
+    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, 0, (uint32_t)((n + T - 1) / T), (uint32_t)n, lv, c->chunk_fail.p, c->d_scalars + kSparseFlagIdx, st, &c->timer));
     FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
     c->launches += 9;
+    return FB200_OK;
+}
+
+// The coverage check of some chunks failed (stream synchronized, flag bit 0 set, bit 1 may be a consequence):
+// evaluate every position of the chunks that follow a failed chunk; a repaired chunk that fails itself
+// hands the problem to its successor.  Afterwards nx is closed under the lazy step again and the caller
+// parses once more.  Returns FB200_OK and *ok = false when it gives up (caller redoes the stream densely).
+static int sparse_repair(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in, size_t n, const LevelArgs& lv, cudaStream_t st,
+                         bool* ok) {
+    *ok = false;
+    const uint32_t T = lz77_sparse_chunk();
+    const uint32_t nch = (uint32_t)((n + T - 1) / T);
+    std::vector<uint32_t> fail(nch), list;
+    std::vector<uint8_t> dense(nch, 0);
+    FB_CUDA_CHECK(cudaMemcpyAsync(fail.data(), c->chunk_fail.p, nch * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i + 1 < nch; i++)
+        if (fail[i]) list.push_back(i + 1);
+    size_t total = 0;
+    for (int round = 0; round < 6 && !list.empty(); round++) {
+        total += list.size();
+        if (total > nch / 2 + 1) return FB200_OK;  // mostly periodic data: the dense tables are the better tool
+        for (uint32_t ch : list) dense[ch] = 1;
+        FB_CUDA_CHECK(cudaMemcpyAsync(c->chunk_list.p, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        FB_CUDA_CHECK(lz77_sparse_dense_chunks(b, d_in, c->chunk_list.p, (uint32_t)list.size(), (uint32_t)n, lv, c->chunk_fail.p,
+                                               c->d_scalars + kSparseFlagIdx, st, &c->timer));
+        c->launches += 1;
+        FB_CUDA_CHECK(cudaMemcpyAsync(fail.data(), c->chunk_fail.p, nch * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        std::vector<uint32_t> next;
+        for (uint32_t ch : list)
+            if (fail[ch] && ch + 1 < nch && !dense[ch + 1]) next.push_back(ch + 1);
+        list.swap(next);
+    }
+    *ok = list.empty();
     return FB200_OK;
 }
 
@@ -272,7 +312,8 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
                                const uint32_t* d_skip, uint32_t nskip, uint8_t* d_out, size_t cap, size_t* end_bytes,
                                bool final_flush, bool with_header, cudaStream_t st, const uint8_t* h_src = nullptr,
                                uint8_t* h_dst = nullptr, size_t h_cap = 0, const uint32_t* d_nx_given = nullptr,
-                               bool force_dense = false) {
+                               int redo = 0) {
+    // redo: 1 = links and a repaired nx table are in place, only parse again; 2 = dense match tables
     // d_nx_given != nullptr: the lazy-step table of the whole stream was produced elsewhere (position-sharded
     // search on several GPUs); only the parse and the block writer run here.
     // h_dst != nullptr: the packed bytes are also copied to host memory at h_dst, part by part, while later
@@ -300,11 +341,16 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         Lz77Buffers b = lz77_view(c);
         c->timer.begin(st);
         constexpr size_t kSlab = 32u << 20, kFirst = 8u << 20, kLag = 8192;  // the search of a slab lags one hash tile behind its copy
-        if (d_nx_given) {
+        if (redo == 1) {
+            sparse = true;
+            FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
+            FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
+            c->launches += 7;
+        } else if (d_nx_given) {
             b.nx = const_cast<uint32_t*>(d_nx_given);
             FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer));
             c->launches += n ? 7 : 0;
-        } else if ((sparse = (begin == 0 && nskip == 0 && n > 0 && !force_dense && c->parse_mode == 0)) && !(h_src && n > kSlab + kLag)) {
+        } else if ((sparse = (begin == 0 && nskip == 0 && n > 0 && redo == 0 && c->parse_mode == 0)) && !(h_src && n > kSlab + kLag)) {
             if (h_src) FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in), h_src, n, cudaMemcpyHostToDevice, st));
             if ((rc = sparse_tokenize(c, b, d_in, n, lv, st))) return rc;
         } else if (sparse) {
@@ -328,7 +374,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
                 const uint32_t chunks_end = range_end == n ? (uint32_t)((n + T - 1) / T)
                                                            : (uint32_t)(range_end > ahead ? (range_end - ahead) / T : 0);
                 if (chunks_end > chunks_done) {
-                    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, chunks_done, chunks_end, (uint32_t)n, lv, c->d_scalars + kSparseFlagIdx, st, &c->timer));
+                    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, chunks_done, chunks_end, (uint32_t)n, lv, c->chunk_fail.p, c->d_scalars + kSparseFlagIdx, st, &c->timer));
                     chunks_done = chunks_end;
                 }
                 c->launches += 2;
@@ -446,11 +492,19 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     if (copied_out) FB_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
     c->timer.collect();
     if (sparse && (uint32_t)c->h_scalars[9] != 0) {
-        // the speculation did not cover the true orbit (e.g. long periodic data, where parses started at
-        // different positions never fall into step): redo the stream with the dense match tables
-        c->sparse_fallbacks++;
+        // The speculation did not cover the true orbit (periodic data, where parses started at different
+        // positions never fall into step).  First try to repair the chunks concerned; if that is not enough
+        // redo the stream with the dense match tables.
+        bool ok = false;
+        if (redo == 0) {
+            Lz77Buffers b = lz77_view(c);
+            int rc = sparse_repair(c, b, d_in, n, lv, st, &ok);
+            if (rc) return rc;
+        }
+        if (ok) c->sparse_repairs++;
+        else c->sparse_fallbacks++;
         return deflate_body_device(c, container, mode, d_in, begin, n, d_skip, nskip, d_out, cap, end_bytes, final_flush, with_header,
-                                   st, nullptr, h_dst, h_cap, nullptr, true);
+                                   st, nullptr, h_dst, h_cap, nullptr, ok ? 1 : 2);
     }
     *end_bytes = (size_t)((c->h_scalars[0] + 7) >> 3);
     return FB200_OK;
@@ -567,7 +621,18 @@ int fb200_debug_tokens(fb200_ctx* c, int level, const uint8_t* in, size_t n, uin
         if ((rc = sparse_tokenize(c, b, c->d_in.p, n, lv, st))) return rc;
         FB_CUDA_CHECK(cudaMemcpyAsync(&bad, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
         FB_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (bad) c->sparse_fallbacks++;
+        if (bad) {
+            bool ok = false;
+            if ((rc = sparse_repair(c, b, c->d_in.p, n, lv, st, &ok))) return rc;
+            if (ok) {
+                FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
+                FB_CUDA_CHECK(lz77_parse_from_nx(b, c->d_in.p, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
+                FB_CUDA_CHECK(cudaMemcpyAsync(&bad, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
+                FB_CUDA_CHECK(cudaStreamSynchronize(st));
+                if (!bad) c->sparse_repairs++;
+            }
+            if (bad) c->sparse_fallbacks++;
+        }
     }
     if (c->parse_mode != 0 || n == 0 || bad) {
         FB_CUDA_CHECK(lz77_tokenize(b, c->d_in.p, 0, (uint32_t)n, nullptr, 0, lv, st));

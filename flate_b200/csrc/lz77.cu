@@ -764,7 +764,6 @@ struct SparseTune {
     uint32_t pend_at;    // run the batched full compares once this many lanes wait for one
     uint32_t done_at;    // run the lazy decisions once this many lanes finished a walk
     uint32_t refill_at;  // hand out new seeds once this many lanes are idle
-    uint32_t levels;     // levels of split seeds handed out after the regular ones (0 = none)
 };
 template <uint32_t kT, uint32_t kW>
 struct SparseCfg {
@@ -777,27 +776,34 @@ struct SparseCfg {
 enum : uint32_t { kSearchDone = 4, kArrive = 5, kStart = 6 };
 constexpr uint32_t kMaxCross = 32;
 
-template <uint32_t kT, uint32_t kW, uint32_t kG, uint32_t kThreads, int kMinBlocks, int kSteps>
+template <uint32_t kT, uint32_t kW, uint32_t kG, uint32_t kThreads, int kMinBlocks, int kSteps, bool kDense>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, uint32_t n, const uint16_t* __restrict__ link,
-                    LevelArgs lv, SparseTune tune, uint32_t* __restrict__ nx, uint32_t* __restrict__ flags) {
+sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, const uint32_t* __restrict__ chunk_list, uint32_t n,
+                    const uint16_t* __restrict__ link, LevelArgs lv, SparseTune tune, uint32_t* __restrict__ nx,
+                    uint32_t* __restrict__ chunk_fail, uint32_t* __restrict__ flags) {
+    // kDense: every position of the CTA's own range is a seed (the overlap keeps the regular seeds, the ones
+    // the next CTA evaluates too).  Used to repair after a failed coverage check: once every entry of chunk
+    // c+1 is evaluated, it no longer matters where the orbits leaving chunk c arrive.
+    // chunk_list (may be null): the chunks to process, one per CTA; else chunk = first_chunk + blockIdx.x.
     using C = SparseCfg<kT, kW>;
     static_assert(C::kBytes % 16 == 0 && (C::kLinks * 2) % 16 == 0 && kT % kG == 0 && kW % kG == 0, "layout");
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ uint32_t seed_next, cross_cnt;
+    __shared__ uint32_t seed_next, cross_cnt, failed;
     __shared__ uint32_t cross[kMaxCross];
     __shared__ __align__(8) uint64_t stage_bar;
     uint8_t* sb = smem_raw;                                               // bytes, slot i+16 = position wb+i
     uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + C::kBytes);     // link (distance, kNoLink = none) per slot
     uint32_t* valid = reinterpret_cast<uint32_t*>(smem_raw + C::kBytes + C::kLinks * 2);  // arrivals claimed by some lane
     uint32_t* safe = valid + C::kWords;                                   // arrivals on the orbit of an overlap seed
-    const uint32_t s = (first_chunk + blockIdx.x) * kT;                   // first own position
+    const uint32_t chunk = chunk_list ? chunk_list[blockIdx.x] : first_chunk + blockIdx.x;
+    const uint32_t s = chunk * kT;                                        // first own position
     const int64_t wb = (int64_t)s - kHist;
     const uint32_t lo = wb < 0 ? (uint32_t)(-wb) : 0;
     const uint32_t span_len = min(C::kSpan, n - s);                       // arrivals evaluated here: offsets < span_len
     const bool open_end = (uint64_t)s + C::kSpan < n;                     // the stream goes on past the span
-    const uint32_t nseeds = (span_len + kG - 1) / kG;
-    const uint32_t total_seeds = nseeds << min(tune.levels, kG == 32 ? 3u : 2u);  // levels of split seeds: n, n, 2n, 4n
+    const uint32_t own_len = min(kT, span_len);
+    const uint32_t n_ov = (span_len - own_len + kG - 1) / kG;              // regular seeds in the overlap
+    const uint32_t nseeds = kDense ? n_ov + own_len : (span_len + kG - 1) / kG;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t ltmask = (1u << lane) - 1;
 
@@ -805,6 +811,7 @@ sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, uint32
     if (threadIdx.x == 0) {
         seed_next = 0;
         cross_cnt = 0;
+        failed = 0;
     }
     // ---- stage window (same scheme as match_search_kernel) ----
     constexpr uint32_t kBytesTx = C::kBytes - kSearchOff, kLinksTx = (C::kLinks - kSearchOff) * 2;
@@ -1018,40 +1025,22 @@ sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, uint32
                 if (st == kSearchDone) decide();
             }
         }
-        // ---- phase D: new seeds for idle lanes ----
-        // Level 0: every kG positions, last segment first (so a lane soon meets the trail of the segment
-        // ahead).  When those run out, idle lanes split the work of the slow ones: level l >= 1 puts seeds
-        // half-way between the seeds of the levels above (spacing kG >> (l-1)); such a seed is only worth
-        // starting where no arrival has been claimed right behind it (the orbit through that segment is
-        // still on its way), and whoever comes from behind stops at its trail.
+        // ---- phase D: new seeds for idle lanes, last segment first (a lane soon meets the trail of the
+        // segment ahead) ----
         const uint32_t idle = __ballot_sync(0xffffffffu, st == kIdle);
-        if (idle) {
-            if (!exhausted && (__popc(idle) >= tune.refill_at || idle == 0xffffffffu)) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&seed_next, (uint32_t)__popc(idle));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base >= total_seeds) {
-                    exhausted = true;
-                } else if (st == kIdle) {
-                    const uint32_t t = base + __popc(idle & ltmask);
-                    if (t < nseeds) {
-                        a_rel = (nseeds - 1 - t) * kG;
-                        from_overlap = a_rel >= kT;
-                        st = kArrive;
-                    } else if (t < total_seeds) {
-                        const uint32_t u = t - nseeds;
-                        const uint32_t lvl = 32 - __clz(u / nseeds + 1);           // 1, 2, 2, 3, 3, 3, 3, ...
-                        const uint32_t first = ((1u << (lvl - 1)) - 1) * nseeds;
-                        const uint32_t sp = kG >> (lvl - 1);
-                        const uint32_t idx = (nseeds << (lvl - 1)) - 1 - (u - first);
-                        const uint32_t rel = idx * sp + sp / 2;
-                        const uint32_t mask = ((1u << (sp / 2)) - 1) << (rel & 31);
-                        if (rel < kT && rel < span_len && (valid[rel >> 5] & mask) == 0) {  // own range only: room to join
-                            from_overlap = false;
-                            a_rel = rel;
-                            st = kArrive;
-                        }
-                    }
+        if (idle && !exhausted && (__popc(idle) >= tune.refill_at || idle == 0xffffffffu)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&seed_next, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= nseeds) {
+                exhausted = true;
+            } else if (st == kIdle) {
+                const uint32_t t = base + __popc(idle & ltmask);
+                if (t < nseeds) {
+                    if (kDense) a_rel = t < n_ov ? kT + (n_ov - 1 - t) * kG : own_len - 1 - (t - n_ov);
+                    else a_rel = (nseeds - 1 - t) * kG;
+                    from_overlap = a_rel >= kT;
+                    st = kArrive;
                 }
             }
         }
@@ -1069,9 +1058,14 @@ sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, uint32
         const uint32_t cnt = cross_cnt;
         if (threadIdx.x < min(cnt, kMaxCross)) {
             const uint32_t r = cross[threadIdx.x];
-            if (!((safe[r >> 5] >> (r & 31)) & 1u)) atomicOr(flags, 1u);
+            if (!((safe[r >> 5] >> (r & 31)) & 1u)) failed = 1;
         }
-        if (threadIdx.x == 0 && cnt > kMaxCross) atomicOr(flags, 1u);
+        if (threadIdx.x == 0 && cnt > kMaxCross) failed = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        chunk_fail[chunk] = failed;  // orbits of this chunk's own range may arrive anywhere in the next chunk
+        if (failed) atomicOr(flags, 1u);
     }
 }
 
@@ -1416,9 +1410,9 @@ static int g_num_sms = 148;
 static int g_search_steps = 8;
 static SearchTune g_tune{3, 8};
 static int g_use_roll = 0;
-constexpr uint32_t kSparseT = 4096, kSparseWideT = 32768, kSparseW = 512;
+constexpr uint32_t kSparseT = 32768, kSparseW = 1024, kSparseThreads = 1024;
 static int g_sparse_variant = 0;  // see lz77_sparse_range
-static SparseTune g_sparse_tune{2, 4, 4, 0};
+static SparseTune g_sparse_tune{1, 1, 1};
 static void lz77_init_once() {
     // function attributes are per device: a process may hold contexts on several GPUs
     static bool done[64] = {};
@@ -1434,13 +1428,11 @@ static void lz77_init_once() {
     cudaFuncSetAttribute(match_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSearchSmem);
     cudaFuncSetAttribute(match_search_roll_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
     cudaFuncSetAttribute(match_search_roll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRollSmem);
-#define FB_SPARSE_ATTR(T, G, TH, MB) cudaFuncSetAttribute(sparse_parse_kernel<T, kSparseW, G, TH, MB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SparseCfg<T, kSparseW>::kSmem)
-    FB_SPARSE_ATTR(kSparseWideT, 32, 1024, 1);
-    FB_SPARSE_ATTR(kSparseWideT, 32, 512, 1);
-    FB_SPARSE_ATTR(kSparseWideT, 32, 256, 1);
-    FB_SPARSE_ATTR(kSparseWideT, 16, 1024, 1);
-    FB_SPARSE_ATTR(kSparseWideT, 16, 512, 1);
-    FB_SPARSE_ATTR(kSparseT, 16, 256, 2);
+#define FB_SPARSE_ATTR(G, ST, D) cudaFuncSetAttribute(sparse_parse_kernel<kSparseT, kSparseW, G, kSparseThreads, 1, ST, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SparseCfg<kSparseT, kSparseW>::kSmem)
+    FB_SPARSE_ATTR(32, 8, false);
+    FB_SPARSE_ATTR(32, 4, false);
+    FB_SPARSE_ATTR(16, 8, false);
+    FB_SPARSE_ATTR(32, 8, true);
 #undef FB_SPARSE_ATTR
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (knobs_read) return;
@@ -1456,12 +1448,12 @@ static void lz77_init_once() {
     }
     const char* e = getenv("FB200_SEARCH");
     g_use_roll = (e && e[0] == 'r') ? 1 : 0;
-    // FB200_SPARSE="variant[,pend_at,done_at,refill_at,levels]": shape and pacing of the sparse parse kernel
+    // FB200_SPARSE="variant[,pend_at,done_at,refill_at]": shape and pacing of the sparse parse kernel
     if (const char* sp = getenv("FB200_SPARSE")) {
-        int v = 0, p = 0, d = 0, r = 0, l = 0;
-        const int got = sscanf(sp, "%d,%d,%d,%d,%d", &v, &p, &d, &r, &l);
+        int v = 0, p = 0, d = 0, r = 0;
+        const int got = sscanf(sp, "%d,%d,%d,%d", &v, &p, &d, &r);
         if (got >= 1) g_sparse_variant = v;
-        if (got == 5) g_sparse_tune = SparseTune{(uint32_t)p, (uint32_t)d, (uint32_t)r, (uint32_t)l};
+        if (got == 4) g_sparse_tune = SparseTune{(uint32_t)p, (uint32_t)d, (uint32_t)r};
     }
 }
 
@@ -1524,25 +1516,35 @@ cudaError_t lz77_link_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t 
 
 // K2s for the sparse-parse chunks [first_chunk, end_chunk) of a stream of n positions (begin = 0, no skip list).
 // b.link must be complete up to min(n, end_chunk * T + W + 256); b.nx must have been filled with kNxInvalid.
-uint32_t lz77_sparse_chunk() { lz77_init_once(); return g_sparse_variant == 5 ? kSparseT : kSparseWideT; }
+// chunk_fail[c] is set when orbits leaving chunk c were not seen to join the next chunk's seeds.
+uint32_t lz77_sparse_chunk() { return kSparseT; }
 uint32_t lz77_sparse_lookahead() { return kSparseW + kSpHalo + 272; }
 cudaError_t lz77_sparse_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t first_chunk, uint32_t end_chunk, uint32_t n,
-                              const LevelArgs& lv, uint32_t* flags, cudaStream_t st, PhaseTimer* pt) {
+                              const LevelArgs& lv, uint32_t* chunk_fail, uint32_t* flags, cudaStream_t st, PhaseTimer* pt) {
     lz77_init_once();
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
     if (end_chunk <= first_chunk) return cudaSuccess;
     const uint32_t grid = end_chunk - first_chunk;
-#define FB_SPARSE(T, G, TH, MB) sparse_parse_kernel<T, kSparseW, G, TH, MB, 4><<<grid, TH, SparseCfg<T, kSparseW>::kSmem, st>>>(d_in, first_chunk, n, b.link, lv, g_sparse_tune, b.nx, flags)
+#define FB_SPARSE(G, ST) sparse_parse_kernel<kSparseT, kSparseW, G, kSparseThreads, 1, ST, false><<<grid, kSparseThreads, SparseCfg<kSparseT, kSparseW>::kSmem, st>>>(d_in, first_chunk, nullptr, n, b.link, lv, g_sparse_tune, b.nx, chunk_fail, flags)
     switch (g_sparse_variant) {
-        case 1: FB_SPARSE(kSparseWideT, 32, 512, 1); break;
-        case 2: FB_SPARSE(kSparseWideT, 32, 256, 1); break;
-        case 3: FB_SPARSE(kSparseWideT, 16, 1024, 1); break;
-        case 4: FB_SPARSE(kSparseWideT, 16, 512, 1); break;
-        case 5: FB_SPARSE(kSparseT, 16, 256, 2); break;
-        default: FB_SPARSE(kSparseWideT, 32, 1024, 1); break;
+        case 1: FB_SPARSE(32, 4); break;
+        case 2: FB_SPARSE(16, 8); break;
+        default: FB_SPARSE(32, 8); break;
     }
 #undef FB_SPARSE
+    pt->mark(st, kPhSparse);
+    return cudaGetLastError();
+}
+// Repair: evaluates every position of the listed chunks (device array of `count` chunk numbers).
+cudaError_t lz77_sparse_dense_chunks(const Lz77Buffers& b, const uint8_t* d_in, const uint32_t* chunk_list, uint32_t count, uint32_t n,
+                                     const LevelArgs& lv, uint32_t* chunk_fail, uint32_t* flags, cudaStream_t st, PhaseTimer* pt) {
+    lz77_init_once();
+    PhaseTimer dummy;
+    if (!pt) pt = &dummy;
+    if (count == 0) return cudaSuccess;
+    sparse_parse_kernel<kSparseT, kSparseW, 32, kSparseThreads, 1, 8, true><<<count, kSparseThreads, SparseCfg<kSparseT, kSparseW>::kSmem, st>>>(
+        d_in, 0, chunk_list, n, b.link, lv, g_sparse_tune, b.nx, chunk_fail, flags);
     pt->mark(st, kPhSparse);
     return cudaGetLastError();
 }

@@ -83,6 +83,8 @@ uint64_t fb200_kernel_launches(const fb200_ctx* ctx);
  * tests and for inputs known to be periodic.  fb200_sparse_fallbacks counts the automatic redos. */
 int fb200_ctx_set_parse_mode(fb200_ctx* ctx, int mode);
 uint64_t fb200_sparse_fallbacks(const fb200_ctx* ctx);
+/* streams whose coverage check failed for some chunks and was repaired by evaluating those chunks densely */
+uint64_t fb200_sparse_repairs(const fb200_ctx* ctx);
 /* optional per-phase device timing with CUDA events on the launching stream (for bench.py's roofline) */
 int fb200_profile_enable(fb200_ctx* ctx, int on); /* also clears the accumulated times */
 int fb200_profile_phases(void);

@@ -1,8 +1,12 @@
-timeout 300 python tools/sparse_check.py > gpurun_out/sparse_wide.log 2>&1; echo "exit $?" >> gpurun_out/sparse_wide.log
-tail -n 3 gpurun_out/sparse_wide.log
+timeout 300 python tools/sparse_check.py > gpurun_out/sparse_repair.log 2>&1; echo "exit $?" >> gpurun_out/sparse_repair.log
+cat gpurun_out/sparse_repair.log
 (
-for t in 0 1 2 3 4 0,2,4,4,3 1,2,4,4,3 1,2,4,4,1 1,1,1,1,0 1,3,8,8,0 4,2,4,4,2; do
+for t in 0 2; do
 FB200_SPARSE=$t timeout 120 python tools/phase_times.py 256 6
 done
-) 2>&1 | sed -e 's/hash_link=.*sparse_parse/sparse_parse/' > gpurun_out/sparse_times.log
+timeout 120 python tools/phase_times.py 256 9
+timeout 120 python tools/phase_times.py 256 4
+FB200_PARSE_MODE=1 timeout 120 python tools/phase_times.py 256 9
+FB200_PARSE_MODE=1 timeout 120 python tools/phase_times.py 256 4
+) 2>&1 > gpurun_out/sparse_times.log
 cat gpurun_out/sparse_times.log

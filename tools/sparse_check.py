@@ -19,7 +19,9 @@ cases = [("empty", np.zeros(0, np.uint8)), ("zeros1M", np.zeros(1 << 20, np.uint
          ("lowent", rng.integers(0, 4, 300000, dtype=np.uint8)),
          ("period7", np.tile(np.arange(7, dtype=np.uint8), 100000)),
          ("mixed", synth.mixed_small(3 << 20, seed=4) if hasattr(synth, "mixed_small") else text[:3 << 20]),
-         ("text+zeros+text", np.concatenate([text[:700000], np.zeros(200000, np.uint8), text[700000:1500000]]))]
+         ("text+zeros+text", np.concatenate([text[:700000], np.zeros(200000, np.uint8), text[700000:1500000]])),
+         ("text+period+text8M", np.concatenate([text[:3000000], np.tile(np.arange(11, dtype=np.uint8), 30000), text[3000000:8000000]])),
+         ("lowent3M", rng.integers(0, 4, 3 << 20, dtype=np.uint8))]
 for k in (1, 3, 4, 5, 100, 4095, 4096, 4097, 4608, 4609, 8191, 8192, 32767, 32768, 32769, 33280, 33281, 65536, 65537,
           100000, 1 << 20, (1 << 20) + 17, 5 * (1 << 20) + 4321, 12 << 20):
     cases.append(("text%d" % k, text[:k]))
@@ -29,14 +31,16 @@ for name, d in cases:
         if level in (8, 9) and d.size > (2 << 20):
             continue
         f0 = sparse.sparse_fallbacks
+        r0 = sparse.sparse_repairs
         a = sparse.compress(d, flate_b200.RAW, level)
         b = dense.compress(d, flate_b200.RAW, level)
         ok = a == b
         fb = sparse.sparse_fallbacks - f0
-        if not ok or fb:
-            print("%s L%d: %s fallbacks=%d (sizes %d %d)" % (name, level, "OK" if ok else "DIFF", fb, len(a), len(b)), flush=True)
+        rp = sparse.sparse_repairs - r0
+        if not ok or fb or rp:
+            print("%s L%d: %s fallbacks=%d repairs=%d (sizes %d %d)" % (name, level, "OK" if ok else "DIFF", fb, rp, len(a), len(b)), flush=True)
         bad += 0 if ok else 1
     # host path == device path for the sparse mode is covered by the test-suite
-print("sparse_check SPARSE=%s: %d cases, %d mismatches, total fallbacks %d" % (
-    os.environ.get("FB200_SPARSE", "-"), len(cases), bad, sparse.sparse_fallbacks))
+print("sparse_check SPARSE=%s: %d cases, %d mismatches, total fallbacks %d, repairs %d" % (
+    os.environ.get("FB200_SPARSE", "-"), len(cases), bad, sparse.sparse_fallbacks, sparse.sparse_repairs))
 sys.exit(1 if bad else 0)
