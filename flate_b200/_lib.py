@@ -32,6 +32,8 @@ SIGNATURES = {
     "fb200_compress_device": (_I, [_P, _I, _I, _P, _SZ, _P, _SZ, _SZP, _P]),
     "fb200_decompress_members_device": (_I, [_P, _I, _P, _P, _P, _SZ, _P, _P, _P, _P, _P, _P, _P]),
     "fb200_decompress_members": (_I, [_P, _I, _P, _P, _P, _SZ, _P, _P, _P, _P, _P, _P]),
+    "fb200_shard_align": (_SZ, []),
+    "fb200_shard_overlap": (_SZ, []),
     "fb200_deflate_shard_search": (_I, [_P, _I, _P, _SZ, _SZ, _SZ, _P, _P]),
     "fb200_deflate_shard_finish": (_I, [_P, _I, _I, _P, _SZ, _P, _P, _SZ, _SZP, _P]),
     "fb200_deflate_create": (_I, [_P, _I, _I, WRITE_FN, _P, C.POINTER(_P)]),

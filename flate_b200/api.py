@@ -42,7 +42,7 @@ _ERROR_NAMES = ["Ok", "EndOfStream", "InvalidCode", "InvalidMatch", "InvalidBloc
                 "InvalidDynamicBlockHeader", "OversubscribedHuffmanTree", "IncompleteHuffmanTree",
                 "MissingEndOfBlockCode", "BadGzipHeader", "BadZlibHeader", "WrongGzipChecksum", "WrongGzipSize",
                 "WrongZlibChecksum", "UnfinishedBits", "InvalidState", "NoSpaceLeft", "InvalidArgument", "CudaError",
-                "NoDevice"]
+                "NoDevice", "RetryDense"]
 ERRORS = {}
 for _i, _n in enumerate(_ERROR_NAMES):
     if _i:
@@ -165,7 +165,21 @@ class Context:
 
     # ---- one stream sharded by position over several GPUs ----
     def shard_search(self, d_in, n, lo, hi, d_nx, level=Level.default, stream=None):
-        _check(self.lib.fb200_deflate_shard_search(self.h, level, d_in, n, lo, hi, d_nx, stream))
+        """Stage 1 of the position-sharded stream.  Returns False when the sparse parse cannot vouch for its
+        coverage (every rank must then repeat the call after set_parse_mode(1))."""
+        rc = self.lib.fb200_deflate_shard_search(self.h, level, d_in, n, lo, hi, d_nx, stream)
+        if rc == 21:
+            return False
+        _check(rc)
+        return True
+
+    @property
+    def shard_align(self):
+        return int(self.lib.fb200_shard_align())
+
+    @property
+    def shard_overlap(self):
+        return int(self.lib.fb200_shard_overlap())
 
     def shard_finish(self, d_in, n, d_nx, d_out, cap, level=Level.default, container=RAW, stream=None):
         out_len = C.c_size_t(0)

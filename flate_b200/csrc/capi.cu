@@ -128,8 +128,8 @@ const char* fb200_strerror(int code) {
                                   "WrongStoredBlockNlen", "InvalidDynamicBlockHeader", "OversubscribedHuffmanTree",
                                   "IncompleteHuffmanTree", "MissingEndOfBlockCode", "BadGzipHeader", "BadZlibHeader",
                                   "WrongGzipChecksum", "WrongGzipSize", "WrongZlibChecksum", "UnfinishedBits",
-                                  "InvalidState", "NoSpaceLeft", "InvalidArgument", "CudaError", "NoDevice"};
-    if (code < 0 || code > 20) return "Unknown";
+                                  "InvalidState", "NoSpaceLeft", "InvalidArgument", "CudaError", "NoDevice", "RetryDense"};
+    if (code < 0 || code > 21) return "Unknown";
     return names[code];
 }
 int fb200_ctx_set_parse_mode(fb200_ctx* ctx, int mode) {
@@ -248,6 +248,7 @@ static inline size_t footer_size(int container) { return container == FB200_GZIP
 // Device flags of the sparse parse (u32 index 20 of d_scalars): bit 0 = an orbit left its span unjoined,
 // bit 1 = the token emitter met an entry that was never evaluated.  Non-zero => redo with dense tables.
 constexpr int kSparseFlagIdx = 20;
+constexpr size_t kSpHaloPlus = 256 + 272;  // lz77_sparse_lookahead() = overlap + lazy halo + compare look-ahead
 static int sparse_begin(fb200_ctx* c, const Lz77Buffers& b, size_t n, cudaStream_t st) {
     FB_CUDA_CHECK(cudaMemsetAsync(b.nx, 0xFF, n * sizeof(uint32_t), st));
     FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
@@ -348,7 +349,8 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
             c->launches += 7;
         } else if (d_nx_given) {
             b.nx = const_cast<uint32_t*>(d_nx_given);
-            FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer));
+            FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
+            FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
             c->launches += n ? 7 : 0;
         } else if ((sparse = (begin == 0 && nskip == 0 && n > 0 && redo == 0 && c->parse_mode == 0)) && !(h_src && n > kSlab + kLag)) {
             if (h_src) FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in), h_src, n, cudaMemcpyHostToDevice, st));
@@ -487,10 +489,11 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     }
     if (container != FB200_RAW && final_flush) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 8, sum_dev, 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8, cudaMemcpyDeviceToHost, st));
-    if (sparse) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 9, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
+    if (sparse || d_nx_given) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 9, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
     if (copied_out) FB_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
     c->timer.collect();
+    if (d_nx_given && (uint32_t)c->h_scalars[9] != 0) return FB200_RETRY_DENSE;  // the given table does not cover the orbit
     if (sparse && (uint32_t)c->h_scalars[9] != 0) {
         // The speculation did not cover the true orbit (periodic data, where parses started at different
         // positions never fall into step).  First try to repair the chunks concerned; if that is not enough
@@ -564,6 +567,8 @@ int fb200_compress(fb200_ctx* c, int container, int mode, const uint8_t* in, siz
 }
 
 // ---- position-sharded single stream ----
+size_t fb200_shard_overlap(void) { return lz77_sparse_lookahead() - kSpHaloPlus; }
+size_t fb200_shard_align(void) { return lz77_sparse_chunk(); }
 int fb200_deflate_shard_search(fb200_ctx* c, int level, const void* d_in, size_t n, size_t from, size_t to, void* d_nx,
                                void* stream) {
     LevelArgs lv;
@@ -572,11 +577,36 @@ int fb200_deflate_shard_search(fb200_ctx* c, int level, const void* d_in, size_t
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     if (to == from) return FB200_OK;
+    const size_t T = lz77_sparse_chunk(), W = fb200_shard_overlap();
+    Lz77Buffers b = lz77_view(c);
+    if (c->parse_mode == 0 && from % T == 0 && (to % T == 0 || to == n)) {
+        // sparse parse of the range's chunks; entries of [to, to + W) belong to the overlap of the last chunk
+        FB_CUDA_CHECK(c->link.ensure(n + 64));
+        FB_CUDA_CHECK(c->chunk_fail.ensure(n / T + 2));
+        b = lz77_view(c);
+        b.nx = reinterpret_cast<uint32_t*>(d_nx);
+        c->timer.begin(st);
+        const size_t nx_end = to + W < n ? to + W : n;
+        FB_CUDA_CHECK(cudaMemsetAsync(b.nx + from, 0xFF, (nx_end - from) * sizeof(uint32_t), st));
+        FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
+        const size_t need = to + lz77_sparse_lookahead();
+        const size_t link_end = need >= n ? n : (need + 8191) / 8192 * 8192 < n ? (need + 8191) / 8192 * 8192 : n;
+        FB_CUDA_CHECK(lz77_link_range(b, (const uint8_t*)d_in, (uint32_t)(from >= kHist ? from - kHist : 0), (uint32_t)link_end,
+                                      (uint32_t)n, st, &c->timer));
+        FB_CUDA_CHECK(lz77_sparse_range(b, (const uint8_t*)d_in, (uint32_t)(from / T), (uint32_t)((to + T - 1) / T), (uint32_t)n, lv,
+                                        c->chunk_fail.p, c->d_scalars + kSparseFlagIdx, st, &c->timer));
+        c->launches += 2;
+        uint32_t bad = 0;
+        FB_CUDA_CHECK(cudaMemcpyAsync(&bad, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        c->timer.collect();
+        return bad ? FB200_RETRY_DENSE : FB200_OK;
+    }
     const size_t span = to - from + 256 + 8192 + 64;
     FB_CUDA_CHECK(c->link.ensure(n + 64));
     FB_CUDA_CHECK(c->r_full.ensure(span));
     FB_CUDA_CHECK(c->r_quarter.ensure(span));
-    Lz77Buffers b = lz77_view(c);
+    b = lz77_view(c);
     c->timer.begin(st);
     FB_CUDA_CHECK(lz77_shard_search(b, (const uint8_t*)d_in, (uint32_t)from, (uint32_t)to, (uint32_t)n, lv,
                                     reinterpret_cast<uint32_t*>(d_nx) + from, st, &c->timer));
@@ -585,7 +615,6 @@ int fb200_deflate_shard_search(fb200_ctx* c, int level, const void* d_in, size_t
     c->timer.collect();
     return FB200_OK;
 }
-
 int fb200_deflate_shard_finish(fb200_ctx* c, int container, int level, const void* d_in, size_t n, const void* d_nx,
                                void* d_out, size_t cap, size_t* out_len, void* stream) {
     LevelArgs lv;

@@ -42,21 +42,53 @@ def concat_ragged(buffer, sizes, pad):
     return b"".join(buffer[r * pad: r * pad + sizes[r]].cpu().numpy().tobytes() for r in range(len(sizes)))
 
 
+def shard_positions(n, world, align):
+    """Position ranges [lo, hi) of a stream of n bytes for every rank: equal parts, `align`-aligned."""
+    per = ((n + world - 1) // world + align - 1) // align * align if n else align
+    return per, [(min(n, r * per), min(n, (r + 1) * per)) for r in range(world)]
+
+
+def merge_overlap(own, tail):
+    """Entries of a position range evaluated by its own rank (`own`) and, for its first positions, by the
+    rank before it (`tail`, the overlap of that rank's last chunk): any evaluated entry (!= -1) is right."""
+    k = min(own.numel(), tail.numel())
+    if k:
+        own[:k] = torch.where(own[:k] == -1, tail[:k], own[:k])
+    return own
+
+
 def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0):
     """One deflate stream of n bytes (resident at torch uint8 tensor d_in on every rank) compressed by all
-    ranks together: every rank searches its own position range, the lazy-step tables are all-gathered
-    over NCCL, rank `root` runs the (cheap, sequential-in-nature) parse + block writer.  Returns the
-    compressed size on `root` (0 elsewhere).  Output is byte-identical to Context.compress_device."""
+    ranks together: every rank evaluates the lazy-parse steps of its own position range (sparse parse), the
+    tables are all-gathered over NCCL, rank `root` runs the (cheap, sequential-in-nature) parse + block
+    writer.  Returns the compressed size on `root` (0 elsewhere).  Output is byte-identical to
+    Context.compress_device."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
-    tile = 8192
-    per = ((n + world - 1) // world + tile - 1) // tile * tile if n else tile
-    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
-    nx = torch.empty(world * per, dtype=torch.int32, device=d_in.device)
+    ov = ctx.shard_overlap
+    per, ranges = shard_positions(n, world, ctx.shard_align)
+    lo, hi = ranges[rank]
+    nx = torch.empty(world * per + ov, dtype=torch.int32, device=d_in.device)
     sp = torch.cuda.current_stream().cuda_stream
-    ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level, stream=sp)
+    ok = ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level, stream=sp)
     if world > 1:
-        dist.all_gather_into_tensor(nx, nx[rank * per:(rank + 1) * per])
+        flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=d_in.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        ok = int(flag.item()) == 0
+    if not ok:  # periodic data somewhere: every rank falls back to the dense tables for its range
+        ctx.set_parse_mode(1)
+        try:
+            ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level, stream=sp)
+        finally:
+            ctx.set_parse_mode(0)
+    if world > 1:
+        tail = nx[rank * per + per: rank * per + per + ov].clone()   # this rank's entries past its range
+        tails = torch.empty(world * ov, dtype=torch.int32, device=d_in.device)
+        dist.all_gather_into_tensor(tails, tail)
+        dist.all_gather_into_tensor(nx[:world * per], nx[rank * per:(rank + 1) * per].clone())
+        if rank == root and ok:
+            for r in range(world - 1):
+                merge_overlap(nx[(r + 1) * per:(r + 1) * per + ov], tails[r * ov:(r + 1) * ov])
     if rank != root:
         return 0
     cap = d_out.numel()

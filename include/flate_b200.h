@@ -53,7 +53,8 @@ enum {
     FB200_NO_SPACE_LEFT = 17, /* caller's output buffer too small (the writer's error in the reference) */
     FB200_INVALID_ARGUMENT = 18,
     FB200_ERR_CUDA = 19,      /* CUDA runtime failure; fb200_last_cuda_error() has the text */
-    FB200_NO_DEVICE = 20      /* no CUDA device: there is NO CPU fallback */
+    FB200_NO_DEVICE = 20,     /* no CUDA device: there is NO CPU fallback */
+    FB200_RETRY_DENSE = 21    /* sharded search only: see fb200_deflate_shard_search */
 };
 
 /* container.zig:17-21 */
@@ -117,13 +118,24 @@ int fb200_decompress_members(fb200_ctx* ctx, int container, const uint8_t* in, c
                              const uint64_t* out_cap, uint64_t* out_len, uint64_t* consumed, int* status);
 
 /* ---- one stream sharded by position over several GPUs ----
- * Match candidates do not depend on the parse, so any range of positions can be searched given a
- * 32 KiB + 258 B halo of input.  Stage 1 runs on every rank for its own range [from, to) (`from` a
- * multiple of 8192) and writes the packed lazy-parse steps into d_nx[from .. to) (uint32 per position;
- * d_nx holds n entries; d_in must be readable on [max(0, from - 32768), min(n, to + 8464))).  The
- * ranks exchange their d_nx ranges (NCCL all-gather) and stage 2 runs on one rank over the complete
- * table: lazy-parse orbit, block cut, Huffman construction, bit-pack.  The result is byte-identical
- * to fb200_compress_device on the same stream.  Replaces deflate.zig:304-347 for one large stream. */
+ * The lazy-parse step from a position does not depend on the parse, so any range of positions can be
+ * evaluated given a 32 KiB halo of input before it and a little after it.  Stage 1 runs on every rank for its
+ * own range [from, to) and writes packed lazy-parse steps (uint32 per position, 0xFFFFFFFF = not evaluated)
+ * into d_nx, which is indexed by stream position and holds n entries.
+ *   - `from` and `to` multiples of fb200_shard_align() (`to` may also be n): the sparse parse runs; it writes
+ *     d_nx[from .. min(n, to + fb200_shard_overlap())).  The entries past `to` continue this range's orbits into
+ *     the next rank's range until they join orbits the next rank evaluates itself.
+ *     d_in must be readable on [max(0, from - 32768), min(n, to + fb200_shard_overlap() + 8720)).
+ *   - otherwise (`from` a multiple of 8192), or after fb200_ctx_set_parse_mode(ctx, 1): dense tables, writes
+ *     d_nx[from .. to); d_in readable on [max(0, from - 32768), min(n, to + 8464)).
+ * The ranks exchange their tables (NCCL all-gather of the [from, to) parts; for a position covered by two ranks
+ * any evaluated entry is the right one) and stage 2 runs on one rank over the joined table: lazy-parse orbit,
+ * block cut, Huffman construction, bit-pack.  The result is byte-identical to fb200_compress_device on the
+ * same stream.  Either stage returns FB200_RETRY_DENSE when the sparse parse cannot vouch for its coverage
+ * (periodic data): every rank then repeats stage 1 in parse mode 1.  Replaces deflate.zig:304-347 for one
+ * large stream. */
+size_t fb200_shard_align(void);
+size_t fb200_shard_overlap(void);
 int fb200_deflate_shard_search(fb200_ctx* ctx, int level, const void* d_in, size_t n, size_t from, size_t to, void* d_nx,
                                void* stream);
 int fb200_deflate_shard_finish(fb200_ctx* ctx, int container, int level, const void* d_in, size_t n, const void* d_nx,

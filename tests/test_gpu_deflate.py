@@ -364,22 +364,115 @@ def test_position_sharded_stream_equals_whole(ctx, o, level):
     tables joined, parse + block writer once: byte-identical to the unsharded stream."""
     import torch
     from flate_b200 import synth
-    data = synth.mixed_small(700001, seed=91) if level != 9 else synth.enwik_like(700001, seed=92)
+    for data in (synth.enwik_like(700001, seed=92), synth.mixed_small(700001, seed=91)):
+        _check_sharded_stream(ctx, o, level, data)
+
+
+def _check_sharded_stream(ctx, o, level, data):
+    import torch
     n = data.size
     d_in = torch.from_numpy(data).cuda()
     cap = ctx.lib.fb200_compress_bound(n, level) + 64
     d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
     want = o.compress(data.tobytes(), 1, level)
     import flate_b200
+    from flate_b200 import sharding
+    ov, align = ctx.shard_overlap, ctx.shard_align
     for parts in (1, 2, 3, 5):
-        per = ((n + parts - 1) // parts + 8191) // 8192 * 8192
-        nx = torch.full((parts * per,), -1, dtype=torch.int32, device="cuda")
-        for r in reversed(range(parts)):
-            # a fresh context per range, like a separate GPU: nothing (links of the history!) is inherited
-            c = flate_b200.Context(0)
-            lo, hi = min(n, r * per), min(n, (r + 1) * per)
-            c.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level)
-            c.close()
-        m = ctx.shard_finish(d_in.data_ptr(), n, nx.data_ptr(), d_out.data_ptr(), cap, level=level, container=1)
-        got = d_out[:m].cpu().numpy().tobytes()
-        assert got == want, (level, parts, first_diff(got, want))
+        for mode in (0, 1):                     # sparse parse per range / dense tables per range
+            per, ranges = sharding.shard_positions(n, parts, align if mode == 0 else 8192)
+            tables = []
+            for r in range(parts):
+                # a fresh context and a private table per range, like a separate GPU: nothing is inherited
+                c = flate_b200.Context(0)
+                c.set_parse_mode(mode)
+                nx_r = torch.full((parts * per + ov,), 0x5a5a5a5a, dtype=torch.int32, device="cuda")
+                lo, hi = ranges[r]
+                ok = c.shard_search(d_in.data_ptr(), n, lo, hi, nx_r.data_ptr(), level=level)
+                c.close()
+                assert ok or mode == 0
+                if not ok:
+                    break
+                tables.append(nx_r)
+            if len(tables) < parts:
+                continue                        # the sparse parse declined (periodic data): the dense run covers it
+            nx = torch.full((parts * per + ov,), -1, dtype=torch.int32, device="cuda")
+            for r in range(parts):              # what the all-gather does
+                nx[r * per:(r + 1) * per] = tables[r][r * per:(r + 1) * per]
+            if mode == 0:
+                for r in range(parts - 1):
+                    sharding.merge_overlap(nx[(r + 1) * per:(r + 1) * per + ov], tables[r][(r + 1) * per:(r + 1) * per + ov])
+            m = ctx.shard_finish(d_in.data_ptr(), n, nx.data_ptr(), d_out.data_ptr(), cap, level=level, container=1)
+            got = d_out[:m].cpu().numpy().tobytes()
+            assert got == want, (level, parts, mode, first_diff(got, want))
+
+
+# ---- parse strategies: the speculative sparse parse (default), its repair path and the dense tables ----
+def _sparse_cases():
+    from flate_b200 import synth
+    rng = np.random.default_rng(21)
+    text = synth.enwik_like(3 << 20, seed=31)
+    return {
+        "zeros1M": np.zeros(1 << 20, np.uint8),
+        "period7": np.tile(np.arange(7, dtype=np.uint8), 60000),
+        "lowentropy600k": rng.integers(0, 4, 600000, dtype=np.uint8),
+        "text+zeros+text": np.concatenate([text[:700000], np.zeros(200000, np.uint8), text[700000:1500000]]),
+        "text+period+text": np.concatenate([text[:1000000], np.tile(np.arange(11, dtype=np.uint8), 30000), text[1000000:2000000]]),
+        "text3M": text,
+        "text32768": text[:32768], "text33791": text[:33791], "text33792": text[:33792], "text33793": text[:33793],
+        "text65536+1025": text[:65536 + 1025],
+    }
+
+
+@pytest.mark.parametrize("level", [4, 6, 9])
+def test_sparse_parse_equals_dense_tables_and_oracle(o, level):
+    """Mode 0 (sparse parse; repaired or redone densely when its coverage check fails) and mode 1 (dense
+    match tables) both give the oracle's bytes, on inputs chosen to make the speculation fail."""
+    import flate_b200
+    sparse, dense = flate_b200.Context(0), flate_b200.Context(0)
+    dense.set_parse_mode(1)
+    try:
+        for name, d in _sparse_cases().items():
+            if level == 9 and d.size > (2 << 20):
+                d = d[:2 << 20]
+            want = o.compress(d.tobytes(), o.RAW, level)
+            a = sparse.compress(d, flate_b200.RAW, level)
+            b = dense.compress(d, flate_b200.RAW, level)
+            assert a == want, (name, "sparse", first_diff(a, want))
+            assert b == want, (name, "dense", first_diff(b, want))
+        assert dense.sparse_fallbacks == 0 and dense.sparse_repairs == 0
+        # zeros and the short period never let two parses fall into step: redone densely;
+        # a periodic stretch inside text is repaired chunk-wise
+        assert sparse.sparse_fallbacks >= 2
+        assert sparse.sparse_repairs >= 2
+    finally:
+        sparse.close()
+        dense.close()
+
+
+def test_sparse_parse_counters_stay_zero_on_text(o):
+    import flate_b200
+    from flate_b200 import synth
+    c = flate_b200.Context(0)
+    try:
+        d = synth.enwik_like(8 << 20, seed=77)
+        got = c.compress(d, flate_b200.GZIP, 6)
+        assert got == o.compress(d.tobytes(), o.GZIP, 6)
+        assert c.sparse_fallbacks == 0 and c.sparse_repairs == 0
+    finally:
+        c.close()
+
+
+def test_dense_mode_tokens_equal_oracle(o):
+    import flate_b200
+    from flate_b200 import synth
+    c = flate_b200.Context(0)
+    c.set_parse_mode(1)
+    try:
+        for n in (5, 4097, 70000, 300001):
+            d = synth.enwik_like(n, seed=n).tobytes()
+            for level in (4, 6, 9):
+                got, want = c.debug_tokens(d, level), o.tokenize(d, level)
+                assert got.size == want.size and (got == want).all(), (n, level)
+    finally:
+        c.close()
