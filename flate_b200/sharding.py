@@ -57,7 +57,7 @@ def merge_overlap(own, tail):
     return own
 
 
-def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0):
+def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0, keep=None):
     """One deflate stream of n bytes (resident at torch uint8 tensor d_in on every rank) compressed by all
     ranks together: every rank evaluates the lazy-parse steps of its own position range (sparse parse), the
     tables are all-gathered over NCCL, rank `root` runs the (cheap, sequential-in-nature) parse + block
@@ -69,7 +69,11 @@ def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0):
     per, ranges = shard_positions(n, world, ctx.shard_align)
     lo, hi = ranges[rank]
     nx = torch.empty(world * per + ov, dtype=torch.int32, device=d_in.device)
-    sp = torch.cuda.current_stream().cuda_stream
+    cur = torch.cuda.current_stream()
+    sp = cur.cuda_stream
+    # the legacy default stream has handle 0, which the C ABI reads as "the context's own stream": make sure
+    # torch's work on the inputs is complete before the library touches them (and again before stage 2)
+    cur.synchronize()
     ok = ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level, stream=sp)
     if world > 1:
         flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=d_in.device)
@@ -78,6 +82,7 @@ def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0):
     if not ok:  # periodic data somewhere: every rank falls back to the dense tables for its range
         ctx.set_parse_mode(1)
         try:
+            cur.synchronize()
             ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level, stream=sp)
         finally:
             ctx.set_parse_mode(0)
@@ -89,8 +94,11 @@ def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0):
         if rank == root and ok:
             for r in range(world - 1):
                 merge_overlap(nx[(r + 1) * per:(r + 1) * per + ov], tails[r * ov:(r + 1) * ov])
+    if keep is not None:
+        keep["nx"], keep["per"] = nx, per   # development aid
     if rank != root:
         return 0
+    cur.synchronize()
     cap = d_out.numel()
     return ctx.shard_finish(d_in.data_ptr(), n, nx.data_ptr(), d_out.data_ptr(), cap, level=level, container=container,
                             stream=sp)
