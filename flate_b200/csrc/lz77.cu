@@ -965,14 +965,21 @@ sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, const 
     bool exhausted = false;
     while (true) {
         // ---- phase A: chain steps (deflate.zig:248 "Hot path loop!") ----
+        // The link of the next candidate is fetched together with the reject byte of this one, before it is
+        // known whether the walk goes on: one shared-memory latency per step on the critical path, not two.
+        uint32_t nl = left ? lds_shared_u16(sl_addr + 2 * qi) : 0;
 #pragma unroll
         for (int u = 0; u < kSteps; u++) {
             if (left) {
-                qi -= lds_shared_u16(sl_addr + 2 * qi);
-                if ((int32_t)qi < (int32_t)lim) {  // end of chain, too far, or at/below the slide base
+                qi -= nl;
+                const bool in_range = (int32_t)qi >= (int32_t)lim;
+                const uint32_t qs = in_range ? qi : pi;  // a slot that is always safe to read
+                const uint32_t b = lds_shared_u8(ro_addr + qs);
+                nl = lds_shared_u16(sl_addr + 2 * qs);
+                if (!in_range) {  // end of chain (kNoLink), too far, or at/below the slide base
                     st = kSearchDone;
                     left = 0;
-                } else if (lds_shared_u8(ro_addr + qi) == cb) {
+                } else if (b == cb) {  // may beat the best so far: needs the full compare
                     st = kPending;
                     saved = left;
                     left = 0;
@@ -982,14 +989,14 @@ sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, const 
             }
         }
         if (st == kStepping && left == 0) st = kSearchDone;
-        // ---- phase B: full compares ----
+        // ---- phase B: full compares (SlidingWindow.match with the running best as min_len) ----
         const uint32_t pend = __ballot_sync(0xffffffffu, st == kPending);
         if (pend) {
             const uint32_t stepping = __ballot_sync(0xffffffffu, st == kStepping);
             if (__popc(pend) >= tune.pend_at || stepping == 0) {
                 if (st == kPending) {
                     st = kStepping;
-                    left = saved - 1;
+                    left = saved - 1;  // this candidate is paid for either way
                     if (lds_u32_unaligned(sb, qi) == first4) {
                         uint32_t i = 4;
                         while (i < max_len) {

@@ -1,12 +1,7 @@
-timeout 300 python tools/sparse_check.py > gpurun_out/sparse_repair.log 2>&1; echo "exit $?" >> gpurun_out/sparse_repair.log
-cat gpurun_out/sparse_repair.log
 (
-for t in 0 2; do
-FB200_SPARSE=$t timeout 120 python tools/phase_times.py 256 6
+for v in 0 3 4; do
+FB200_SPARSE=$v timeout 120 python tools/phase_times.py 256 6
 done
-timeout 120 python tools/phase_times.py 256 9
-timeout 120 python tools/phase_times.py 256 4
-FB200_PARSE_MODE=1 timeout 120 python tools/phase_times.py 256 9
-FB200_PARSE_MODE=1 timeout 120 python tools/phase_times.py 256 4
-) 2>&1 > gpurun_out/sparse_times.log
+FB200_SPARSE=4 timeout 120 python tools/phase_times.py 256 9
+) 2>&1 | sed -e 's/hash_link=.*sparse_parse/sparse_parse/' > gpurun_out/sparse_times.log
 cat gpurun_out/sparse_times.log
