@@ -42,6 +42,13 @@ def concat_ragged(buffer, sizes, pad):
     return b"".join(buffer[r * pad: r * pad + sizes[r]].cpu().numpy().tobytes() for r in range(len(sizes)))
 
 
+class _NoStream:  # CPU tensors (host-logic tests with a stub context)
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+
 def shard_positions(n, world, align):
     """Position ranges [lo, hi) of a stream of n bytes for every rank: equal parts, `align`-aligned."""
     per = ((n + world - 1) // world + align - 1) // align * align if n else align
@@ -69,7 +76,7 @@ def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0, k
     per, ranges = shard_positions(n, world, ctx.shard_align)
     lo, hi = ranges[rank]
     nx = torch.empty(world * per + ov, dtype=torch.int32, device=d_in.device)
-    cur = torch.cuda.current_stream()
+    cur = torch.cuda.current_stream() if d_in.is_cuda else _NoStream()
     sp = cur.cuda_stream
     # the legacy default stream has handle 0, which the C ABI reads as "the context's own stream": make sure
     # torch's work on the inputs is complete before the library touches them (and again before stage 2)

@@ -72,3 +72,101 @@ def test_ragged_all_gather_world2():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert res[0][2] == res[1][2] and len(res[0][2]) == 2
+
+
+# ---- one stream sharded by position: the driver logic with a stub context (no GPU) ----
+class _StubCtx:
+    """Stands in for flate_b200.Context: 'evaluates' position p as the value p + 1 for every third position
+    of its range, and continues 5 entries into the next rank's range like the overlap of the sparse parse."""
+    shard_align = 64
+    shard_overlap = 16
+
+    def __init__(self, fail_on=None):
+        self.mode = 0
+        self.fail_on = fail_on
+        self.calls = []
+
+    def set_parse_mode(self, mode):
+        self.mode = mode
+
+    def shard_search(self, d_in, n, lo, hi, d_nx, level=6, stream=None):
+        self.calls.append((self.mode, lo, hi))
+        nx = self.table
+        if self.mode == 0:
+            if self.fail_on is not None and lo <= self.fail_on < hi:
+                return False
+            nx[lo:min(n, hi + self.shard_overlap)] = -1
+            for p in range(lo, hi, 3):
+                nx[p] = p + 1
+            for p in range(hi, min(n, hi + 5)):
+                nx[p] = p + 1
+        else:
+            for p in range(lo, hi):
+                nx[p] = p + 1
+        return True
+
+    def shard_finish(self, d_in, n, d_nx, d_out, cap, level=6, container=0, stream=None):
+        self.final = self.table[:n].clone()
+        return n
+
+
+def _stream_worker(rank, world, port, q, fail_on):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 300
+        ctx = _StubCtx(fail_on)
+        real_empty = torch.empty
+
+        def tracking_empty(*a, **k):   # the driver allocates the table itself: keep a handle on it
+            t = real_empty(*a, **k)
+            if k.get("dtype") == torch.int32 and t.numel() > 2 * _StubCtx.shard_overlap:
+                ctx.table = t
+            return t
+        torch.empty = tracking_empty
+        try:
+            m = sharding.compress_stream_sharded(ctx, torch.zeros(n, dtype=torch.uint8), n, torch.zeros(16, dtype=torch.uint8))
+        finally:
+            torch.empty = real_empty
+        final = ctx.final.tolist() if rank == 0 else None
+        q.put((rank, m, final, ctx.calls))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_on", [None, 200])
+def test_stream_sharding_driver_world2(fail_on):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stream_worker, args=(r, 2, port, q, fail_on)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    (r0, m0, final, calls0), (r1, m1, _, calls1) = res
+    assert (m0, m1) == (300, 0)
+    per, ranges = sharding.shard_positions(300, 2, 64)
+    assert ranges == [(0, 192), (192, 300)]
+    if fail_on is None:
+        assert calls0 == [(0, 0, 192)] and calls1 == [(0, 192, 300)]
+        for p in range(300):
+            own = (p - (0 if p < 192 else 192)) % 3 == 0
+            tail = 192 <= p < 197                       # rank 0's overlap entries, merged into rank 1's range
+            assert final[p] == (p + 1 if own or tail else -1), p
+    else:
+        # one rank declined: both ranks repeat with the dense tables and the overlap merge is skipped
+        assert calls0 == [(0, 0, 192), (1, 0, 192)] and calls1 == [(0, 192, 300), (1, 192, 300)]
+        assert final == [p + 1 for p in range(300)]
+
+
+def test_shard_positions_and_merge():
+    per, ranges = sharding.shard_positions(1000, 3, 128)
+    assert per == 384 and ranges == [(0, 384), (384, 768), (768, 1000)]
+    per, ranges = sharding.shard_positions(100, 4, 64)
+    assert ranges == [(0, 64), (64, 100), (100, 100), (100, 100)]
+    own = torch.tensor([-1, 5, -1, 7], dtype=torch.int32)
+    tail = torch.tensor([1, 5, -1], dtype=torch.int32)
+    assert sharding.merge_overlap(own, tail).tolist() == [1, 5, -1, 7]
