@@ -62,6 +62,36 @@ def test_host_path_slab_overlap_equals_device_path(ctx, text256):
     assert ctx.compress(data, 0, 6) == _device_compress(ctx, data, 6)
 
 
+@pytest.mark.parametrize("n", [32 * MIB + 8192 + 1, 40 * MIB + 32768, 41 * MIB - 1, 72 * MIB + 1551])
+def test_host_path_sizes_around_slab_and_chunk_boundaries(ctx, text256, n):
+    """The sparse parse follows the copy front by its look-ahead and in 32 KiB chunks: no size may matter."""
+    data = text256[:n]
+    assert ctx.compress(data, 0, 6) == _device_compress(ctx, data, 6)
+
+
+def test_host_path_repairs_periodic_stretch_like_device_path(text256):
+    """Coverage check fails inside the periodic stretches: the repair (and the second parse) must also work when
+    the input arrived slab-wise and the output leaves part by part."""
+    import flate_b200
+    data = text256[:48 * MIB].copy()
+    data[5 * MIB:5 * MIB + 300000] = 0
+    data[37 * MIB:37 * MIB + 70000] = np.tile(np.arange(13, dtype=np.uint8), 5385)[:70000]
+    host, dev, dense = flate_b200.Context(0), flate_b200.Context(0), flate_b200.Context(0)
+    dense.set_parse_mode(1)
+    try:
+        a = host.compress(data, 0, 6)
+        b = _device_compress(dev, data, 6)
+        c = dense.compress(data, 0, 6)
+        assert a == c and b == c
+        assert host.sparse_repairs >= 1 and host.sparse_fallbacks == 0
+        assert dev.sparse_repairs >= 1 and dev.sparse_fallbacks == 0
+        assert zlib.decompress(a, -15) == data.tobytes()
+    finally:
+        host.close()
+        dev.close()
+        dense.close()
+
+
 def test_c5_huffman_only_1GiB_roundtrip(ctx):
     """configs[4] shape (random + zeros mix, stored and dynamic blocks alternating), 1 GiB per GPU."""
     from flate_b200 import synth
