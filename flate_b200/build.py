@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         o = os.path.join(LIB_DIR, s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        extra = os.environ.get("FB200_NVCC_EXTRA", "").split()   # development experiments (-D...)
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for cmd, p in procs:

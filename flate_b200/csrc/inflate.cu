@@ -36,6 +36,12 @@ struct WarpTables {
     uint32_t crc_tab[256];
 };
 
+__device__ __forceinline__ uint32_t bfe32(uint32_t v, uint32_t pos, uint32_t len) {  // bit-field extract, len may be 0
+    uint32_t r;
+    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(len));
+    return r;
+}
+
 struct BitCursor {  // lane 0 only
     const uint8_t* next;
     const uint8_t* end;
@@ -314,9 +320,12 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
     W.A = (uint32_t)((uintptr_t)out & 15);
     W.flushed = 0;
 
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t lit_fast_addr = (uint32_t)__cvta_generic_to_shared(T.lit_fast);
-    const uint32_t dist_fast_addr = (uint32_t)__cvta_generic_to_shared(T.dist_fast);
+    // shared-window addresses, made opaque so that they live in registers instead of being re-derived (S2R) per token
+    uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    asm volatile("mov.u32 %0, %0;" : "+r"(ring_addr));
+    const uint32_t lit_fast_addr = ring_addr + kRing + (uint32_t)offsetof(WarpTables, lit_fast);
+    const uint32_t dist_fast_addr = ring_addr + kRing + (uint32_t)offsetof(WarpTables, dist_fast);
+    const uint32_t queue_addr = ring_addr + kRing + (uint32_t)offsetof(WarpTables, queue);
     BitCursor bc;
     bc.next = d_in + md.in_off;
     bc.end = bc.next + md.in_len;
@@ -494,80 +503,93 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                 uint32_t nq = 0;
                 const uint64_t pos0 = pos;  // uniform here; lane 0 runs ahead from it
                 if (lane == 0) {
-                    // local, 32-bit state: every instruction here is on the member's critical path
+                    // Local state, 32-bit arithmetic only: every instruction here is on the member's critical
+                    // path (one warp issues a dependent instruction every ~6 cycles).  The cursor is a bit
+                    // offset `bo` (< 32) into three consecutive little-endian words w0, w1, w2 of the input;
+                    // w2 is loaded 32 bits ahead of its use, so the load latency stays off the chain.
                     const uint64_t stop = min(min(cap, W.flushed + kFlushAt), pos + kBatchSpan);
                     const uint32_t stop32 = (uint32_t)(stop - pos0);          // < 2^13
                     const uint32_t room32 = (uint32_t)min(cap - pos0, (uint64_t)0x7fffffffu);
                     const uint32_t slot0 = (uint32_t)pos0 + W.A;
                     const uint64_t reach = md.hist + pos0;                     // bytes a match may reach back from pos0
-                    uint64_t buf = bc.buf;
-                    uint32_t cnt = bc.cnt;
-                    const uint8_t* nxp = bc.next;
-                    const uint8_t* const endp = bc.end;
+                    const unsigned long long q0 = (unsigned long long)(uintptr_t)bc.next * 8ull - bc.cnt;  // cursor as a bit address
+                    const uintptr_t wa = (uintptr_t)((q0 >> 3) & ~3ull);
+                    const uintptr_t lo_addr = (uintptr_t)(d_in + md.in_off), end_addr = (uintptr_t)bc.end;
                     uint32_t p32 = 0;
-                    while (p32 < stop32 && nq < kQueue) {
-                        if (cnt <= 32) {
-                            if ((((uintptr_t)nxp) & 3) == 0 && nxp + 4 <= endp) {
-                                buf |= (uint64_t)__ldg(reinterpret_cast<const uint32_t*>(nxp)) << cnt;
-                                nxp += 4;
-                                cnt += 32;
-                            } else {
-                                while (cnt <= 56 && nxp < endp) {
-                                    buf |= (uint64_t)(*nxp++) << cnt;
-                                    cnt += 8;
+                    if (wa >= lo_addr && wa + 12 <= end_addr) {
+                        const uint32_t* const wbase = reinterpret_cast<const uint32_t*>(wa);
+                        const uint32_t wlim = (uint32_t)(((end_addr & ~(uintptr_t)3) - wa) >> 2);  // whole words from wbase
+                        uint32_t w0 = __ldg(wbase), w1 = __ldg(wbase + 1), w2 = __ldg(wbase + 2);
+                        uint32_t wi = 3;                                       // next word to load
+                        uint32_t bo = (uint32_t)(q0 - (unsigned long long)wa * 8ull);
+                        const uint32_t reach32 = (uint32_t)min(reach, (uint64_t)0xffff0000u);
+                        // a token takes at most 10 + 5 + 8 + 13 = 36 bits: two word advances, both must be loadable
+                        while (p32 < stop32 && nq < kQueue && wi + 2 <= wlim) {
+                            const uint32_t win = __funnelshift_r(w0, w1, bo);
+                            uint32_t e;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_fast_addr + ((win & ((1u << kLitFast) - 1)) << 2)));
+                            const uint32_t nb = e & 15;
+                            if (nb == 0) break;
+                            const uint32_t sym = bfe32(e, 4, 9);
+                            if (sym < 256) {
+                                asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_addr + ((slot0 + p32) & (kRing - 1))), "r"(sym));
+                                bo += nb;
+                                p32++;
+                                if (bo >= 32) {
+                                    bo -= 32;
+                                    w0 = w1;
+                                    w1 = w2;
+                                    w2 = __ldg(wbase + wi);
+                                    wi++;
                                 }
+                                continue;
                             }
-                        }
-                        uint32_t e;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_fast_addr + (((uint32_t)buf & ((1u << kLitFast) - 1)) << 2)));
-                        const uint32_t nb = e & 15, sym = (e >> 4) & 511u;
-                        if (nb == 0 || nb > cnt) break;
-                        if (sym < 256) {
-                            buf >>= nb;
-                            cnt -= nb;
-                            asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_addr + ((slot0 + p32) & (kRing - 1))), "r"(sym));
-                            p32++;
-                            continue;
-                        }
-                        if (sym == 256 || sym > 285) break;
-                        // length + distance on copies, so that an irregular case leaves the cursor untouched
-                        const uint32_t leb = (e >> 13) & 15;
-                        if (nb + leb > cnt) break;
-                        uint64_t tbuf = buf >> nb;
-                        const uint32_t length = (e >> 17) + ((uint32_t)tbuf & ((1u << leb) - 1));
-                        tbuf >>= leb;
-                        uint32_t tcnt = cnt - nb - leb;
-                        const uint8_t* tnx = nxp;
-                        if (tcnt <= 32) {
-                            if ((((uintptr_t)tnx) & 3) == 0 && tnx + 4 <= endp) {
-                                tbuf |= (uint64_t)__ldg(reinterpret_cast<const uint32_t*>(tnx)) << tcnt;
-                                tnx += 4;
-                                tcnt += 32;
-                            } else {
-                                while (tcnt <= 56 && tnx < endp) {
-                                    tbuf |= (uint64_t)(*tnx++) << tcnt;
-                                    tcnt += 8;
-                                }
+                            if (sym - 257u > 28u) break;  // end of block, or 286/287
+                            // length + distance; an irregular case restores the cursor from (bo0, wi0)
+                            const uint32_t bo0 = bo, wi0 = wi;
+                            const uint32_t leb = bfe32(e, 13, 4);
+                            const uint32_t length = (e >> 17) + bfe32(win, nb, leb);
+                            bo += nb + leb;
+                            if (bo >= 32) {
+                                bo -= 32;
+                                w0 = w1;
+                                w1 = w2;
+                                w2 = __ldg(wbase + wi);
+                                wi++;
                             }
+                            const uint32_t dwin = __funnelshift_r(w0, w1, bo);
+                            uint32_t de;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(de) : "r"(dist_fast_addr + ((dwin & ((1u << kDistFast) - 1)) << 2)));
+                            const uint32_t dnb = de & 15, deb = bfe32(de, 13, 4);
+                            const uint32_t distance = (de >> 17) + bfe32(dwin, dnb, deb);  // dnb + deb <= 21 bits
+                            if (dnb == 0 || bfe32(de, 4, 9) > 29 || reach32 + p32 < distance || p32 + length > room32) {
+                                bo = bo0;  // rare: put the cursor back to the start of the token
+                                wi = wi0;
+                                w0 = __ldg(wbase + wi - 3);
+                                w1 = __ldg(wbase + wi - 2);
+                                w2 = __ldg(wbase + wi - 1);
+                                break;
+                            }
+                            bo += dnb + deb;
+                            if (bo >= 32) {
+                                bo -= 32;
+                                w0 = w1;
+                                w1 = w2;
+                                w2 = __ldg(wbase + wi);
+                                wi++;
+                            }
+                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(queue_addr + 8 * nq), "r"(p32), "r"((length << 16) | (distance - 1)));
+                            nq++;
+                            p32 += length;
                         }
-                        uint32_t de;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(de) : "r"(dist_fast_addr + (((uint32_t)tbuf & ((1u << kDistFast) - 1)) << 2)));
-                        const uint32_t dnb = de & 15, deb = (de >> 13) & 15;
-                        if (dnb == 0 || ((de >> 4) & 511u) > 29 || dnb + deb > tcnt) break;
-                        tbuf >>= dnb;
-                        const uint32_t distance = (de >> 17) + ((uint32_t)tbuf & ((1u << deb) - 1));
-                        if (reach + p32 < distance || p32 + length > room32) break;
-                        buf = tbuf >> deb;
-                        cnt = tcnt - dnb - deb;
-                        nxp = tnx;
-                        T.queue[2 * nq] = p32;
-                        T.queue[2 * nq + 1] = (length << 16) | (distance - 1);
-                        nq++;
-                        p32 += length;
+                        if (p32) {
+                            // back to the cursor of the exact path, straight from the registers: w0 and w1 are whole
+                            // bytes of the stream, so cnt mod 8 stays the stream's bit phase (align_to_byte relies on it)
+                            bc.buf = (((uint64_t)w1 << 32) | w0) >> bo;
+                            bc.cnt = 64 - bo;
+                            bc.next = reinterpret_cast<const uint8_t*>(wbase + wi - 1);
+                        }
                     }
-                    bc.buf = buf;
-                    bc.cnt = cnt;
-                    bc.next = nxp;
                     pos = pos0 + p32;
                 }
                 __syncwarp();
@@ -575,6 +597,9 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                 // Resolve the queue: four matches at a time, eight lanes each.  A match may only run together
                 // with earlier ones of its group if its source ends before the group's first destination
                 // (conservative); otherwise it starts the next group.
+#ifdef FB200_EXP_NO_RESOLVE
+                nq = 0;
+#endif
                 for (uint32_t k = 0; k < nq;) {
                     const uint32_t g = lane >> 3, sub = lane & 7;
                     const bool valid = k + g < nq;
