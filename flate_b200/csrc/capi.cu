@@ -341,7 +341,18 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         if ((rc = ensure_blocks(c, max_blocks))) return rc;
         Lz77Buffers b = lz77_view(c);
         c->timer.begin(st);
-        constexpr size_t kSlab = 32u << 20, kFirst = 8u << 20, kLag = 8192;  // the search of a slab lags one hash tile behind its copy
+        constexpr size_t kLag = 8192;  // the search of a slab lags one hash tile behind its copy
+        // slab-wise input copy: a quarter of the input per slab (4..64 MiB), a small first slab to start early
+        size_t kSlab = ((n - begin) / 4 + (1u << 20) - 1) >> 20 << 20;
+        kSlab = kSlab < (4u << 20) ? (4u << 20) : kSlab > (64u << 20) ? (64u << 20) : kSlab;
+        size_t kFirst = kSlab / 4;
+        if (const char* e = getenv("FB200_SLAB")) {  // development knob: FB200_SLAB="first_MiB,slab_MiB"
+            int a = 0, b2 = 0;
+            if (sscanf(e, "%d,%d", &a, &b2) == 2 && a > 0 && b2 > 0) {
+                kFirst = (size_t)a << 20;
+                kSlab = (size_t)b2 << 20;
+            }
+        }
         if (redo == 1) {
             sparse = true;
             FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
