@@ -597,38 +597,41 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
                 // Resolve the queue: four matches at a time, eight lanes each.  A match may only run together
                 // with earlier ones of its group if its source ends before the group's first destination
                 // (conservative); otherwise it starts the next group.
-#ifdef FB200_EXP_NO_RESOLVE
-                nq = 0;
-#endif
+                // (32-bit positions relative to the batch start; the ring is addressed through its shared window)
+                const uint32_t slot0r = (uint32_t)pos0 + W.A;
+                const uint32_t back32 = (uint32_t)min(pos0, (uint64_t)0xffff0000u);  // output bytes before the batch
                 for (uint32_t k = 0; k < nq;) {
                     const uint32_t g = lane >> 3, sub = lane & 7;
                     const bool valid = k + g < nq;
-                    uint32_t qlo = 0, q_len = 0, q_dist = 1;
-                    if (valid) {
-                        qlo = T.queue[2 * (k + g)];
-                        const uint32_t w1 = T.queue[2 * (k + g) + 1];
-                        q_len = w1 >> 16;
-                        q_dist = (w1 & 0xffffu) + 1;
-                    }
+                    uint32_t qlo = 0, w1 = 0;
+                    if (valid) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(qlo), "=r"(w1) : "r"(queue_addr + 8 * (k + g)));
+                    const uint32_t q_len = w1 >> 16, q_dist = (w1 & 0xffffu) + 1;
                     const uint32_t first_lo = __shfl_sync(0xffffffffu, qlo, 0);
-                    // source bytes actually read: [qpos - dist, qpos - dist + min(len, dist))
-                    const int64_t src_end = (int64_t)qlo - q_dist + min(q_len, q_dist);
-                    const bool conflict = valid && g > 0 && src_end > (int64_t)first_lo;
+                    // source bytes actually read: [qlo - dist, qlo - dist + min(len, dist))
+                    const int32_t src_end = (int32_t)qlo - (int32_t)q_dist + (int32_t)min(q_len, q_dist);
+                    const bool conflict = valid && g > 0 && src_end > (int32_t)first_lo;
                     const uint32_t cmask = __ballot_sync(0xffffffffu, conflict);
                     const uint32_t take = cmask ? (uint32_t)(__ffs(cmask) - 1) >> 3 : min(4u, nq - k);
                     if (valid && g < take) {
-                        const uint64_t qpos = pos0 + qlo;  // queue positions are relative to the batch start
-                        if (q_dist <= kRing - kBatchSpan - 512 && q_dist <= qpos) {
-                            const uint32_t from = (uint32_t)qpos - q_dist + W.A, to = (uint32_t)qpos + W.A;
+                        if (q_dist <= kRing - kBatchSpan - 512 && q_dist <= back32 + qlo) {
+                            const uint32_t to = slot0r + qlo, from = to - q_dist;
                             if (q_dist >= q_len) {
-                                for (uint32_t i = sub; i < q_len; i += 8) W.ring[(to + i) & (kRing - 1)] = W.ring[(from + i) & (kRing - 1)];
+                                for (uint32_t i = sub; i < q_len; i += 8) {
+                                    uint32_t b;
+                                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(ring_addr + ((from + i) & (kRing - 1))));
+                                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_addr + ((to + i) & (kRing - 1))), "r"(b));
+                                }
                             } else {
-                                for (uint32_t i = sub; i < q_len; i += 8)
-                                    W.ring[(to + i) & (kRing - 1)] = W.ring[(from + i % q_dist) & (kRing - 1)];
+                                for (uint32_t i = sub; i < q_len; i += 8) {
+                                    uint32_t b;
+                                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(ring_addr + ((from + i % q_dist) & (kRing - 1))));
+                                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_addr + ((to + i) & (kRing - 1))), "r"(b));
+                                }
                             }
                         } else {
                             // far match, or one that reaches into an earlier member's output: the source left the ring
                             // but was drained to HBM long ago (pending <= kFlushAt + kBatchSpan + 258)
+                            const uint64_t qpos = pos0 + qlo;
                             for (uint32_t i = sub; i < q_len; i += 8) {
                                 const int64_t sp = (int64_t)qpos - q_dist + (q_dist >= q_len ? i : i % q_dist);
                                 uint8_t b;
