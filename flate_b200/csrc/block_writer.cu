@@ -144,7 +144,8 @@ __device__ __forceinline__ uint32_t bit_reverse(uint32_t v, uint32_t nbits) { re
 // the whole warp executes it redundantly on broadcast shared-memory reads; the one O(level) step --
 // copying a row of leaf counts when a pair is taken (:199) -- is spread over the lanes.  Element
 // (l, j < l) of leaf_counts is only ever written and read by lane j, the diagonal and the level
-// records are written identically by every lane, so no synchronisation is needed inside the loop.
+// records are written identically by every lane; one __syncwarp per step separates the reads of a step
+// from the (identical) writes of the lanes that are ahead.
 __device__ uint32_t bit_counts_warp(HuffScratch& s, uint32_t n, uint32_t max_bits) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t kMaxI32 = 0x7fffffffu;
@@ -161,6 +162,11 @@ __device__ uint32_t bit_counts_warp(HuffScratch& s, uint32_t n, uint32_t max_bit
     uint32_t level = max_bits;
     while (true) {  // :168-224
         LevelInfo l = s.levels[level];
+        const uint32_t diag = s.leaf_counts[level][level];
+        // Every lane has read this step's state before any lane overwrites it.  All lanes then write the same
+        // values, and no lane can reach the writes of the next step before all have passed this point, so a
+        // lane never reads a value "from the future" even if the warp's lanes drift apart.
+        __syncwarp();
         if (l.next_pair_freq == kMaxI32 && l.next_char_freq == kMaxI32) {  // :170 (leaf sentinel is 65535: not taken)
             s.levels[level].needed = 0;
             s.levels[level + 1].next_pair_freq = kMaxI32;
@@ -169,7 +175,7 @@ __device__ uint32_t bit_counts_warp(HuffScratch& s, uint32_t n, uint32_t max_bit
         }
         const uint32_t prev_freq = l.last_freq;
         if (l.next_char_freq < l.next_pair_freq) {  // :182 next item is a leaf
-            const uint32_t next = s.leaf_counts[level][level] + 1;
+            const uint32_t next = diag + 1;
             l.last_freq = l.next_char_freq;
             s.leaf_counts[level][level] = next;
             l.next_char_freq = (next >= n) ? 65535u : (uint32_t)s.s_freq[next];  // :188-192, maxNode :282
