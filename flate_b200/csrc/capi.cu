@@ -95,7 +95,7 @@ struct fb200_ctx {
     uint64_t sparse_fallbacks = 0;   // streams redone with the dense tables
     uint64_t sparse_repairs = 0;     // streams whose sparse parse was completed by evaluating some chunks densely
     // LZ77 workspace
-    DevBuf<uint16_t> link, exits, gexits, gentry, entry;
+    DevBuf<uint16_t> link, exits, gexits, gentry, entry, jumps;
     DevBuf<uint32_t> r_full, r_quarter, nx, bitmap, chunk_tokens, tok_offset, tokens, cut_rp;
     DevBuf<uint32_t> chunk_fail, chunk_list;  // sparse parse: coverage check per chunk, chunks to repair
     // block writer workspace
@@ -215,6 +215,7 @@ static int ensure_lz77(fb200_ctx* c, size_t n) {
     FB_CUDA_CHECK(c->gexits.ensure(ngroups * kEntries));
     FB_CUDA_CHECK(c->gentry.ensure(ngroups));
     FB_CUDA_CHECK(c->entry.ensure(nchunks));
+    FB_CUDA_CHECK(c->jumps.ensure(nchunks * kChunk));
     FB_CUDA_CHECK(c->bitmap.ensure(nchunks * (kChunk / 32)));
     FB_CUDA_CHECK(c->chunk_tokens.ensure(nchunks));
     FB_CUDA_CHECK(c->tok_offset.ensure(nchunks));
@@ -234,7 +235,7 @@ static int ensure_blocks(fb200_ctx* c, size_t max_blocks) {
 static Lz77Buffers lz77_view(fb200_ctx* c) {
     Lz77Buffers b;
     b.link = c->link.p; b.r_full = c->r_full.p; b.r_quarter = c->r_quarter.p; b.nx = c->nx.p;
-    b.exits = c->exits.p; b.gexits = c->gexits.p; b.gentry = c->gentry.p; b.entry = c->entry.p;
+    b.exits = c->exits.p; b.gexits = c->gexits.p; b.gentry = c->gentry.p; b.entry = c->entry.p; b.jumps = c->jumps.p;
     b.bitmap = c->bitmap.p; b.chunk_tokens = c->chunk_tokens.p; b.tok_offset = c->tok_offset.p;
     b.total_tokens = c->d_scalars; b.tokens = c->tokens.p; b.cut_rp = c->cut_rp.p;
     return b;

@@ -1174,29 +1174,40 @@ __global__ void lazy_step_range_kernel(const uint32_t* __restrict__ r_full, cons
     nx[i] = out;
 }
 
-// K3b alone: exit tables from nx.
+// K3b alone: exit tables from nx.  Pointer jumping is restricted to 256-position sub-chunks (jump[i] =
+// first arrival at or past the end of i's sub-chunk: 8-9 rounds instead of 12 for the whole chunk); the 516
+// possible entries then hop from sub-chunk to sub-chunk (at most 16 hops).  The jump table is kept in HBM
+// (2 B per position): orbit_mark needs exactly this table and would otherwise rebuild it.
+constexpr uint32_t kSub = 256;                    // sub-chunk walked by one lane of orbit_mark
+constexpr uint32_t kSubs = kChunk / kSub;         // 16 walkers per chunk
 __global__ void __launch_bounds__(1024)
-chunk_exit_kernel(const uint32_t* __restrict__ nx, uint32_t n, uint16_t* __restrict__ exits) {
-    __shared__ uint16_t nxt[kChunk];
+chunk_exit_kernel(const uint32_t* __restrict__ nx, uint32_t n, uint16_t* __restrict__ exits, uint16_t* __restrict__ jumps) {
+    __shared__ __align__(16) uint16_t jump[kChunk];
     const uint32_t c = blockIdx.x;
     const uint32_t cs = c * kChunk;
     for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
         const uint32_t p = cs + i;
-        nxt[i] = (uint16_t)(p < n ? i + nx_step(nx_clean(nx[p])) : kChunk);
+        jump[i] = (uint16_t)(p < n ? i + nx_step(nx_clean(nx[p])) : kChunk);  // <= 4095 + 515
     }
     __syncthreads();
     while (true) {
         bool pending = false;
         for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
-            const uint32_t t = nxt[i];
-            if (t < kChunk) {
-                nxt[i] = nxt[t];
+            const uint32_t t = jump[i];
+            if (t < (i | (kSub - 1)) + 1) {  // still inside i's sub-chunk
+                jump[i] = jump[t];           // racing reads see some power of f: still correct
                 pending = true;
             }
         }
         if (!__syncthreads_or(pending)) break;
     }
-    for (uint32_t i = threadIdx.x; i < kEntries; i += blockDim.x) exits[(size_t)c * kEntries + i] = nxt[i] - kChunk;
+    for (uint32_t e = threadIdx.x; e < kEntries; e += blockDim.x) {
+        uint32_t cur = e;
+        while (cur < kChunk) cur = jump[cur];
+        exits[(size_t)c * kEntries + e] = (uint16_t)(cur - kChunk);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(jumps + (size_t)c * kChunk);
+    for (uint32_t i = threadIdx.x; i < kChunk / 8; i += blockDim.x) dst[i] = reinterpret_cast<const uint4*>(jump)[i];
 }
 
 // K3c: resolve the true entry offset of every chunk.  Two-level: groups of kGroup chunks.
@@ -1235,17 +1246,16 @@ __global__ void chunk_entry_kernel(const uint16_t* __restrict__ exits, const uin
 // the tokens they emit (k literals + 1 match, or 1 literal).
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kMarkThreads = 256;
-constexpr uint32_t kSub = 256;                    // sub-chunk walked by one lane
-constexpr uint32_t kSubs = kChunk / kSub;         // 16 walkers per chunk
 __global__ void __launch_bounds__(kMarkThreads)
 orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* __restrict__ entry,
-                  uint32_t* __restrict__ bitmap, uint32_t* __restrict__ chunk_tokens) {
+                  const uint16_t* __restrict__ jumps, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ chunk_tokens) {
+    // jumps (may be null): the sub-chunk jump table chunk_exit_kernel left in HBM
     // The orbit inside a chunk is sequential, but once the first arrival in every 256-position
     // sub-chunk is known the 16 sub-chunks can be walked at the same time.  Those arrivals come from
     // pointer jumping restricted to sub-chunks (jump[i] = first arrival at or past the end of i's
     // sub-chunk), chained from the chunk's true entry.
     __shared__ uint32_t sn[kChunk];    // step | tokens emitted by an arrival here << 16
-    __shared__ uint16_t jump[kChunk];
+    __shared__ __align__(16) uint16_t jump[kChunk];
     __shared__ uint32_t bits[kChunk / 32];
     __shared__ uint32_t sub_entry[kSubs];
     __shared__ uint32_t sub_tokens[kSubs];
@@ -1260,11 +1270,15 @@ orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* _
             t = (v >> 16) ? (v & 255u) + 1 : 1;
         }
         sn[i] = s | (t << 16);
-        jump[i] = (uint16_t)(i + s);  // <= 4095 + 515
+        if (!jumps) jump[i] = (uint16_t)(i + s);  // <= 4095 + 515
+    }
+    if (jumps) {
+        const uint4* src = reinterpret_cast<const uint4*>(jumps + (size_t)c * kChunk);
+        for (uint32_t i = threadIdx.x; i < kChunk / 8; i += kMarkThreads) reinterpret_cast<uint4*>(jump)[i] = src[i];
     }
     for (uint32_t i = threadIdx.x; i < kChunk / 32; i += kMarkThreads) bits[i] = 0;
     __syncthreads();
-    while (true) {
+    while (!jumps) {
         bool pending = false;
         for (uint32_t i = threadIdx.x; i < kChunk; i += kMarkThreads) {
             const uint32_t t = jump[i];
@@ -1419,6 +1433,7 @@ static SearchTune g_tune{3, 8};
 static int g_use_roll = 0;
 constexpr uint32_t kSparseT = 32768, kSparseW = 1024, kSparseThreads = 1024;
 static int g_sparse_variant = 0;  // see lz77_sparse_range
+static int g_exit_threads = 128;   // chunk_exit_kernel block size (FB200_EXIT_THREADS): small blocks hide the load latency better
 static SparseTune g_sparse_tune{1, 1, 1};
 static void lz77_init_once() {
     // function attributes are per device: a process may hold contexts on several GPUs
@@ -1456,6 +1471,7 @@ static void lz77_init_once() {
     const char* e = getenv("FB200_SEARCH");
     g_use_roll = (e && e[0] == 'r') ? 1 : 0;
     // FB200_SPARSE="variant[,pend_at,done_at,refill_at]": shape and pacing of the sparse parse kernel
+    if (const char* et = getenv("FB200_EXIT_THREADS")) g_exit_threads = atoi(et) >= 128 && atoi(et) <= 1024 ? atoi(et) : 128;
     if (const char* sp = getenv("FB200_SPARSE")) {
         int v = 0, p = 0, d = 0, r = 0;
         const int got = sscanf(sp, "%d,%d,%d,%d", &v, &p, &d, &r);
@@ -1576,7 +1592,7 @@ cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin
     group_entry_kernel<<<1, 32, 0, st>>>(b.gexits, ngroups, b.gentry);
     chunk_entry_kernel<<<(ngroups + 127) / 128, 128, 0, st>>>(b.exits, b.gentry, nchunks, b.entry);
     pt->mark(st, kPhResolve);
-    orbit_mark_kernel<<<nchunks, kMarkThreads, 0, st>>>(b.nx, n, b.entry, b.bitmap, b.chunk_tokens);
+    orbit_mark_kernel<<<nchunks, kMarkThreads, 0, st>>>(b.nx, n, b.entry, nullptr, b.bitmap, b.chunk_tokens);
     pt->mark(st, kPhMark);
     scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
     pt->mark(st, kPhScan);
@@ -1614,13 +1630,13 @@ cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32
     }
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
     const uint32_t ngroups = (nchunks + kGroup - 1) / kGroup;
-    chunk_exit_kernel<<<nchunks, 1024, 0, st>>>(b.nx, n, b.exits);
+    chunk_exit_kernel<<<nchunks, g_exit_threads, 0, st>>>(b.nx, n, b.exits, b.jumps);
     pt->mark(st, kPhChunkExit);
     group_exit_kernel<<<ngroups, 544, 0, st>>>(b.exits, nchunks, b.gexits);
     group_entry_kernel<<<1, 32, 0, st>>>(b.gexits, ngroups, b.gentry);
     chunk_entry_kernel<<<(ngroups + 127) / 128, 128, 0, st>>>(b.exits, b.gentry, nchunks, b.entry);
     pt->mark(st, kPhResolve);
-    orbit_mark_kernel<<<nchunks, kMarkThreads, 0, st>>>(b.nx, n, b.entry, b.bitmap, b.chunk_tokens);
+    orbit_mark_kernel<<<nchunks, kMarkThreads, 0, st>>>(b.nx, n, b.entry, b.jumps, b.bitmap, b.chunk_tokens);
     pt->mark(st, kPhMark);
     scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
     pt->mark(st, kPhScan);

@@ -61,6 +61,7 @@ struct Lz77Buffers {
     uint16_t* gexits;        // ngroups * kEntries
     uint16_t* gentry;        // ngroups
     uint16_t* entry;         // nchunks
+    uint16_t* jumps;         // nchunks * kChunk   sub-chunk jump table (chunk_exit -> orbit_mark, sparse strategy)
     uint32_t* bitmap;        // nchunks * kChunk/32   arrivals actually visited
     uint32_t* chunk_tokens;  // nchunks
     uint32_t* tok_offset;    // nchunks

@@ -1,7 +1,2 @@
-(
-for v in 0 3 4; do
-FB200_SPARSE=$v timeout 120 python tools/phase_times.py 256 6
-done
-FB200_SPARSE=4 timeout 120 python tools/phase_times.py 256 9
-) 2>&1 | sed -e 's/hash_link=.*sparse_parse/sparse_parse/' > gpurun_out/sparse_times.log
-cat gpurun_out/sparse_times.log
+timeout 120 python tools/phase_times.py 256 6 2>&1 | tail -1 | sed -e 's/hash_link=[0-9.]* //' | cut -c1-200
+timeout 900 python -m pytest tests/test_gpu_deflate.py -x -q -k "token or sparse or sharded or bit_exact" 2>&1 | tail -2
