@@ -1433,6 +1433,7 @@ static SearchTune g_tune{3, 8};
 static int g_use_roll = 0;
 constexpr uint32_t kSparseT = 32768, kSparseW = 1024, kSparseThreads = 1024;
 static int g_sparse_variant = 0;  // see lz77_sparse_range
+static uint32_t g_link_run = 128;  // longest run of hash tiles per CTA (FB200_LINK_RUN): each run pays 4 warm-up tiles
 static int g_exit_threads = 128;   // chunk_exit_kernel block size (FB200_EXIT_THREADS): small blocks hide the load latency better
 static SparseTune g_sparse_tune{1, 1, 1};
 static void lz77_init_once() {
@@ -1471,6 +1472,7 @@ static void lz77_init_once() {
     const char* e = getenv("FB200_SEARCH");
     g_use_roll = (e && e[0] == 'r') ? 1 : 0;
     // FB200_SPARSE="variant[,pend_at,done_at,refill_at]": shape and pacing of the sparse parse kernel
+    if (const char* lr = getenv("FB200_LINK_RUN")) g_link_run = atoi(lr) >= 4 && atoi(lr) <= 4096 ? (uint32_t)atoi(lr) : 128;
     if (const char* et = getenv("FB200_EXIT_THREADS")) g_exit_threads = atoi(et) >= 128 && atoi(et) <= 1024 ? atoi(et) : 128;
     if (const char* sp = getenv("FB200_SPARSE")) {
         int v = 0, p = 0, d = 0, r = 0;
@@ -1495,10 +1497,10 @@ cudaError_t lz77_search_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_
     if (range_end <= from) return cudaSuccess;
     if (link_from > from) link_from = from;
     const uint32_t ntiles = (range_end + kLinkTile - 1) / kLinkTile - link_from / kLinkTile;
-    // run length: long enough to amortise the 4 warm-up tiles (<= 32 tiles), and chosen so that the grid is
+    // run length: long enough to amortise the 4 warm-up tiles (<= g_link_run tiles), and chosen so that the grid is
     // close to a whole number of waves of 2 CTAs per SM
     const uint32_t slots = 2 * (uint32_t)g_num_sms;
-    const uint32_t waves = (ntiles + slots * 32 - 1) / (slots * 32);
+    const uint32_t waves = (ntiles + slots * g_link_run - 1) / (slots * g_link_run);
     const uint32_t run = max(1u, (ntiles + slots * waves - 1) / (slots * waves));
     hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, link_from, range_end, n, run, d_skip, nskip, b.link);
     pt->mark(st, kPhLink);
@@ -1530,7 +1532,7 @@ cudaError_t lz77_link_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t 
     if (range_end <= link_from) return cudaSuccess;
     const uint32_t ntiles = (range_end + kLinkTile - 1) / kLinkTile - link_from / kLinkTile;
     const uint32_t slots = 2 * (uint32_t)g_num_sms;
-    const uint32_t waves = (ntiles + slots * 32 - 1) / (slots * 32);
+    const uint32_t waves = (ntiles + slots * g_link_run - 1) / (slots * g_link_run);
     const uint32_t run = max(1u, (ntiles + slots * waves - 1) / (slots * waves));
     hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, link_from, range_end, n, run, nullptr, 0, b.link);
     pt->mark(st, kPhLink);
