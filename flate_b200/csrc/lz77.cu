@@ -1380,7 +1380,7 @@ emit_tokens_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
     constexpr uint32_t kPer = kChunk / kEmitThreads;  // 16 positions per thread
     const uint32_t i0 = threadIdx.x * kPer;
     const uint32_t word = bitmap[(size_t)c * (kChunk / 32) + (i0 >> 5)];
-    const uint32_t mask = (word >> (i0 & 31)) & ((1u << kPer) - 1);
+    const uint32_t mask = kPer >= 32 ? word : (word >> (i0 & 31)) & ((1u << (kPer & 31)) - 1);
     // tokens of my arrivals
     uint32_t mine = 0;
     for (uint32_t m = mask; m; m &= m - 1) {
