@@ -1588,7 +1588,7 @@ cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin
     n -= begin;
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
     const uint32_t ngroups = (nchunks + kGroup - 1) / kGroup;
-    lazy_exit_kernel<<<nchunks, 1024, 0, st>>>(b.r_full, b.r_quarter, n, lv, b.nx, b.exits);
+    lazy_exit_kernel<<<nchunks, 256, 0, st>>>(b.r_full, b.r_quarter, n, lv, b.nx, b.exits);
     pt->mark(st, kPhChunkExit);
     group_exit_kernel<<<ngroups, 544, 0, st>>>(b.exits, nchunks, b.gexits);
     group_entry_kernel<<<1, 32, 0, st>>>(b.gexits, ngroups, b.gentry);
