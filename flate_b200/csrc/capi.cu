@@ -250,23 +250,26 @@ static inline size_t footer_size(int container) { return container == FB200_GZIP
 // bit 1 = the token emitter met an entry that was never evaluated.  Non-zero => redo with dense tables.
 constexpr int kSparseFlagIdx = 20;
 constexpr size_t kSpHaloPlus = 256 + 272;  // lz77_sparse_lookahead() = overlap + lazy halo + compare look-ahead
-static int sparse_begin(fb200_ctx* c, const Lz77Buffers& b, size_t n, cudaStream_t st) {
-    FB_CUDA_CHECK(cudaMemsetAsync(b.nx, 0xFF, n * sizeof(uint32_t), st));
+static int sparse_begin(fb200_ctx* c, const Lz77Buffers& b, size_t count, cudaStream_t st) {
+    FB_CUDA_CHECK(cudaMemsetAsync(b.nx, 0xFF, count * sizeof(uint32_t), st));
     FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
     return FB200_OK;
 }
-// whole stream already on the device
-static int sparse_tokenize(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in, size_t n, const LevelArgs& lv, cudaStream_t st) {
-    if (n == 0) {
+// segment [begin, n) of a stream that is already on the device (begin > 0: earlier bytes are history, their links
+// are in place; d_skip/nskip: history positions the reference never inserted into its chains)
+static int sparse_tokenize(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in, size_t begin, size_t n, const uint32_t* d_skip,
+                           uint32_t nskip, const LevelArgs& lv, cudaStream_t st) {
+    if (n == begin) {
         FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, 0, lv, st, &c->timer));
         return FB200_OK;
     }
-    int rc = sparse_begin(c, b, n, st);
+    int rc = sparse_begin(c, b, n - begin, st);
     if (rc) return rc;
     const uint32_t T = lz77_sparse_chunk();
-    FB_CUDA_CHECK(lz77_link_range(b, d_in, 0, (uint32_t)n, (uint32_t)n, st, &c->timer));
-    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, 0, (uint32_t)((n + T - 1) / T), (uint32_t)n, lv, c->chunk_fail.p, c->d_scalars + kSparseFlagIdx, st, &c->timer));
-    FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
+    FB_CUDA_CHECK(lz77_link_range(b, d_in, (uint32_t)begin, (uint32_t)n, (uint32_t)n, st, &c->timer, d_skip, nskip));
+    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, (uint32_t)(begin / T), (uint32_t)((n + T - 1) / T), (uint32_t)n, lv, c->chunk_fail.p,
+                                    c->d_scalars + kSparseFlagIdx, st, &c->timer, (uint32_t)begin));
+    FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in + begin, (uint32_t)(n - begin), lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
     c->launches += 9;
     return FB200_OK;
 }
@@ -275,8 +278,8 @@ static int sparse_tokenize(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_
 // evaluate every position of the chunks that follow a failed chunk; a repaired chunk that fails itself
 // hands the problem to its successor.  Afterwards nx is closed under the lazy step again and the caller
 // parses once more.  Returns FB200_OK and *ok = false when it gives up (caller redoes the stream densely).
-static int sparse_repair(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in, size_t n, const LevelArgs& lv, cudaStream_t st,
-                         bool* ok) {
+static int sparse_repair(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in, size_t begin, size_t n, const LevelArgs& lv,
+                         cudaStream_t st, bool* ok) {
     *ok = false;
     const uint32_t T = lz77_sparse_chunk();
     const uint32_t nch = (uint32_t)((n + T - 1) / T);
@@ -284,7 +287,7 @@ static int sparse_repair(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in
     std::vector<uint8_t> dense(nch, 0);
     FB_CUDA_CHECK(cudaMemcpyAsync(fail.data(), c->chunk_fail.p, nch * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
-    for (uint32_t i = 0; i + 1 < nch; i++)
+    for (uint32_t i = (uint32_t)(begin / T); i + 1 < nch; i++)  // chunks before the segment were not evaluated now
         if (fail[i]) list.push_back(i + 1);
     size_t total = 0;
     for (int round = 0; round < 6 && !list.empty(); round++) {
@@ -293,7 +296,7 @@ static int sparse_repair(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in
         for (uint32_t ch : list) dense[ch] = 1;
         FB_CUDA_CHECK(cudaMemcpyAsync(c->chunk_list.p, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         FB_CUDA_CHECK(lz77_sparse_dense_chunks(b, d_in, c->chunk_list.p, (uint32_t)list.size(), (uint32_t)n, lv, c->chunk_fail.p,
-                                               c->d_scalars + kSparseFlagIdx, st, &c->timer));
+                                               c->d_scalars + kSparseFlagIdx, st, &c->timer, (uint32_t)begin));
         c->launches += 1;
         FB_CUDA_CHECK(cudaMemcpyAsync(fail.data(), c->chunk_fail.p, nch * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         FB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -357,16 +360,16 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         if (redo == 1) {
             sparse = true;
             FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
-            FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
+            FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in + begin, (uint32_t)(n - begin), lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
             c->launches += 7;
         } else if (d_nx_given) {
             b.nx = const_cast<uint32_t*>(d_nx_given);
             FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
             FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
             c->launches += n ? 7 : 0;
-        } else if ((sparse = (begin == 0 && nskip == 0 && n > 0 && redo == 0 && c->parse_mode == 0)) && !(h_src && n > kSlab + kLag)) {
-            if (h_src) FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in), h_src, n, cudaMemcpyHostToDevice, st));
-            if ((rc = sparse_tokenize(c, b, d_in, n, lv, st))) return rc;
+        } else if ((sparse = (n > begin && redo == 0 && c->parse_mode == 0)) && !(h_src && begin == 0 && n > kSlab + kLag)) {
+            if (h_src) FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in) + begin, h_src, n - begin, cudaMemcpyHostToDevice, st));
+            if ((rc = sparse_tokenize(c, b, d_in, begin, n, d_skip, nskip, lv, st))) return rc;
         } else if (sparse) {
             // slab-overlapped copy: links follow the copy front one hash tile behind, the sparse parse follows the
             // links by its look-ahead
@@ -513,7 +516,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         bool ok = false;
         if (redo == 0) {
             Lz77Buffers b = lz77_view(c);
-            int rc = sparse_repair(c, b, d_in, n, lv, st, &ok);
+            int rc = sparse_repair(c, b, d_in, begin, n, lv, st, &ok);
             if (rc) return rc;
         }
         if (ok) c->sparse_repairs++;
@@ -659,12 +662,12 @@ int fb200_debug_tokens(fb200_ctx* c, int level, const uint8_t* in, size_t n, uin
     Lz77Buffers b = lz77_view(c);
     uint32_t total = 0, bad = 0;
     if (c->parse_mode == 0 && n) {
-        if ((rc = sparse_tokenize(c, b, c->d_in.p, n, lv, st))) return rc;
+        if ((rc = sparse_tokenize(c, b, c->d_in.p, 0, n, nullptr, 0, lv, st))) return rc;
         FB_CUDA_CHECK(cudaMemcpyAsync(&bad, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
         FB_CUDA_CHECK(cudaStreamSynchronize(st));
         if (bad) {
             bool ok = false;
-            if ((rc = sparse_repair(c, b, c->d_in.p, n, lv, st, &ok))) return rc;
+            if ((rc = sparse_repair(c, b, c->d_in.p, 0, n, lv, st, &ok))) return rc;
             if (ok) {
                 FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
                 FB_CUDA_CHECK(lz77_parse_from_nx(b, c->d_in.p, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));

@@ -778,9 +778,12 @@ constexpr uint32_t kMaxCross = 32;
 
 template <uint32_t kT, uint32_t kW, uint32_t kG, uint32_t kThreads, int kMinBlocks, int kSteps, bool kDense>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, const uint32_t* __restrict__ chunk_list, uint32_t n,
-                    const uint16_t* __restrict__ link, LevelArgs lv, SparseTune tune, uint32_t* __restrict__ nx,
+sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t first_chunk, const uint32_t* __restrict__ chunk_list,
+                    uint32_t n, const uint16_t* __restrict__ link, LevelArgs lv, SparseTune tune, uint32_t* __restrict__ nx,
                     uint32_t* __restrict__ chunk_fail, uint32_t* __restrict__ flags) {
+    // begin: first position of the segment being compressed (0 for a whole stream; > 0 after a sync flush, when
+    // earlier bytes are history only).  The parse restarts clean at `begin`, so `begin` is a seed; positions before
+    // it are never evaluated.  nx is indexed by stream position (the caller passes its table shifted by -begin).
     // kDense: every position of the CTA's own range is a seed (the overlap keeps the regular seeds, the ones
     // the next CTA evaluates too).  Used to repair after a failed coverage check: once every entry of chunk
     // c+1 is evaluated, it no longer matters where the orbits leaving chunk c arrive.
@@ -803,7 +806,9 @@ sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, const 
     const bool open_end = (uint64_t)s + C::kSpan < n;                     // the stream goes on past the span
     const uint32_t own_len = min(kT, span_len);
     const uint32_t n_ov = (span_len - own_len + kG - 1) / kG;              // regular seeds in the overlap
-    const uint32_t nseeds = kDense ? n_ov + own_len : (span_len + kG - 1) / kG;
+    const uint32_t nreg = kDense ? n_ov + own_len : (span_len + kG - 1) / kG;  // regular seeds
+    const bool has_begin = begin > s && begin - s < own_len;                   // the segment starts inside this chunk
+    const uint32_t nseeds = nreg + (has_begin ? 1u : 0u);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t ltmask = (1u << lane) - 1;
 
@@ -1044,10 +1049,11 @@ sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t first_chunk, const 
             } else if (st == kIdle) {
                 const uint32_t t = base + __popc(idle & ltmask);
                 if (t < nseeds) {
-                    if (kDense) a_rel = t < n_ov ? kT + (n_ov - 1 - t) * kG : own_len - 1 - (t - n_ov);
-                    else a_rel = (nseeds - 1 - t) * kG;
+                    if (t == nreg) a_rel = begin - s;  // the segment's first position: where the true orbit starts
+                    else if (kDense) a_rel = t < n_ov ? kT + (n_ov - 1 - t) * kG : own_len - 1 - (t - n_ov);
+                    else a_rel = (nreg - 1 - t) * kG;
                     from_overlap = a_rel >= kT;
-                    st = kArrive;
+                    if (s + a_rel >= begin) st = kArrive;  // positions before the segment are history, not seeds
                 }
             }
         }
@@ -1525,7 +1531,7 @@ cudaError_t lz77_search_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_
 
 // K1 alone for positions [link_from, range_end).
 cudaError_t lz77_link_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t link_from, uint32_t range_end, uint32_t n,
-                            cudaStream_t st, PhaseTimer* pt) {
+                            cudaStream_t st, PhaseTimer* pt, const uint32_t* d_skip, uint32_t nskip) {
     lz77_init_once();
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
@@ -1534,7 +1540,7 @@ cudaError_t lz77_link_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t 
     const uint32_t slots = 2 * (uint32_t)g_num_sms;
     const uint32_t waves = (ntiles + slots * g_link_run - 1) / (slots * g_link_run);
     const uint32_t run = max(1u, (ntiles + slots * waves - 1) / (slots * waves));
-    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, link_from, range_end, n, run, nullptr, 0, b.link);
+    hash_link_kernel<<<(ntiles + run - 1) / run, kLinkThreads, kLinkSmem, st>>>(d_in, link_from, range_end, n, run, d_skip, nskip, b.link);
     pt->mark(st, kPhLink);
     return cudaGetLastError();
 }
@@ -1545,13 +1551,15 @@ cudaError_t lz77_link_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t 
 uint32_t lz77_sparse_chunk() { return kSparseT; }
 uint32_t lz77_sparse_lookahead() { return kSparseW + kSpHalo + 272; }
 cudaError_t lz77_sparse_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t first_chunk, uint32_t end_chunk, uint32_t n,
-                              const LevelArgs& lv, uint32_t* chunk_fail, uint32_t* flags, cudaStream_t st, PhaseTimer* pt) {
+                              const LevelArgs& lv, uint32_t* chunk_fail, uint32_t* flags, cudaStream_t st, PhaseTimer* pt,
+                              uint32_t begin) {
+    // begin > 0: b.nx is relative to the segment start (like every table after the match search)
     lz77_init_once();
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
     if (end_chunk <= first_chunk) return cudaSuccess;
     const uint32_t grid = end_chunk - first_chunk;
-#define FB_SPARSE(G, ST) sparse_parse_kernel<kSparseT, kSparseW, G, kSparseThreads, 1, ST, false><<<grid, kSparseThreads, SparseCfg<kSparseT, kSparseW>::kSmem, st>>>(d_in, first_chunk, nullptr, n, b.link, lv, g_sparse_tune, b.nx, chunk_fail, flags)
+#define FB_SPARSE(G, ST) sparse_parse_kernel<kSparseT, kSparseW, G, kSparseThreads, 1, ST, false><<<grid, kSparseThreads, SparseCfg<kSparseT, kSparseW>::kSmem, st>>>(d_in, begin, first_chunk, nullptr, n, b.link, lv, g_sparse_tune, b.nx - begin, chunk_fail, flags)
     switch (g_sparse_variant) {
         case 1: FB_SPARSE(32, 4); break;
         case 2: FB_SPARSE(16, 8); break;
@@ -1563,13 +1571,14 @@ cudaError_t lz77_sparse_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_
 }
 // Repair: evaluates every position of the listed chunks (device array of `count` chunk numbers).
 cudaError_t lz77_sparse_dense_chunks(const Lz77Buffers& b, const uint8_t* d_in, const uint32_t* chunk_list, uint32_t count, uint32_t n,
-                                     const LevelArgs& lv, uint32_t* chunk_fail, uint32_t* flags, cudaStream_t st, PhaseTimer* pt) {
+                                     const LevelArgs& lv, uint32_t* chunk_fail, uint32_t* flags, cudaStream_t st, PhaseTimer* pt,
+                                     uint32_t begin) {
     lz77_init_once();
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
     if (count == 0) return cudaSuccess;
     sparse_parse_kernel<kSparseT, kSparseW, 32, kSparseThreads, 1, 8, true><<<count, kSparseThreads, SparseCfg<kSparseT, kSparseW>::kSmem, st>>>(
-        d_in, 0, chunk_list, n, b.link, lv, g_sparse_tune, b.nx, chunk_fail, flags);
+        d_in, begin, 0, chunk_list, n, b.link, lv, g_sparse_tune, b.nx - begin, chunk_fail, flags);
     pt->mark(st, kPhSparse);
     return cudaGetLastError();
 }
