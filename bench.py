@@ -4,12 +4,14 @@
 Default workload = BASELINE.json configs[1]: raw deflate level 6 over 256 MiB of enwik-like synthetic
 bytes on one B200.  A "step" is one pass of the hot path over that batch.  With --gpus N (launched
 under torchrun) every rank compresses its own independent 256 MiB chunk (the path shards by chunk;
-weak scaling) and the per-shard outputs are all-gathered over NCCL.  The same run also measures the
-inflate side (config C3 shape: 1 MiB gzip members, 1 GiB of plain output at N = 1).
+weak scaling) and the per-shard outputs are all-gathered over NCCL; for N > 1 it also compresses ONE stream
+sharded by position over all ranks (single_stream).  The same run also measures the inflate side (config C3
+shape: 1 MiB gzip members, 1 GiB of plain output split over the ranks, plus 1 GiB per rank as inflate.weak).
 
   value     : whole-job deflate L6 throughput, MB/s of INPUT, inputs resident in HBM (CUDA events)
   e2e       : same metric through the public host-buffer call (pinned host -> H2D -> kernels -> D2H)
-  roofline  : dominant kernel (match_search) algorithmic bytes / its live CUDA-event time vs measured HBM peak
+  roofline  : dominant kernel (the phase with the largest live CUDA-event time: sparse_parse) algorithmic bytes /
+              that time vs the measured HBM peak; traffic from profiles/traffic.json (ncu --set full)
   cpu_baseline : the CPU oracle (a port of the reference's algorithm; the reference is Zig and there
                  is no zig toolchain) timed on this box's host cores, single thread like the reference
 
