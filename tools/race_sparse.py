@@ -1,5 +1,8 @@
-import os, sys
-sys.path.insert(0, "/root/repo")
+"""Small sparse-parse run (one dense repair included) for compute-sanitizer --tool racecheck."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, zlib
 import flate_b200
 from flate_b200 import synth
