@@ -113,6 +113,70 @@ static void run_chunks(int T, int W, int G, int L, int strategy, long* work_out,
     free(claimed); free(pos); free(seg_end); free(busy); free(heap);
 }
 
+
+// Rolling form: ONE persistent CTA over the whole input.  Ring of 65536 positions with load front lb (epochs of
+// 4096); an arrival a may begin when a + 544 <= lb; an epoch may be loaded when min(active arrivals, next seed)
+// >= lb + 4096 - 32768.  Seeds ascending.  A lane whose next arrival is not loaded parks it (list of `park_cap`
+// entries; overflow = dropped, counted) and goes back to the seed counter; idle lanes resume parked arrivals first.
+static void run_rolling(int G, int L, int park_cap) {
+    uint8_t* claimed = calloc(n + 1024, 1);
+    size_t* pos = malloc(sizeof(size_t) * L);
+    char* busy = malloc(L);
+    size_t* park = malloc(sizeof(size_t) * (park_cap + 1));
+    int npark = 0;
+    heap = malloc(sizeof(Ev) * (L + 8));
+    hn = 0;
+    long work = 0, t_end = 0, dropped = 0, parked_total = 0, waits = 0;
+    size_t next_seed = 0, lb = 16384;
+    const size_t load_end = (n + 544 + 4095) / 4096 * 4096;
+    memset(busy, 0, L);
+    for (int l = 0; l < L; l++) hpush((Ev){0, l});
+    while (hn) {
+        Ev e = hpop();
+        int l = e.lane;
+        // try to advance the load front as far as allowed (cheap in the model; on the GPU: one block-wide episode each)
+        for (;;) {
+            if (lb >= load_end) break;
+            size_t pmin = next_seed < n ? next_seed : (size_t)-1;
+            for (int k = 0; k < L; k++) if (busy[k] && pos[k] < pmin) pmin = pos[k];
+            for (int k = 0; k < npark; k++) if (park[k] < pmin) pmin = park[k];
+            // only load when somebody needs it: a parked arrival, or the seed front close to the loaded front
+            int need = npark > 0 || next_seed + 2048 + 544 >= lb;
+            if (!need || (pmin != (size_t)-1 && pmin + 28672 < lb)) break;
+            lb += 4096;
+        }
+        const size_t avail = lb >= load_end ? n : lb - 544;
+        size_t p;
+        if (!busy[l]) {
+            int got = 0;
+            for (int k = 0; k < npark; k++)
+                if (park[k] < avail) { p = park[k]; park[k] = park[--npark]; got = 1; break; }
+            if (!got) {
+                if (next_seed < n && next_seed < avail) { p = next_seed; next_seed += G; }
+                else if (next_seed >= n && npark == 0) { if (e.t > t_end) t_end = e.t; continue; }  // nothing left for this lane
+                else { waits++; hpush((Ev){e.t + 1, l}); continue; }                             // wait for a load
+            }
+            busy[l] = 1;
+        } else p = pos[l];
+        if (p >= n || claimed[p]) { busy[l] = 0; hpush((Ev){e.t + 1, l}); continue; }
+        if (p >= avail) {  // next arrival not resident: park it and take other work
+            if (npark < park_cap) { park[npark++] = p; parked_total++; } else dropped++;
+            busy[l] = 0;
+            hpush((Ev){e.t + 1, l});
+            continue;
+        }
+        claimed[p] = 1;
+        int r = 0;
+        pos[l] = step(p, &r);
+        work += r;
+        hpush((Ev){e.t + r, l});
+        if (e.t + r > t_end) t_end = e.t + r;
+    }
+    printf("rolling, G=%d, %d lanes, park list %d: work %ld rounds, makespan %ld, lane utilisation %.1f %%, parked %ld, dropped %ld, idle waits %ld\n",
+           G, L, park_cap, work, t_end, 100.0 * work / ((double)L * t_end), parked_total, dropped, waits);
+    free(claimed); free(pos); free(busy); free(park); free(heap);
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) { fprintf(stderr, "usage: %s FILE [level]\n", argv[0]); return 2; }
     FILE* f = fopen(argv[1], "rb");
@@ -145,5 +209,12 @@ int main(int argc, char** argv) {
         printf("%-58s work %9ld rounds, makespan %8ld, ideal %8ld, lane utilisation %.1f %%, candidates %ld\n", cfg[i].name, w, sp, id,
                100.0 * w / ((double)cfg[i].L * sp), g_visits);
     }
+    run_rolling(32, 1024, 256);
+    run_rolling(32, 768, 256);
+    run_rolling(32, 512, 256);
+    run_rolling(16, 1024, 256);
+    run_rolling(16, 512, 256);
+    run_rolling(8, 1024, 256);
+    run_rolling(24, 1024, 256);
     return 0;
 }
