@@ -1,0 +1,37 @@
+"""The reference arm of bench.py runs without a GPU: one JSON line with the contract's keys, also for N > 1
+(where only rank 0 works and prints)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra,
+                       capture_output=True, text=True, timeout=600, env=e, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return [ln for ln in p.stdout.splitlines() if ln.strip()]
+
+
+def test_reference_arm_one_json_line():
+    lines = _run([])
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "MB/s" and d["value"] > 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    assert _run(["--gpus", "2"], {"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+    lines = _run(["--gpus", "2"], {"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["cpu_baseline"]["cores"] >= 1
