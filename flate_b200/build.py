@@ -8,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libflate_b200.so")
-SOURCES = ["lz77.cu", "block_writer.cu", "inflate.cu", "capi.cu"]
-HEADERS = ["common.cuh", "pipeline.cuh", "inflate.cuh", os.path.join("..", "..", "include", "flate_b200.h")]
+SOURCES = ["lz77.cu", "block_writer.cu", "inflate.cu", "inflate_par.cu", "capi.cu"]
+HEADERS = ["common.cuh", "pipeline.cuh", "inflate.cuh", "inflate_dev.cuh", "inflate_span.cuh", os.path.join("..", "..", "include", "flate_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math"]
 

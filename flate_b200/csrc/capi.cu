@@ -169,11 +169,17 @@ int fb200_ctx_create(int device, fb200_ctx** out) {
     fb200_ctx* c = new (std::nothrow) fb200_ctx();
     if (!c) return FB200_INVALID_ARGUMENT;
     c->device = device;
-    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (auto& e : c->slab_ev) FB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    FB_CUDA_CHECK(cudaMalloc(&c->d_scalars, 256));
-    FB_CUDA_CHECK(cudaMallocHost(&c->h_scalars, 128));
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (auto& ev : c->slab_ev)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_scalars, 256);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_scalars, 128);
+    if (e != cudaSuccess) {  // release whatever was created
+        fb::set_last_cuda_error(e, __FILE__, __LINE__);
+        fb200_ctx_destroy(c);
+        return FB200_ERR_CUDA;
+    }
     *out = c;
     return FB200_OK;
 }
@@ -186,12 +192,14 @@ void fb200_ctx_destroy(fb200_ctx* c) {
     c->r_full.release(); c->r_quarter.release(); c->nx.release(); c->bitmap.release(); c->chunk_tokens.release();
     c->tok_offset.release(); c->tokens.release(); c->cut_rp.release(); c->plans.release(); c->descs.release();
     c->lit_freq.release(); c->dist_freq.release(); c->d_in.release(); c->d_out.release(); c->m_desc.release();
+    c->jumps.release(); c->chunk_fail.release(); c->chunk_list.release();
+    c->timer.destroy();
     if (c->d_scalars) cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
     for (auto& e : c->slab_ev)
         if (e) cudaEventDestroy(e);
-    cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -767,12 +775,19 @@ static int run_members(fb200_ctx* c, int container, const uint8_t* d_in, const M
     MemberResult* d_res = reinterpret_cast<MemberResult*>(c->m_desc.p + desc_words);
     FB_CUDA_CHECK(cudaMemcpyAsync(d_desc, h_desc, k * sizeof(MemberDesc), cudaMemcpyHostToDevice, st));
     c->timer.begin(st);
-    FB_CUDA_CHECK(inflate_members(container, d_in, d_desc, (uint32_t)k, d_out, d_res, st));
+    static const bool warp_kernel = [] { const char* e = getenv("FB200_INFLATE"); return e && strcmp(e, "warp") == 0; }();
+    if (warp_kernel) FB_CUDA_CHECK(inflate_members(container, d_in, d_desc, (uint32_t)k, d_out, d_res, st));
+    else FB_CUDA_CHECK(inflate_members_par(container, d_in, d_desc, (uint32_t)k, d_out, d_res, st));
     c->timer.mark(st, kPhInflate);
     c->launches += 1;
     FB_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, k * sizeof(MemberResult), cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
     c->timer.collect();
+    static const bool stats = getenv("FB200_INFLATE_STATS") != nullptr;  // development: rounds / retries / exact-path calls
+    if (stats)
+        for (size_t i = 0; i < k && i < 4; i++)
+            fprintf(stderr, "inflate member %zu: status %u out %llu rounds %u retries %u exact %u\n", i, h_res[i].status,
+                    (unsigned long long)h_res[i].out_len, h_res[i].pad & 0xfff, (h_res[i].pad >> 12) & 0x3ff, h_res[i].pad >> 22);
     return FB200_OK;
 }
 

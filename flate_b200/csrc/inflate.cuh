@@ -16,6 +16,10 @@ struct MemberResult {
 };
 constexpr uint32_t kNeedsHistory = 100;  // internal: match reaches before the member; redo after predecessors
 
+// one CTA per member, lane-parallel symbol decode inside the member (inflate_par.cu): the default
+cudaError_t inflate_members_par(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
+                                MemberResult* d_res, cudaStream_t st);
+// one warp per member (inflate.cu): kept for comparison, FB200_INFLATE=warp
 cudaError_t inflate_members(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
                             MemberResult* d_res, cudaStream_t st);
 

@@ -34,6 +34,11 @@ struct PhaseTimer {
         cudaEventRecord(ev[n], st);
         phase_of[n++] = phase;
     }
+    void destroy() {
+        if (created)
+            for (int i = 0; i < kMaxMarks; i++) cudaEventDestroy(ev[i]);
+        created = false;
+    }
     void collect() {  // after the stream was synchronized
         if (!on) return;
         for (int i = 1; i < n; i++) {
