@@ -110,6 +110,8 @@ struct fb200_ctx {
     uint64_t* h_scalars = nullptr;  // pinned: [0] total_bits [1] nblocks [2..] part offsets; [8] checksum
     // inflate workspace
     DevBuf<uint64_t> m_desc;        // member descriptors / results
+    DevBuf<uint8_t> m_scratch;      // work counter + per-CTA match queues of the member-parallel inflate kernel
+    int sm_count = 148;
     std::vector<uint64_t> h_members;
 };
 
@@ -169,6 +171,7 @@ int fb200_ctx_create(int device, fb200_ctx** out) {
     fb200_ctx* c = new (std::nothrow) fb200_ctx();
     if (!c) return FB200_INVALID_ARGUMENT;
     c->device = device;
+    if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count <= 0) c->sm_count = 148;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& ev : c->slab_ev)
@@ -192,7 +195,7 @@ void fb200_ctx_destroy(fb200_ctx* c) {
     c->r_full.release(); c->r_quarter.release(); c->nx.release(); c->bitmap.release(); c->chunk_tokens.release();
     c->tok_offset.release(); c->tokens.release(); c->cut_rp.release(); c->plans.release(); c->descs.release();
     c->lit_freq.release(); c->dist_freq.release(); c->d_in.release(); c->d_out.release(); c->m_desc.release();
-    c->jumps.release(); c->chunk_fail.release(); c->chunk_list.release();
+    c->jumps.release(); c->chunk_fail.release(); c->chunk_list.release(); c->m_scratch.release();
     c->timer.destroy();
     if (c->d_scalars) cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -777,7 +780,10 @@ static int run_members(fb200_ctx* c, int container, const uint8_t* d_in, const M
     c->timer.begin(st);
     static const bool warp_kernel = [] { const char* e = getenv("FB200_INFLATE"); return e && strcmp(e, "warp") == 0; }();
     if (warp_kernel) FB_CUDA_CHECK(inflate_members(container, d_in, d_desc, (uint32_t)k, d_out, d_res, st));
-    else FB_CUDA_CHECK(inflate_members_par(container, d_in, d_desc, (uint32_t)k, d_out, d_res, st));
+    else {
+        FB_CUDA_CHECK(c->m_scratch.ensure(inflate_par_scratch_bytes((uint32_t)k, c->sm_count)));
+        FB_CUDA_CHECK(inflate_members_par(container, d_in, d_desc, (uint32_t)k, d_out, d_res, c->m_scratch.p, c->sm_count, st));
+    }
     c->timer.mark(st, kPhInflate);
     c->launches += 1;
     FB_CUDA_CHECK(cudaMemcpyAsync(h_res, d_res, k * sizeof(MemberResult), cudaMemcpyDeviceToHost, st));

@@ -29,12 +29,12 @@ namespace fb {
 
 namespace par {
 
-constexpr uint32_t kLanes = 256, kWarps = kLanes / 32;
-constexpr uint32_t kRing = 65536;                     // output window: 32 KiB of history + one round
+constexpr uint32_t kLanes = 512, kWarps = kLanes / 32;
+constexpr uint32_t kRing = 131072;                    // output window: 32 KiB of history + one round
 constexpr uint32_t kBudget = kRing - 32768 - 16;      // output bytes a round may commit
-constexpr uint32_t kQueue = 3072;                     // matches a round may commit
+constexpr uint32_t kQueue = 16384;                    // matches a round may commit (queue in HBM/L2, one per resident CTA)
 constexpr uint32_t kWarm = 640;                       // V: bits decoded before a lane's span to fall into step
-constexpr uint32_t kSpanMin = 64, kSpanMax = 1024, kSpanInit = 384;
+constexpr uint32_t kSpanMin = 64, kSpanMax = 2048, kSpanInit = 512;
 constexpr uint32_t kMaxRetry = 4;
 constexpr uint32_t kFastMinBits = 4096;               // closer to the end of the input only the exact path runs
 constexpr uint32_t kTailSlack = 256;                  // bits before the end of the input where lanes stop
@@ -57,13 +57,14 @@ struct Ctrl {                 // written by one thread, read by all after a barr
     uint32_t stored_len;
     unsigned long long stored_src;
     uint32_t rounds, retries, exact_calls;
+    uint32_t member;          // index of the member this CTA works on
 };
 
 struct Shared {
     DecTables T;
-    uint2 queue[kQueue];
-    uint32_t l_start[kLanes], l_end[kLanes], l_bytes[kLanes], l_nm[kLanes], l_flag[kLanes];
+    uint32_t l_start[kLanes], l_end[kLanes], l_flag[kLanes];
     uint32_t w_a[kWarps], w_b[kWarps], w_c[kWarps];
+    uint32_t pend[(kBudget + 31) / 32 + 1];  // pending-byte bitmap of the round being resolved
     uint32_t crc_tab[256];
     Ctrl c;
 };
@@ -71,6 +72,7 @@ struct Shared {
 struct Window {
     uint8_t* ring;
     uint8_t* out;
+    uint2* queue;  // this CTA's match queue (global memory; written in the emit pass, read back through L2)
     uint32_t A;
     __device__ __forceinline__ uint32_t slot(uint64_t p) const { return (uint32_t)(p + A) & (kRing - 1); }
 };
@@ -122,35 +124,64 @@ __device__ __forceinline__ uint32_t first_false_cta(bool ok, uint32_t* s) {
     return r;
 }
 
-// Resolve queue[0, M) in stream order.  base = ring slot of the round's first byte; pos0 = its output position;
-// hist = bytes before the member's output that may be referenced (they live in HBM before W.out).
-__device__ void resolve_matches(Shared& S, const Window& W, uint32_t M, uint64_t pos0) {
+// ---- pending-byte bitmap of a round: bit p is set while output byte p (relative to the round's first byte) is the
+// destination of a match that has not been copied yet.  A match may copy as soon as no byte of its source is pending.
+__device__ __forceinline__ void pend_update(uint32_t* bm, uint32_t a, uint32_t b, bool set) {  // bits [a, b), a < b
+    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    for (uint32_t w = wa; w <= wb; w++) {
+        uint32_t m = 0xffffffffu;
+        if (w == wa) m &= 0xffffffffu << (a & 31);
+        if (w == wb) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+        if (set) atomicOr(bm + w, m);
+        else atomicAnd(bm + w, ~m);
+    }
+}
+__device__ __forceinline__ bool pend_any(const volatile uint32_t* bm, uint32_t a, uint32_t b) {  // any bit of [a, b) set; a < b
+    const uint32_t wa = a >> 5, wb = (b - 1) >> 5;
+    uint32_t acc = 0;
+    for (uint32_t w = wa; w <= wb; w++) {
+        uint32_t m = 0xffffffffu;
+        if (w == wa) m &= 0xffffffffu << (a & 31);
+        if (w == wb) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+        acc |= bm[w] & m;
+    }
+    return acc != 0;
+}
+
+// Resolve queue[0, M) (stream order) of a round that produced tot_b bytes starting at output position pos0.
+// Groups of 32 consecutive matches are dealt round-robin to the warps; a warp copies a match as soon as its source
+// bytes are final (pending bitmap), so only true dependency chains serialise.  The earliest unfinished match is
+// always ready and its warp is always working on its group (a warp's earlier groups are earlier in the stream),
+// hence progress.  Bytes before the member's output (history of earlier members) come from HBM.
+__device__ void resolve_matches(Shared& S, const Window& W, uint32_t M, uint64_t pos0, uint32_t tot_b) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t base = (uint32_t)(pos0 + W.A);
     const int64_t floor_rel = -(int64_t)min(pos0, (uint64_t)0x40000000u);  // sources below this are before the member's output
-    for (uint32_t g0 = 0; g0 < M; g0 += kLanes) {
-        const bool have = g0 + tid < M;
+    uint32_t* bm = S.pend;
+    for (uint32_t i = tid; i < (tot_b + 31) / 32; i += kLanes) bm[i] = 0;
+    __syncthreads();
+    for (uint32_t k = tid; k < M; k += kLanes) {
+        const uint2 q = __ldcg(W.queue + k);
+        pend_update(bm, q.x, q.x + (q.y >> 16), true);
+    }
+    __syncthreads();
+    for (uint32_t g0 = w * 32; g0 < M; g0 += kLanes) {
+        const bool have = g0 + lane < M;
         uint32_t dst = 0, len = 0, dist = 1;
         if (have) {
-            const uint2 q = S.queue[g0 + tid];
+            const uint2 q = __ldcg(W.queue + g0 + lane);
             dst = q.x;
             len = q.y >> 16;
             dist = (q.y & 0xffffu) + 1;
         }
         const int32_t src = (int32_t)dst - (int32_t)dist;
-        const int32_t need_end = src + (int32_t)min(len, dist);  // source bytes that exist before the copy starts
+        const int32_t need_end = src + (int32_t)min(len, dist);  // source bytes that must exist before the copy starts
+        const bool far = have && (int64_t)src < floor_rel;       // reaches before the member's output
         bool pending = have;
-        for (;;) {
-            const uint32_t pm = __ballot_sync(0xffffffffu, pending);
-            const uint32_t first_dst = __shfl_sync(0xffffffffu, dst, pm ? __ffs(pm) - 1 : 0);
-            if (lane == 0) S.w_c[w] = pm ? first_dst : 0xffffffffu;
-            __syncthreads();
-            uint32_t done_upto = 0xffffffffu;
-#pragma unroll
-            for (uint32_t i = 0; i < kWarps; i++) done_upto = min(done_upto, S.w_c[i]);
-            if (done_upto == 0xffffffffu) break;  // uniform
-            const bool ready = pending && need_end <= (int32_t)done_upto;
-            const bool far = ready && (int64_t)src < floor_rel;  // reaches before the member's output: bytes come from HBM
+        while (__any_sync(0xffffffffu, pending)) {
+            const bool ready = pending && (need_end <= 0 || !pend_any(bm, (uint32_t)max(src, 0), (uint32_t)need_end));
+            if (!__any_sync(0xffffffffu, ready)) continue;  // the bytes we wait for belong to another warp's group
+            __threadfence_block();  // the bitmap was read before the bytes are
             // short copies: one thread each, byte by byte in order (so overlapping copies replicate)
             if (ready && !far && len <= kThreadCopy) {
                 for (uint32_t i = 0; i < len; i++)
@@ -186,11 +217,14 @@ __device__ void resolve_matches(Shared& S, const Window& W, uint32_t M, uint64_t
                 }
                 __syncwarp();
             }
-            if (ready) pending = false;
-            __syncthreads();
+            __threadfence_block();  // the bytes are written before the bitmap says so
+            if (ready) {
+                pend_update(bm, dst, dst + len, false);
+                pending = false;
+            }
         }
-        __syncthreads();
     }
+    __syncthreads();
 }
 
 // CRC-32 / Adler-32 of the member's output (in HBM, written by this CTA), all threads; result in every thread
@@ -460,6 +494,7 @@ __device__ void block_header(Shared& S, BitCursor& bc, const MemberDesc& md, boo
     } else if (!status) {
         status = FB200_INVALID_BLOCK_TYPE;  // inflate.zig:267
     }
+    if (!status && btype != 0 && lane < 2) span_long_tables(T, lane, lane ? T.dist_count : T.lit_count);
     if (lane == 0) {
         S.c.status = status;
         S.c.bfinal = bfinal;
@@ -548,7 +583,7 @@ __device__ void fast_round(Shared& S, const Window& W, const MemberDesc& md, uin
         em.ring_mask = kRing - 1;
         em.slot0 = (uint32_t)(pos0 + W.A) + eb;
         em.rel0 = eb;
-        em.queue = S.queue;
+        em.queue = W.queue;
         em.q0 = em_;
         const uint64_t reach = md.hist + pos0 + eb;
         em.reach = (uint32_t)min(reach, (uint64_t)0xffff0000u);
@@ -577,24 +612,20 @@ __device__ void fast_round(Shared& S, const Window& W, const MemberDesc& md, uin
     __syncthreads();
 
     // 5. resolution
-    resolve_matches(S, W, S.c.tot_m, pos0);
+    resolve_matches(S, W, S.c.tot_m, pos0, S.c.tot_b);
 }
 
 }  // namespace par
 
 using namespace par;
 
-__global__ void __launch_bounds__(par::kLanes, 2)
-inflate_members_par_kernel(int container, const uint8_t* __restrict__ d_in, const MemberDesc* __restrict__ descs, uint32_t k,
-                           uint8_t* d_out, MemberResult* __restrict__ results) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t m = blockIdx.x;
-    if (m >= k) return;
-    Shared& S = *reinterpret_cast<Shared*>(smem_raw + kRing);
-    const MemberDesc md = descs[m];
+// one member, all threads of the CTA
+static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue, int container, const uint8_t* __restrict__ d_in,
+                                          const MemberDesc md, uint8_t* d_out, MemberResult* __restrict__ result) {
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
     Window W;
-    W.ring = smem_raw;
+    W.ring = ring;
+    W.queue = queue;
     W.out = d_out + md.out_off;
     W.A = (uint32_t)((uintptr_t)W.out & 15);
     const uint8_t* in_begin = d_in + md.in_off;
@@ -768,12 +799,35 @@ inflate_members_par_kernel(int container, const uint8_t* __restrict__ d_in, cons
         res.consumed = (uint64_t)((bc.next - (bc.cnt >> 3)) - in_begin);
         res.status = (uint32_t)status;
         res.pad = S.c.rounds | (S.c.retries << 12) | (S.c.exact_calls << 22);
-        results[m] = res;
+        *result = res;
     }
 }
 
+// Persistent CTAs: each takes the next member from a work counter until none is left, so that members of very
+// different sizes balance and the match queues (one per CTA) stay L2-resident.
+__global__ void __launch_bounds__(par::kLanes, 1)
+inflate_members_par_kernel(int container, const uint8_t* __restrict__ d_in, const MemberDesc* __restrict__ descs, uint32_t k,
+                           uint8_t* d_out, MemberResult* __restrict__ results, uint2* __restrict__ queues, uint32_t* work_counter) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Shared& S = *reinterpret_cast<Shared*>(smem_raw + kRing);
+    uint2* queue = queues + (size_t)blockIdx.x * par::kQueue;
+    for (;;) {
+        __syncthreads();  // the previous member's last reads of the control block are done
+        if (threadIdx.x == 0) S.c.member = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t m = S.c.member;
+        if (m >= k) break;
+        inflate_one_member(S, smem_raw, queue, container, d_in, descs[m], d_out, results + m);
+    }
+}
+
+size_t inflate_par_scratch_bytes(uint32_t k, int sm_count) {
+    const uint32_t grid = k < (uint32_t)sm_count ? k : (uint32_t)sm_count;
+    return 256 + (size_t)grid * par::kQueue * sizeof(uint2);
+}
+
 cudaError_t inflate_members_par(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
-                                MemberResult* d_res, cudaStream_t st) {
+                                MemberResult* d_res, void* d_scratch, int sm_count, cudaStream_t st) {
     if (k == 0) return cudaSuccess;
     static bool attr_set[64] = {};  // per device
     const size_t smem = par::kRing + sizeof(par::Shared);
@@ -783,7 +837,13 @@ cudaError_t inflate_members_par(int container, const uint8_t* d_in, const Member
         cudaFuncSetAttribute(inflate_members_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    inflate_members_par_kernel<<<k, par::kLanes, smem, st>>>(container, d_in, d_desc, k, d_out, d_res);
+    // scratch: a work counter (first 256 bytes), then one match queue per CTA
+    const uint32_t grid = k < (uint32_t)sm_count ? k : (uint32_t)sm_count;
+    uint32_t* counter = reinterpret_cast<uint32_t*>(d_scratch);
+    uint2* queues = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(d_scratch) + 256);
+    cudaError_t e = cudaMemsetAsync(counter, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    inflate_members_par_kernel<<<grid, par::kLanes, smem, st>>>(container, d_in, d_desc, k, d_out, d_res, queues, counter);
     return cudaGetLastError();
 }
 

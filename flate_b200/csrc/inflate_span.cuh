@@ -30,12 +30,28 @@ constexpr uint32_t kSpanInvalid = 0xffffffffu;
 // direct-table entry: code length (4 bits, 0 = not in the direct table) | symbol << 4 (9 bits) |
 // extra-bit count << 13 (4 bits) | base value << 17 (length or distance base; 15 bits)
 struct DecTables {
-    uint32_t lit_fast[1u << kLitFastBits];
+    uint32_t lit_fast[1u << kLitFastBits];    // the two direct tables are adjacent: one load serves both kinds of step
     uint32_t dist_fast[1u << kDistFastBits];
+    // codes longer than the direct tables, [0] literal/length, [1] distance: for length l, lim = (first + count)
+    // left-justified to 15 bits, first = first canonical code, index = symbols with shorter codes
+    uint32_t long_lim[2][16];
+    uint16_t long_first[2][16], long_index[2][16];
     uint16_t lit_count[16], dist_count[16];
     uint16_t lit_sym[288], dist_sym[32];
     uint8_t lit_lens[288], dist_lens[32];
 };
+
+// fills long_* of one alphabet from its per-length counts (one thread)
+FB_HD void span_long_tables(DecTables& T, uint32_t which, const uint16_t* count) {
+    uint32_t first = 0, index = 0;
+    for (uint32_t len = 1; len <= 15; len++) {
+        T.long_first[which][len] = (uint16_t)first;
+        T.long_index[which][len] = (uint16_t)index;
+        T.long_lim[which][len] = (first + count[len]) << (15 - len);
+        index += count[len];
+        first = (first + count[len]) << 1;
+    }
+}
 
 FB_HD uint32_t span_len_base(uint32_t code) {  // RFC 1951 3.2.5, code index 0..28
     if (code < 8) return 3 + code;
@@ -115,7 +131,9 @@ struct SpanEmit {       // emit pass: where this lane's literals and matches go
 #if defined(__CUDA_ARCH__)
 #define FB_FUNNEL_R(lo, hi, s) __funnelshift_r((lo), (hi), (s))
 #define FB_LDG32(p) __ldg(p)
+#define FB_STQ(p, v) __stcg((p), (v))
 #else
+#define FB_STQ(p, v) (*(p) = (v))
 #define FB_FUNNEL_R(lo, hi, s) ((uint32_t)(((((uint64_t)(hi)) << 32) | (lo)) >> ((s) & 31)))
 #define FB_LDG32(p) (*(p))
 #endif
@@ -126,6 +144,9 @@ struct SpanEmit {       // emit pass: where this lane's literals and matches go
 //   emit pass (EMIT = true): `bp` is a true boundary, `span_end` the end found by the count pass; literals go
 //     to the ring, matches to the queue.
 // `limit`: last bit offset at which a token may start (all loads below stay inside the member's input).
+// One loop iteration decodes ONE Huffman symbol with its extra bits -- a literal/length symbol, or the distance
+// symbol of the match whose length was decoded by the previous iteration -- so that the lanes of a warp, which
+// sit at unrelated places of the stream, execute the same instructions whatever kind of token they are in.
 template <bool EMIT>
 FB_HD void decode_span(const DecTables& T, const uint32_t* __restrict__ wb, uint32_t bp, uint32_t count_from, uint32_t span_end,
                        int32_t limit, SpanResult& r, const SpanEmit* em = nullptr) {
@@ -140,99 +161,108 @@ FB_HD void decode_span(const DecTables& T, const uint32_t* __restrict__ wb, uint
     bool counting = EMIT;
     if (EMIT) r.start = bp;
     uint32_t bytes = 0, nm = 0;
-#define FB_CONSUME(nbits)               \
-    do {                                \
-        bo += (nbits);                  \
-        if (bo >= 32) {                 \
-            bo -= 32;                   \
-            idx++;                      \
-            w0 = w1;                    \
-            w1 = w2;                    \
-            w2 = FB_LDG32(wb + idx + 2); \
-        }                               \
-    } while (0)
+    uint32_t want_dist = 0, length = 0, tok = bp;
+    uint32_t flag = kSpanDead, end = kSpanInvalid;
     for (;;) {
-        const uint32_t tok = (idx << 5) + bo;
-        if (!EMIT && !counting && tok >= count_from) {
-            counting = true;
-            r.start = tok;
-            bytes = 0;
-            nm = 0;
-        }
-        if (tok >= span_end) {  // count_from <= span_end, so counting is on here
-            r.end = tok;
-            r.flag = kSpanNone;
-            break;
-        }
-        if ((int32_t)tok > limit) {
-            if (counting) { r.end = tok; r.flag = kSpanIrreg; }
-            break;
+        if (!want_dist) {
+            tok = (idx << 5) + bo;
+            if (!EMIT && !counting && tok >= count_from) {
+                counting = true;
+                r.start = tok;
+                bytes = 0;
+                nm = 0;
+            }
+            if (tok >= span_end) {  // count_from <= span_end, so counting is on here
+                end = tok;
+                flag = kSpanNone;
+                break;
+            }
+            if ((int32_t)tok > limit) {
+                end = tok;
+                flag = kSpanIrreg;
+                break;
+            }
         }
         const uint32_t win = FB_FUNNEL_R(w0, w1, bo);
-        uint32_t e = T.lit_fast[win & ((1u << kLitFastBits) - 1)];
+        uint32_t e = T.lit_fast[want_dist ? (1u << kLitFastBits) + (win & ((1u << kDistFastBits) - 1)) : (win & ((1u << kLitFastBits) - 1))];
         uint32_t nb = e & 15;
         if (nb == 0) {  // code longer than the direct table, or no code at all
-            uint32_t sym;
-            if (!span_slow_find(T.lit_count, T.lit_sym, win & 0x7fffu, sym, nb)) {
-                if (counting) { r.end = tok; r.flag = kSpanIrreg; }
+#if defined(__CUDA_ARCH__)
+            const uint32_t code15 = __brev(win) >> 17;
+#else
+            uint32_t code15 = 0;
+            for (int b = 0; b < 15; b++) code15 |= ((win >> b) & 1u) << (14 - b);
+#endif
+            uint32_t len = (want_dist ? kDistFastBits : kLitFastBits) + 1;
+            while (len <= 15 && code15 >= T.long_lim[want_dist][len]) len++;
+            uint32_t off = 0xffffffffu, cnt = 0;
+            if (len <= 15) {
+                off = (code15 >> (15 - len)) - T.long_first[want_dist][len];
+                cnt = (want_dist ? T.dist_count : T.lit_count)[len];
+            }
+            if (off >= cnt) {  // no code matches these bits: the exact path decides what that means
+                end = tok;
+                flag = kSpanIrreg;
                 break;
             }
-            e = span_entry(sym, nb, true);
+            const uint32_t sym = (want_dist ? T.dist_sym : T.lit_sym)[T.long_index[want_dist][len] + off];
+            e = span_entry(sym, len, !want_dist);
+            nb = len;
         }
         const uint32_t sym = (e >> 4) & 511u;
-        if (sym < 256) {
-            if (EMIT) em->ring[(em->slot0 + bytes) & em->ring_mask] = (uint8_t)sym;
-            bytes++;
-            FB_CONSUME(nb);
-            continue;
+        const uint32_t eb = (e >> 13) & 15u;
+        const uint32_t val = (e >> 17) + ((win >> nb) & ((1u << eb) - 1));
+        bo += nb + eb;  // at most 15 + 13 bits
+        if (bo >= 32) {
+            bo -= 32;
+            idx++;
+            w0 = w1;
+            w1 = w2;
+            w2 = FB_LDG32(wb + idx + 2);
         }
-        if (sym == 256) {
-            if (counting) { r.end = tok + nb; r.flag = kSpanEob; }
-            break;
-        }
-        if (sym > 285) {
-            if (counting) { r.end = tok; r.flag = kSpanIrreg; }
-            break;
-        }
-        const uint32_t leb = (e >> 13) & 15u;
-        const uint32_t length = (e >> 17) + ((win >> nb) & ((1u << leb) - 1));
-        FB_CONSUME(nb + leb);
-        const uint32_t dwin = FB_FUNNEL_R(w0, w1, bo);
-        uint32_t de = T.dist_fast[dwin & ((1u << kDistFastBits) - 1)];
-        uint32_t dnb = de & 15;
-        if (dnb == 0) {
-            uint32_t dsym;
-            if (!span_slow_find(T.dist_count, T.dist_sym, dwin & 0x7fffu, dsym, dnb)) {
-                if (counting) { r.end = tok; r.flag = kSpanIrreg; }
+        if (!want_dist) {
+            if (sym < 256) {
+                if (EMIT) em->ring[(em->slot0 + bytes) & em->ring_mask] = (uint8_t)sym;
+                bytes++;
+            } else if (sym == 256) {
+                end = tok + nb;
+                flag = kSpanEob;
+                break;
+            } else if (sym > 285) {
+                end = tok;
+                flag = kSpanIrreg;
+                break;
+            } else {
+                length = val;
+                want_dist = 1;
+            }
+        } else {
+            if (sym > 29) {
+                end = tok;
+                flag = kSpanIrreg;
                 break;
             }
-            de = span_entry(dsym, dnb, false);
-        }
-        if (((de >> 4) & 511u) > 29) {
-            if (counting) { r.end = tok; r.flag = kSpanIrreg; }
-            break;
-        }
-        const uint32_t deb = (de >> 13) & 15u;
-        const uint32_t distance = (de >> 17) + ((dwin >> dnb) & ((1u << deb) - 1));
-        FB_CONSUME(dnb + deb);
-        if (EMIT) {
-            if (distance > em->reach + bytes) {  // CircularBuffer.zig:45: left to the exact path
-                r.end = tok;
-                r.flag = kSpanBad;
-                break;
+            if (EMIT) {
+                if (val > em->reach + bytes) {  // CircularBuffer.zig:45: left to the exact path
+                    end = tok;
+                    flag = kSpanBad;
+                    break;
+                }
+                FB_STQ(em->queue + em->q0 + nm, make_uint2(em->rel0 + bytes, (length << 16) | (val - 1)));
             }
-            em->queue[em->q0 + nm] = make_uint2(em->rel0 + bytes, (length << 16) | (distance - 1));
+            bytes += length;
+            nm++;
+            want_dist = 0;
         }
-        bytes += length;
-        nm++;
     }
-#undef FB_CONSUME
-    if (!counting) {
+    if (!counting) {  // an irregular token (or the end of the block) while still falling into step
         r.start = kSpanInvalid;
-        r.flag = kSpanDead;
+        return;
     }
-    r.bytes = counting ? bytes : 0;
-    r.nm = counting ? nm : 0;
+    r.end = end;
+    r.flag = flag;
+    r.bytes = bytes;
+    r.nm = nm;
 }
 
 }  // namespace fb

@@ -118,6 +118,8 @@ int main(int argc, char** argv) {
             }
             build_tables(T, ll, hlit, true);
             build_tables(T, ll + hlit, hdist, false);
+            span_long_tables(T, 0, T.lit_count);
+            span_long_tables(T, 1, T.dist_count);
             // ---- the block's body: rounds ----
             uint64_t cur = br.pos;
             bool done = false;
