@@ -65,6 +65,8 @@ struct Shared {
     uint32_t l_start[kLanes], l_end[kLanes], l_flag[kLanes];
     uint32_t w_a[kWarps], w_b[kWarps], w_c[kWarps];
     uint32_t pend[(kBudget + 31) / 32 + 1];  // pending-byte bitmap of the round being resolved
+    uint32_t cg_fast[128];                   // direct table of the code-length code (7 bits)
+    uint32_t cnt32[16], offs32[16];          // build_decoder_warp scratch
     uint32_t crc_tab[256];
     Ctrl c;
 };
@@ -383,6 +385,82 @@ __device__ void exact_tokens(Shared& S, const Window& W, BitCursor& bc, const Me
     }
 }
 
+// huffman_decoder.zig:126-153 checkCompletnes + canonical tables, warp-parallel: per-length counts with shared-memory
+// atomics, the validation on one lane (15 steps), then a stable counting sort of the symbols 32 at a time
+// (__match_any_sync ranks the lanes that share a code length).  Returns the status (uniform).  Same validation order
+// as build_decoder (inflate_dev.cuh): MissingEndOfBlockCode, Oversubscribed, Incomplete.
+__device__ int build_decoder_warp(Shared& S, const uint8_t* lens, uint32_t n, bool is_lit, uint32_t max_code_bits, uint16_t* count,
+                                  uint16_t* symbol, uint32_t* fast, uint32_t fast_bits) {
+    const uint32_t lane = threadIdx.x & 31;
+    int status = FB200_OK;
+    uint32_t* cnt32 = S.cnt32;
+    uint32_t* offs = S.offs32;
+    if (lane < 16) cnt32[lane] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t l = lens[i];
+        if (l) atomicAdd(cnt32 + l, 1u);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (is_lit && lens[256] == 0) status = FB200_MISSING_END_OF_BLOCK_CODE;  // :127-128
+        if (status == FB200_OK) {
+            uint32_t mx = 0;
+            for (uint32_t len = 1; len < 16; len++)
+                if (cnt32[len]) mx = len;
+            if (mx != 0) {
+                int left = 1;
+                for (uint32_t len = 1; len <= max_code_bits; len++) {
+                    left <<= 1;
+                    if ((int)cnt32[len] > left) { status = FB200_OVERSUBSCRIBED_HUFFMAN_TREE; break; }
+                    left -= (int)cnt32[len];
+                }
+                if (status == FB200_OK && left > 0) {
+                    // incomplete is tolerated only for a single one-bit code in the literal and distance alphabets
+                    if (!(max_code_bits > 7 && mx == cnt32[1])) status = FB200_INCOMPLETE_HUFFMAN_TREE;  // :148-151
+                }
+            }
+            count[0] = 0;
+            offs[0] = 0;
+            offs[1] = 0;
+            for (uint32_t len = 1; len < 16; len++) {
+                count[len] = (uint16_t)cnt32[len];
+                if (len < 15) offs[len + 1] = offs[len] + cnt32[len];
+            }
+        }
+    }
+    __syncwarp();
+    status = __shfl_sync(0xffffffffu, status, 0);
+    if (status != FB200_OK) return status;
+    for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+        const uint32_t i = c0 + lane;
+        const uint32_t l = i < n ? lens[i] : 0;
+        const uint32_t same = __match_any_sync(0xffffffffu, l);
+        const uint32_t rank = __popc(same & ((1u << lane) - 1));
+        if (l) symbol[offs[l] + rank] = (uint16_t)i;
+        __syncwarp();
+        if (l && rank == 0) offs[l] += __popc(same);
+        __syncwarp();
+    }
+    if (fast == nullptr) return status;
+    for (uint32_t i = lane; i < (1u << fast_bits); i += 32) fast[i] = 0;
+    __syncwarp();
+    uint32_t code = 0, index = 0;
+    for (uint32_t len = 1; len <= fast_bits && len <= max_code_bits; len++) {
+        const uint32_t cnt = count[len];
+        // symbols symbol[index .. index+cnt) have codes code .. code+cnt-1 (MSB-first)
+        for (uint32_t k = lane; k < cnt; k += 32) {
+            const uint32_t rev = __brev(code + k) >> (32 - len);
+            const uint32_t entry = span_entry(symbol[index + k], len, is_lit);
+            for (uint32_t e = rev; e < (1u << fast_bits); e += (1u << len)) fast[e] = entry;
+        }
+        code = (code + cnt) << 1;
+        index += cnt;
+    }
+    __syncwarp();
+    return status;
+}
+
 // ---- block header, warp 0 (inflate.zig:251-268 step, :144-185 dynamicBlockHeader); leaves the tables in S.T
 __device__ void block_header(Shared& S, BitCursor& bc, const MemberDesc& md, bool& fixed_ready) {
     const uint32_t lane = threadIdx.x & 31;
@@ -432,7 +510,7 @@ __device__ void block_header(Shared& S, BitCursor& bc, const MemberDesc& md, boo
         }
         status = BCAST(status);
         // CodegenDecoder(19, 7, 7): built into dist_count / dist_sym (no fast table)
-        if (!status) status = build_decoder(T.dist_lens, 19, false, 7, T.dist_count, T.dist_sym, nullptr, 0);
+        if (!status) status = build_decoder_warp(S, T.dist_lens, 19, false, 7, T.dist_count, T.dist_sym, S.cg_fast, 7);
         if (!status) {
             if (lane == 0) {
                 // two passes: literal lengths then distance lengths (inflate.zig:161-180)
@@ -446,9 +524,9 @@ __device__ void block_header(Shared& S, BitCursor& bc, const MemberDesc& md, boo
                     uint32_t p = 0;
                     while (p < want && !status) {
                         if (bc.empty()) { status = FB200_END_OF_STREAM; break; }  // peekF(u7): fill(7)
-                        uint32_t sym = 0, nb = 0;
-                        status = slow_find(T.dist_count, T.dist_sym, 7, bc.peek(7), sym, nb);
-                        if (status) break;
+                        const uint32_t ce = S.cg_fast[bc.peek(7)];  // every code of the 7-bit alphabet is in the direct table
+                        const uint32_t sym = (ce >> 4) & 511u, nb = ce & 15;
+                        if (nb == 0) { status = FB200_INVALID_CODE; break; }
                         if (!bc.shift(nb)) { status = FB200_END_OF_STREAM; break; }
                         if (p >= lens_len) { status = FB200_INVALID_DYNAMIC_BLOCK_HEADER; break; }  // inflate.zig:189-216
                         uint32_t v = 0;
@@ -479,16 +557,16 @@ __device__ void block_header(Shared& S, BitCursor& bc, const MemberDesc& md, boo
             status = BCAST(status);
             __syncwarp();
         }
-        if (!status) status = build_decoder(T.lit_lens, kNumLit, true, 15, T.lit_count, T.lit_sym, T.lit_fast, kLitFast);
-        if (!status) status = build_decoder(T.dist_lens, kNumDist, false, 15, T.dist_count, T.dist_sym, T.dist_fast, kDistFast);
+        if (!status) status = build_decoder_warp(S, T.lit_lens, kNumLit, true, 15, T.lit_count, T.lit_sym, T.lit_fast, kLitFast);
+        if (!status) status = build_decoder_warp(S, T.dist_lens, kNumDist, false, 15, T.dist_count, T.dist_sym, T.dist_fast, kDistFast);
     } else if (!status && btype == 1) {
         if (!fixed_ready) {
             // fixed block: the reference decodes by arithmetic (bit_reader.zig:205-217); the same symbols come out of
             // the canonical code with lengths 8/9/7/8 over 288 symbols and 32 five-bit distance codes.  286/287 and
             // 30/31 decode and are then rejected (inflate.zig:111,136).
             build_fixed_lens(T.lit_lens, T.dist_lens);
-            status = build_decoder(T.lit_lens, 288, true, 15, T.lit_count, T.lit_sym, T.lit_fast, kLitFast);
-            if (!status) status = build_decoder(T.dist_lens, 32, false, 15, T.dist_count, T.dist_sym, T.dist_fast, kDistFast);
+            status = build_decoder_warp(S, T.lit_lens, 288, true, 15, T.lit_count, T.lit_sym, T.lit_fast, kLitFast);
+            if (!status) status = build_decoder_warp(S, T.dist_lens, 32, false, 15, T.dist_count, T.dist_sym, T.dist_fast, kDistFast);
             fixed_ready = !status;
         }
     } else if (!status) {
