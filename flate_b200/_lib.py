@@ -36,6 +36,10 @@ SIGNATURES = {
     "fb200_shard_overlap": (_SZ, []),
     "fb200_deflate_shard_search": (_I, [_P, _I, _P, _SZ, _SZ, _SZ, _P, _P]),
     "fb200_deflate_shard_finish": (_I, [_P, _I, _I, _P, _SZ, _P, _P, _SZ, _SZP, _P]),
+    "fb200_simple_shard_plan": (_I, [_P, _I, _I, _P, _SZ, _I, _P, _P, _P, _P, _P]),
+    "fb200_simple_shard_pack": (_I, [_P, C.c_uint64, _P, _SZ, _P, _P, _P, _P]),
+    "fb200_crc32_combine": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint64]),
+    "fb200_adler32_combine": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint64]),
     "fb200_deflate_create": (_I, [_P, _I, _I, WRITE_FN, _P, C.POINTER(_P)]),
     "fb200_deflate_write": (_I, [_P, _P, _SZ]),
     "fb200_deflate_flush": (_I, [_P]),

@@ -187,6 +187,27 @@ class Context:
                                                    stream))
         return out_len.value
 
+    # ---- huffman-only / store stream sharded by 65535-byte block ranges over several GPUs ----
+    def simple_shard_plan(self, d_in, shard_bytes, is_last, mode=HUFFMAN, container=RAW, stream=None):
+        """Stage 1: returns (pre_bits, has_stored, post_bits, checksum) of this rank's range of slices."""
+        pre, post, has, sm = C.c_uint64(0), C.c_uint64(0), C.c_int(0), C.c_uint32(0)
+        _check(self.lib.fb200_simple_shard_plan(self.h, container, mode, d_in, shard_bytes, int(bool(is_last)), C.byref(pre),
+                                                C.byref(has), C.byref(post), C.byref(sm), stream))
+        return pre.value, has.value, post.value, sm.value
+
+    def simple_shard_pack(self, start_bit, d_out, cap, stream=None):
+        """Stage 2: packs the planned shard at its stream bit offset.  Returns (byte_lo, nbytes, end_bit): d_out[0:nbytes]
+        are the stream's bytes from byte_lo on, zero before start_bit."""
+        lo, nb, end = C.c_uint64(0), C.c_size_t(0), C.c_uint64(0)
+        _check(self.lib.fb200_simple_shard_pack(self.h, start_bit, d_out, cap, C.byref(lo), C.byref(nb), C.byref(end), stream))
+        return lo.value, nb.value, end.value
+
+    def crc32_combine(self, crc1, crc2, len2):
+        return int(self.lib.fb200_crc32_combine(crc1, crc2, len2))
+
+    def adler32_combine(self, a1, a2, len2):
+        return int(self.lib.fb200_adler32_combine(a1, a2, len2))
+
     # ---- test seams ----
     def debug_tokens(self, data, level=Level.default):
         a = _as_u8(data)

@@ -514,6 +514,10 @@ __global__ void scan_block_offsets_kernel(BlockDesc* __restrict__ descs, const u
 #pragma unroll
     for (uint32_t i = 0; i + 1 < kPackParts; i++) mark[i] = (uint32_t)(((uint64_t)nb * (i + 1)) / kPackParts);
     uint64_t off = start_bits;
+    // shard summary (block-range sharded streams): bits up to and including the 3 header bits of the first stored
+    // block, and the bits from the byte boundary that block aligns to up to the end; total_bits[16..18]
+    uint64_t pre = 0, aligned_at = 0;
+    bool seen_stored = false;
     for (uint32_t base = 0; base < nb; base += 32) {
         const uint32_t b = base + lane;
         uint32_t type = kFixed, in_len = 0;
@@ -531,6 +535,11 @@ __global__ void scan_block_offsets_kernel(BlockDesc* __restrict__ descs, const u
             const uint64_t bits_j = __shfl_sync(0xffffffffu, (unsigned long long)bits, j);
             if (j == lane) my_off = off;
             if (t == kStored) {
+                if (!seen_stored) {
+                    seen_stored = true;
+                    pre = off + 3 - start_bits;
+                    aligned_at = (off + 3 + 7) & ~(uint64_t)7;
+                }
                 off = (off + 3 + 7) & ~(uint64_t)7;
                 off += 32 + 8ull * len_j;
             } else {
@@ -547,6 +556,9 @@ __global__ void scan_block_offsets_kernel(BlockDesc* __restrict__ descs, const u
     if (lane == 0) {
         total_bits[0] = off;
         total_bits[1] = nb;
+        total_bits[16] = seen_stored ? pre : off - start_bits;
+        total_bits[17] = seen_stored ? 1 : 0;
+        total_bits[18] = seen_stored ? off - aligned_at : 0;
     }
 }
 

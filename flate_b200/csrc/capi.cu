@@ -24,6 +24,8 @@ __global__ void plan_simple_blocks_kernel(uint64_t begin, uint64_t end, uint32_t
                                           BlockPlan* __restrict__ plans, uint32_t* __restrict__ nblocks_dev) {
     // SimpleCompressor (deflate.zig:449-529): the segment is cut into 65535-byte slices, the last
     // (possibly empty) one closes the segment; a sync flush appends an empty stored block (:474-478).
+    // final_flush: 0 = sync flush, 1 = finish, 2 = a shard in the middle of a block-range sharded stream
+    // (whole slices only, neither BFINAL nor a marker)
     const uint32_t total = nblocks + (final_flush ? 0 : 1);
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) *nblocks_dev = total;
@@ -36,7 +38,7 @@ __global__ void plan_simple_blocks_kernel(uint64_t begin, uint64_t end, uint32_t
         pl.in_begin = begin + (uint64_t)b * kMaxStore;  // deflate.zig:456: 65535-byte slices
         const uint64_t rem = end - pl.in_begin;
         pl.in_len = (uint32_t)(rem < kMaxStore ? rem : kMaxStore);
-        pl.eof = (b + 1 == nblocks) && final_flush;
+        pl.eof = (b + 1 == nblocks) && final_flush == 1;
         pl.kind = kind;
     } else {
         pl.in_begin = 0;
@@ -112,6 +114,9 @@ struct fb200_ctx {
     DevBuf<uint64_t> m_desc;        // member descriptors / results
     DevBuf<uint8_t> m_scratch;      // work counter + per-CTA match queues of the member-parallel inflate kernel
     int sm_count = 148;
+    // block-range sharded simple stream: state between the plan and the pack stage
+    const uint8_t* shard_in = nullptr;
+    uint32_t shard_blocks = 0;
     std::vector<uint64_t> h_members;
 };
 
@@ -658,6 +663,133 @@ int fb200_deflate_shard_finish(fb200_ctx* c, int container, int level, const voi
     if (flen) FB_CUDA_CHECK(cudaStreamSynchronize(st));
     *out_len = end + flen;
     return FB200_OK;
+}
+
+// ---- huffman-only / store stream sharded by 65535-byte block ranges ----
+int fb200_simple_shard_plan(fb200_ctx* c, int container, int mode, const void* d_in, size_t shard_bytes, int is_last,
+                            uint64_t* pre_bits, int* has_stored, uint64_t* post_bits, uint32_t* checksum, void* stream) {
+    if (!c || (mode != FB200_MODE_HUFFMAN && mode != FB200_MODE_STORE) || container < 0 || container > 2 || (!d_in && shard_bytes) ||
+        !pre_bits || !has_stored || !post_bits)
+        return FB200_INVALID_ARGUMENT;
+    if (!is_last && (shard_bytes == 0 || shard_bytes % kMaxStore != 0)) return FB200_INVALID_ARGUMENT;  // whole slices only
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const uint64_t nb64 = shard_bytes / kMaxStore + (is_last ? 1 : 0);  // deflate.zig:456: the last slice may be empty
+    if (nb64 == 0 || nb64 > 0x7ffffff0ull) return FB200_INVALID_ARGUMENT;
+    const uint32_t nslices = (uint32_t)nb64;
+    int rc = ensure_blocks(c, nslices);
+    if (rc) return rc;
+    uint32_t* nblocks_dev = c->d_scalars + 1;
+    uint64_t* total_bits_dev = reinterpret_cast<uint64_t*>(c->d_scalars + 2);
+    c->timer.begin(st);
+    plan_simple_blocks_kernel<<<(nslices + 255) / 256, 256, 0, st>>>(0, shard_bytes, nslices, mode == FB200_MODE_HUFFMAN ? kHuffmanBlock : 3u,
+                                                                     is_last ? 1 : 2, c->plans.p, nblocks_dev);
+    FB_CUDA_CHECK(cudaGetLastError());
+    c->launches += 1;
+    if (mode == FB200_MODE_HUFFMAN) {
+        FB_CUDA_CHECK(histogram_bytes((const uint8_t*)d_in, c->plans.p, nslices, c->lit_freq.p, st));
+        c->launches += 1;
+        c->timer.mark(st, kPhHist);
+    }
+    FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, nslices, c->lit_freq.p, c->dist_freq.p, c->descs.p, st));
+    c->timer.mark(st, kPhBuild);
+    FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, 0, total_bits_dev, st));
+    c->launches += 2;
+    uint32_t* sum_dev = c->d_scalars + 16;
+    if (container == FB200_GZIP) {
+        FB_CUDA_CHECK(crc32_device((const uint8_t*)d_in, shard_bytes, sum_dev, st));
+        c->launches += shard_bytes ? 1 : 0;
+    } else if (container == FB200_ZLIB) {
+        FB_CUDA_CHECK(adler32_device((const uint8_t*)d_in, shard_bytes, sum_dev, reinterpret_cast<uint64_t*>(c->d_scalars + 24), st));
+        c->launches += shard_bytes ? 2 : 1;
+    }
+    uint64_t summary[3] = {0, 0, 0};
+    uint32_t sum = 0;
+    FB_CUDA_CHECK(cudaMemcpyAsync(summary, total_bits_dev + 16, sizeof summary, cudaMemcpyDeviceToHost, st));
+    if (container != FB200_RAW) FB_CUDA_CHECK(cudaMemcpyAsync(&sum, sum_dev, 4, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    c->timer.collect();
+    *pre_bits = summary[0];
+    *has_stored = (int)summary[1];
+    *post_bits = summary[2];
+    if (checksum) *checksum = sum;
+    c->shard_in = (const uint8_t*)d_in;
+    c->shard_blocks = nslices;
+    return FB200_OK;
+}
+
+int fb200_simple_shard_pack(fb200_ctx* c, uint64_t start_bit, void* d_out, size_t cap, uint64_t* byte_lo, size_t* nbytes,
+                            uint64_t* end_bit, void* stream) {
+    if (!c || !d_out || !byte_lo || !nbytes || !end_bit || c->shard_blocks == 0 || ((uintptr_t)d_out & 15) != 0) return FB200_INVALID_ARGUMENT;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const uint64_t lo = (start_bit >> 3) & ~15ull;  // stream byte held by d_out[0]; 16-byte steps keep word alignment
+    const uint64_t local_start = start_bit - 8 * lo;
+    uint32_t* nblocks_dev = c->d_scalars + 1;
+    uint64_t* total_bits_dev = reinterpret_cast<uint64_t*>(c->d_scalars + 2);
+    c->timer.begin(st);
+    FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, local_start, total_bits_dev, st));
+    zero_output_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<uint32_t*>(d_out), total_bits_dev, cap / 4);
+    FB_CUDA_CHECK(cudaGetLastError());
+    c->timer.mark(st, kPhOffsets);
+    // the size is known from the plan stage only up to the alignment of the first stored block: check the capacity
+    // against the scan's result before packing
+    uint64_t total_bits = 0;
+    FB_CUDA_CHECK(cudaMemcpyAsync(&total_bits, total_bits_dev, 8, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (((total_bits + 31) >> 5) * 4 + 8 > cap) return FB200_NO_SPACE_LEFT;
+    FB_CUDA_CHECK(pack_blocks(c->shard_in, nullptr, c->descs.p, nblocks_dev, c->shard_blocks, reinterpret_cast<uint32_t*>(d_out), st));
+    c->timer.mark(st, kPhPack);
+    c->launches += 3;
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    c->timer.collect();
+    *byte_lo = lo;
+    *nbytes = (size_t)((total_bits + 7) >> 3);
+    *end_bit = 8 * lo + total_bits;
+    return FB200_OK;
+}
+
+// zlib's crc32_combine / adler32_combine: checksum of A||B from the checksums of A and B and the length of B
+static uint32_t gf2_times(const uint32_t* mat, uint32_t vec) {
+    uint32_t sum = 0;
+    for (int i = 0; vec; vec >>= 1, i++)
+        if (vec & 1) sum ^= mat[i];
+    return sum;
+}
+static void gf2_square(uint32_t* sq, const uint32_t* mat) {
+    for (int n = 0; n < 32; n++) sq[n] = gf2_times(mat, mat[n]);
+}
+uint32_t fb200_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+    if (len2 == 0) return crc1;
+    uint32_t even[32], odd[32];
+    odd[0] = 0xEDB88320u;  // one zero bit
+    uint32_t row = 1;
+    for (int n = 1; n < 32; n++) { odd[n] = row; row <<= 1; }
+    gf2_square(even, odd);  // two zero bits
+    gf2_square(odd, even);  // four
+    do {
+        gf2_square(even, odd);
+        if (len2 & 1) crc1 = gf2_times(even, crc1);
+        len2 >>= 1;
+        if (len2 == 0) break;
+        gf2_square(odd, even);
+        if (len2 & 1) crc1 = gf2_times(odd, crc1);
+        len2 >>= 1;
+    } while (len2 != 0);
+    return crc1 ^ crc2;
+}
+uint32_t fb200_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2) {
+    const uint32_t BASE = 65521;
+    const uint32_t rem = (uint32_t)(len2 % BASE);
+    uint32_t sum1 = adler1 & 0xffff;
+    uint32_t sum2 = (uint32_t)(((uint64_t)rem * sum1) % BASE);
+    sum1 += (adler2 & 0xffff) + BASE - 1;
+    sum2 += ((adler1 >> 16) & 0xffff) + ((adler2 >> 16) & 0xffff) + BASE - rem;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum1 >= BASE) sum1 -= BASE;
+    if (sum2 >= (BASE << 1)) sum2 -= (BASE << 1);
+    if (sum2 >= BASE) sum2 -= BASE;
+    return sum1 | (sum2 << 16);
 }
 
 // ---- test seams ----

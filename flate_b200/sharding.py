@@ -109,3 +109,111 @@ def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0, k
     cap = d_out.numel()
     return ctx.shard_finish(d_in.data_ptr(), n, nx.data_ptr(), d_out.data_ptr(), cap, level=level, container=container,
                             stream=sp)
+
+
+# ---- huffman-only / store: ONE stream sharded by 65535-byte block ranges ----
+SLICE = 65535  # deflate.zig:456
+
+
+def simple_shard_ranges(n, world):
+    """Byte range [lo, hi) of the stream for every rank: contiguous ranges of whole 65535-byte slices; the stream
+    has n // 65535 + 1 slices (the last one may be empty, deflate.zig:449-511) and the final one goes to the last rank."""
+    nblocks = n // SLICE + 1
+    out = []
+    for r in range(world):
+        lo, hi = shard_range(nblocks - 1, r, world)   # the final slice is dealt separately
+        out.append((lo * SLICE, hi * SLICE))
+    out[-1] = (out[-1][0], n)
+    return out
+
+
+def shard_start_bits(summaries, start_bit):
+    """Exclusive scan of the shard size summaries (pre_bits, has_stored, post_bits): a shard placed at bit x ends at
+    align8(x + pre) + post when it holds a stored block (block_writer.zig:283-291 re-aligns), else at x + pre.
+    Returns (start bit of every shard, end bit of the stream)."""
+    x, starts = int(start_bit), []
+    for pre, has, post in summaries:
+        starts.append(x)
+        x = ((x + int(pre) + 7) & ~7) + int(post) if has else x + int(pre)
+    return starts, x
+
+
+def assemble_shards(final, gathered, pad, placements):
+    """OR-merge of the gathered shard buffers into the stream: rank r's buffer holds the stream's bytes from
+    byte_lo[r] on, zero before its first bit, so only the (at most 17) bytes shared with its predecessor need the OR."""
+    for r, (lo, nbytes) in enumerate(placements):
+        if nbytes == 0:
+            continue
+        src = gathered[r * pad: r * pad + nbytes]
+        k = min(nbytes, 17)
+        final[lo: lo + k] |= src[:k]
+        if nbytes > k:
+            final[lo + k: lo + nbytes] = src[k:]
+    return final
+
+
+_HEADERS = {0: b"", 1: bytes([0x1f, 0x8b, 0x08, 0, 0, 0, 0, 0, 0, 0x03]), 2: bytes([0x78, 0x9c])}  # container.zig:64,78
+
+
+def compress_simple_sharded(ctx, d_shard, lo, hi, n, mode=1, container=0, local=None):
+    """One huffman-only (mode 1) or store (mode 0) stream of n bytes compressed by all ranks together: this rank holds
+    the stream's bytes [lo, hi) (its range from simple_shard_ranges) in the uint8 tensor d_shard.  Every rank ends up
+    with the whole compressed stream (all-gather of the per-shard outputs).  Returns (stream tensor, length).
+    Byte-identical with Context.compress_device on the whole stream."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dev = d_shard.device
+    cur = torch.cuda.current_stream() if d_shard.is_cuda else _NoStream()
+    sp = cur.cuda_stream
+    cur.synchronize()
+    is_last = rank == world - 1
+    nbytes_in = hi - lo
+    if nbytes_in or is_last:
+        pre, has, post, sm = ctx.simple_shard_plan(d_shard.data_ptr(), nbytes_in, is_last, mode=mode, container=container, stream=sp)
+    else:
+        pre, has, post, sm = 0, 0, 0, (1 if container == 2 else 0)   # empty range: nothing to emit (Adler-32 of nothing is 1)
+    mine = torch.tensor([pre, has, post, sm, nbytes_in], dtype=torch.int64, device=dev)
+    if world > 1:
+        allm = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        allm = [t.tolist() for t in allm]
+    else:
+        allm = [mine.tolist()]
+    header = _HEADERS[container]
+    starts, end_bit = shard_start_bits([(a[0], a[1], a[2]) for a in allm], 8 * len(header))
+    cap = (nbytes_in + nbytes_in // 8 + 1024 + 15) // 16 * 16
+    if local is None or local.numel() < cap:
+        local = torch.empty(cap, dtype=torch.uint8, device=dev)
+    if nbytes_in or is_last:
+        byte_lo, nb, _ = ctx.simple_shard_pack(starts[rank], local.data_ptr(), local.numel(), stream=sp)
+    else:
+        byte_lo, nb = starts[rank] >> 3, 0
+    place = torch.tensor([byte_lo, nb], dtype=torch.int64, device=dev)
+    if world > 1:
+        allp = [torch.zeros_like(place) for _ in range(world)]
+        dist.all_gather(allp, place)
+        placements = [tuple(t.tolist()) for t in allp]
+        pad = (max(p[1] for p in placements) + 255) // 256 * 256
+        if local.numel() < pad:
+            bigger = torch.zeros(pad, dtype=torch.uint8, device=dev)
+            bigger[:nb] = local[:nb]
+            local = bigger
+        gathered = torch.empty(world * pad, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, local[:pad])
+    else:
+        placements, pad, gathered = [(byte_lo, nb)], nb, local
+    body_end = (end_bit + 7) >> 3
+    footer = b""
+    if container:
+        total = allm[0][3]
+        for a in allm[1:]:
+            total = ctx.crc32_combine(total, a[3], a[4]) if container == 1 else ctx.adler32_combine(total, a[3], a[4])
+        footer = (int(total).to_bytes(4, "little") + int(n & 0xffffffff).to_bytes(4, "little")) if container == 1 \
+            else int(total).to_bytes(4, "big")
+    final = torch.zeros(body_end + len(footer), dtype=torch.uint8, device=dev)
+    if header:
+        final[: len(header)] = torch.frombuffer(bytearray(header), dtype=torch.uint8).to(dev)
+    assemble_shards(final, gathered, pad, placements)
+    if footer:
+        final[body_end:] = torch.frombuffer(bytearray(footer), dtype=torch.uint8).to(dev)
+    return final, body_end + len(footer)

@@ -141,6 +141,30 @@ int fb200_deflate_shard_search(fb200_ctx* ctx, int level, const void* d_in, size
 int fb200_deflate_shard_finish(fb200_ctx* ctx, int container, int level, const void* d_in, size_t n, const void* d_nx,
                                void* d_out, size_t cap, size_t* out_len, void* stream);
 
+/* ---- huffman-only / store stream sharded by 65535-byte block ranges over several GPUs ----
+ * The blocks of SimpleCompressor (deflate.zig:449-529) are the 65535-byte slices of the stream and do not depend on
+ * each other; only their bit offsets do.  Every rank takes a contiguous range of whole slices (is_last = 0; shard_bytes
+ * a multiple of 65535) and the last rank the rest, which ends with the stream's final, possibly empty, slice.
+ *   stage 1, fb200_simple_shard_plan: histograms, codes and block sizes of the shard's slices; returns the shard's
+ *     size summary: placed at stream bit x the shard ends at bit
+ *         has_stored ? ((x + pre_bits + 7) & ~7) + post_bits : x + pre_bits
+ *     (a stored block re-aligns to a byte boundary, block_writer.zig:283-291), and with container != raw the
+ *     CRC-32 / Adler-32 of the shard's plain bytes (join them with fb200_crc32_combine / fb200_adler32_combine).
+ *   exchange: an exclusive scan of the summaries over the ranks (the container header's bits first) gives every
+ *     shard's start bit.
+ *   stage 2, fb200_simple_shard_pack: packs the shard at its start bit into d_out (16-byte aligned, device), whose
+ *     byte 0 is stream byte *byte_lo = (start_bit / 8) & ~15; bits before start_bit are zero, so the stream is the OR
+ *     of the shards' bytes: a shard overlaps its predecessor in at most 17 bytes.  cap >= shard_bytes + shard_bytes / 8
+ *     + 1024 always suffices.
+ * Byte-identical with fb200_compress_device on the whole stream.  Replaces deflate.zig:449-529 for one large
+ * huffman-only / store stream. */
+int fb200_simple_shard_plan(fb200_ctx* ctx, int container, int mode, const void* d_in, size_t shard_bytes, int is_last,
+                            uint64_t* pre_bits, int* has_stored, uint64_t* post_bits, uint32_t* checksum, void* stream);
+int fb200_simple_shard_pack(fb200_ctx* ctx, uint64_t start_bit, void* d_out, size_t cap, uint64_t* byte_lo, size_t* nbytes,
+                            uint64_t* end_bit, void* stream);
+uint32_t fb200_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+uint32_t fb200_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2);
+
 /* ---- streaming compressor (Compressor / SimpleCompressor) ---- */
 typedef struct fb200_deflate fb200_deflate;
 typedef int (*fb200_write_fn)(void* user, const uint8_t* data, size_t len); /* the `writer`; non-zero = error */

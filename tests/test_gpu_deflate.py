@@ -476,3 +476,55 @@ def test_dense_mode_tokens_equal_oracle(o):
                 assert got.size == want.size and (got == want).all(), (n, level)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_block_range_sharded_stream_equals_whole(ctx, o, mode):
+    """a huffman-only / store stream cut into ranges of 65535-byte slices, every range planned and
+    packed on its own ("ranks" run one after the other on this GPU), joined by the exclusive scan of the shard size
+    summaries and an OR of the boundary bytes: byte-identical with the oracle's stream (deflate.zig:449-529)."""
+    import torch
+    from flate_b200 import sharding, synth
+    sizes = [0, 1, 65534, 65535, 65536, 131070, 200000, 1500000]
+    for n in sizes:
+        data = synth.random_zero_mix(n, seed=0x5EED0005 + n) if n else np.zeros(0, dtype=np.uint8)
+        if n > 300000:   # text in the middle: dynamic blocks of every size between stored ones
+            data[400000:900000] = synth.enwik_like(500000, seed=9)
+        for container in (0, 1, 2):
+            want = o.compress(data.tobytes(), container, mode)
+            for world in (1, 2, 3, 5, 8):
+                ranges = sharding.simple_shard_ranges(n, world)
+                d_in = torch.from_numpy(data.copy()).cuda() if n else torch.zeros(16, dtype=torch.uint8, device="cuda")
+                plans = []
+                for r, (lo, hi) in enumerate(ranges):
+                    last = r == world - 1
+                    if hi > lo or last:
+                        plans.append(ctx.simple_shard_plan(d_in.data_ptr() + lo, hi - lo, last, mode=mode, container=container))
+                    else:
+                        plans.append((0, 0, 0, 1 if container == 2 else 0))
+                header = sharding._HEADERS[container]
+                starts, end_bit = sharding.shard_start_bits([p[:3] for p in plans], 8 * len(header))
+                pad = max(hi - lo for lo, hi in ranges)
+                pad = (pad + pad // 8 + 1024 + 255) // 256 * 256
+                gathered = torch.zeros(world * pad, dtype=torch.uint8, device="cuda")
+                placements = []
+                for r, (lo, hi) in enumerate(ranges):
+                    last = r == world - 1
+                    if hi > lo or last:
+                        ctx.simple_shard_plan(d_in.data_ptr() + lo, hi - lo, last, mode=mode, container=container)
+                        blo, nb, _ = ctx.simple_shard_pack(starts[r], gathered.data_ptr() + r * pad, pad)
+                        placements.append((blo, nb))
+                    else:
+                        placements.append((starts[r] >> 3, 0))
+                body_end = (end_bit + 7) >> 3
+                final = torch.zeros(body_end, dtype=torch.uint8, device="cuda")
+                if header:
+                    final[: len(header)] = torch.frombuffer(bytearray(header), dtype=torch.uint8).cuda()
+                sharding.assemble_shards(final, gathered, pad, placements)
+                total = plans[0][3]
+                for p, (lo, hi) in zip(plans[1:], ranges[1:]):
+                    total = ctx.crc32_combine(total, p[3], hi - lo) if container == 1 else ctx.adler32_combine(total, p[3], hi - lo)
+                footer = b"" if container == 0 else (
+                    total.to_bytes(4, "little") + (n & 0xffffffff).to_bytes(4, "little") if container == 1 else total.to_bytes(4, "big"))
+                got = final.cpu().numpy().tobytes() + footer
+                assert got == want, (n, container, world, first_diff(got, want))
