@@ -90,6 +90,7 @@ struct fb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // host-to-device slabs, overlapped with the search of earlier slabs
+    cudaStream_t copy_stream2 = nullptr;  // device-to-host copies of finished inflate batches
     cudaEvent_t slab_ev[16] = {};
     uint64_t launches = 0;
     PhaseTimer timer;
@@ -179,6 +180,7 @@ int fb200_ctx_create(int device, fb200_ctx** out) {
     if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count <= 0) c->sm_count = 148;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking);
     for (auto& ev : c->slab_ev)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_scalars, 256);
@@ -207,6 +209,7 @@ void fb200_ctx_destroy(fb200_ctx* c) {
     for (auto& e : c->slab_ev)
         if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->copy_stream2) cudaStreamDestroy(c->copy_stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -957,24 +960,69 @@ int fb200_decompress_members_device(fb200_ctx* c, int container, const void* d_i
 int fb200_decompress_members(fb200_ctx* c, int container, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len,
                              size_t k, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
                              uint64_t* consumed, int* status) {
-    if (!c || (k && (!in || !out || !in_off || !in_len || !out_off || !out_cap || !out_len))) return FB200_INVALID_ARGUMENT;
+    if (!c || container < 0 || container > 2 || k > 0x7fffffffu || (k && (!in || !out || !in_off || !in_len || !out_off || !out_cap || !out_len)))
+        return FB200_INVALID_ARGUMENT;
+    for (size_t i = 0; i < k; i++) {  // nothing below may leave these unwritten
+        out_len[i] = 0;
+        if (consumed) consumed[i] = 0;
+        if (status) status[i] = FB200_OK;
+    }
+    if (k == 0) return FB200_OK;
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     uint64_t in_end = 0, out_end = 0;
+    bool ordered = true;  // members one after the other in both buffers: the copies can be pipelined batch by batch
     for (size_t i = 0; i < k; i++) {
         if (in_off[i] + in_len[i] > in_end) in_end = in_off[i] + in_len[i];
         if (out_off[i] + out_cap[i] > out_end) out_end = out_off[i] + out_cap[i];
+        if (i && (in_off[i] < in_off[i - 1] + in_len[i - 1] || out_off[i] < out_off[i - 1] + out_cap[i - 1])) ordered = false;
     }
     FB_CUDA_CHECK(c->d_in.ensure(in_end + 512));
     FB_CUDA_CHECK(c->d_out.ensure(out_end + 512));
     cudaStream_t st = c->stream;
-    if (in_end) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, in_end, cudaMemcpyHostToDevice, st));
-    int rc = fb200_decompress_members_device(c, container, c->d_in.p, in_off, in_len, k, c->d_out.p, out_off, out_cap,
-                                             out_len, consumed, status, st);
-    // deliver what was produced (also for failed members: the caller decides what to do with it)
-    for (size_t i = 0; i < k; i++)
-        if (out_len[i]) FB_CUDA_CHECK(cudaMemcpyAsync(out + out_off[i], c->d_out.p + out_off[i], out_len[i], cudaMemcpyDeviceToHost, st));
+    const size_t desc_words = k * (sizeof(MemberDesc) / 8), res_words = k * (sizeof(MemberResult) / 8);
+    FB_CUDA_CHECK(c->m_desc.ensure(desc_words + res_words));
+    FB_CUDA_CHECK(c->m_scratch.ensure(inflate_par_scratch_bytes((uint32_t)k, c->sm_count)));
+    MemberDesc* d_desc = reinterpret_cast<MemberDesc*>(c->m_desc.p);
+    MemberResult* d_res = reinterpret_cast<MemberResult*>(c->m_desc.p + desc_words);
+    std::vector<MemberDesc> desc(k);
+    std::vector<MemberResult> res(k);
+    for (size_t i = 0; i < k; i++) desc[i] = MemberDesc{in_off[i], in_len[i], out_off[i], out_cap[i], 0};
+    FB_CUDA_CHECK(cudaMemcpyAsync(d_desc, desc.data(), k * sizeof(MemberDesc), cudaMemcpyHostToDevice, st));
+    // Batches of members: the input of batch b+1 crosses PCIe while batch b is inflated and the output of batch b-1
+    // goes back (three streams).  A batch's output copy covers its members' whole capacity ranges: out_len is only
+    // known on the host at the end, and bytes past out_len inside out_cap belong to the caller's buffer anyway.
+    const size_t nbatch = !ordered ? 1 : k >= 64 ? 8 : k >= 8 ? 4 : 1;
+    static const bool warp_kernel = [] { const char* e = getenv("FB200_INFLATE"); return e && strcmp(e, "warp") == 0; }();
+    c->timer.begin(st);
+    for (size_t b = 0; b < nbatch; b++) {
+        const size_t m0 = k * b / nbatch, m1 = k * (b + 1) / nbatch;
+        if (m1 == m0) continue;
+        uint64_t lo = in_off[m0], hi = in_off[m1 - 1] + in_len[m1 - 1], olo = out_off[m0], ohi = out_off[m1 - 1] + out_cap[m1 - 1];
+        if (!ordered) { lo = 0; hi = in_end; olo = 0; ohi = out_end; }
+        cudaEvent_t ev_in = c->slab_ev[(2 * b) % 16], ev_k = c->slab_ev[(2 * b + 1) % 16];
+        if (hi > lo) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, c->copy_stream));
+        FB_CUDA_CHECK(cudaEventRecord(ev_in, c->copy_stream));
+        FB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_in, 0));
+        if (warp_kernel) FB_CUDA_CHECK(inflate_members(container, c->d_in.p, d_desc + m0, (uint32_t)(m1 - m0), c->d_out.p, d_res + m0, st));
+        else FB_CUDA_CHECK(inflate_members_par(container, c->d_in.p, d_desc + m0, (uint32_t)(m1 - m0), c->d_out.p, d_res + m0, c->m_scratch.p, c->sm_count, st));
+        c->launches += 1;
+        FB_CUDA_CHECK(cudaEventRecord(ev_k, st));
+        FB_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream2, ev_k, 0));
+        if (ohi > olo) FB_CUDA_CHECK(cudaMemcpyAsync(out + olo, c->d_out.p + olo, ohi - olo, cudaMemcpyDeviceToHost, c->copy_stream2));
+    }
+    c->timer.mark(st, kPhInflate);
+    FB_CUDA_CHECK(cudaMemcpyAsync(res.data(), d_res, k * sizeof(MemberResult), cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
-    return rc;
+    FB_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream2));
+    c->timer.collect();
+    int first = FB200_OK;
+    for (size_t i = 0; i < k; i++) {
+        out_len[i] = res[i].out_len;
+        if (consumed) consumed[i] = res[i].consumed;
+        if (status) status[i] = (int)res[i].status;
+        if (first == FB200_OK && res[i].status) first = (int)res[i].status;
+    }
+    return first;
 }
 
 int fb200_decompress(fb200_ctx* c, int container, const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len,

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _run(extra, env=None):
     e = dict(os.environ)
     e.update(env or {})
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"] + extra,
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--bytes", str(8 << 20)] + extra,
                        capture_output=True, text=True, timeout=600, env=e, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     return [ln for ln in p.stdout.splitlines() if ln.strip()]
