@@ -1311,6 +1311,11 @@ void fb200_inflate_set_reader(fb200_inflate* s, fb200_read_fn reader, void* user
     s->user = user;
     if (s->state == fb200_inflate::kEnd) s->state = fb200_inflate::kHeader;  // inflate.zig:283-288
 }
+void fb200_inflate_rebind(fb200_inflate* s, fb200_read_fn reader, void* user) {
+    if (!s) return;
+    s->reader = reader;  // same reader object at a new address: the read state is left alone (unlike set_reader)
+    s->user = user;
+}
 void fb200_inflate_destroy(fb200_inflate* s) { delete s; }
 
 }  // extern "C"

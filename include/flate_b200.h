@@ -185,6 +185,9 @@ int fb200_inflate_get(fb200_inflate* s, size_t limit, const uint8_t** data, size
 int fb200_inflate_read(fb200_inflate* s, uint8_t* buf, size_t cap, size_t* n);
 int fb200_inflate_reset(fb200_inflate* s);
 void fb200_inflate_set_reader(fb200_inflate* s, fb200_read_fn reader, void* user);
+/* the caller's reader object moved (a by-value host struct, like the reference's Inflate): new callback context,
+ * no change of state (fb200_inflate_set_reader restarts the header parse after an end of member, inflate.zig:283-288) */
+void fb200_inflate_rebind(fb200_inflate* s, fb200_read_fn reader, void* user);
 void fb200_inflate_destroy(fb200_inflate* s);
 
 /* ---- test seams (all run on the GPU) ---- */

@@ -80,3 +80,17 @@ def test_synth_is_deterministic():
     assert 2.2 < ratio < 3.6
     m = synth.random_zero_mix(1 << 20)
     assert m.size == 1 << 20 and (m == 0).mean() > 0.2
+
+
+def test_zig_binding_declares_every_symbol():
+    """zig/flate_b200.zig is the reference-side binding (not compiled here: no zig toolchain): its extern block must
+    name exactly the symbols of the header, and the shim must keep the reference's public names (src/gzip.zig:5-66)."""
+    src = open(os.path.join(ROOT, "zig", "flate_b200.zig")).read()
+    externs = sorted(set(re.findall(r'pub extern "c" fn (fb200_[a-z0-9_]+)\(', src)))
+    assert externs == declared_symbols(), set(externs) ^ set(declared_symbols())
+    for name in ("pub fn compress(", "pub fn compressor(", "pub fn Compressor(", "pub fn decompress(", "pub fn decompressor(",
+                 "pub fn Inflate(", "pub const huffman", "pub const store", "pub fn flush(", "pub fn finish(", "pub fn setWriter(",
+                 "pub fn next(", "pub fn get(", "pub fn read(", "pub fn reader(", "pub fn reset(", "pub fn setReader(",
+                 "pub const flate = ", "pub const gzip = ", "pub const zlib = "):
+        assert name in src, name
+    assert "..." not in re.sub(r"//.*", "", src)   # no elided bodies
