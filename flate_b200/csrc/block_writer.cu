@@ -356,6 +356,39 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
     }
     __syncwarp();
 
+    // ---- stored without building the code, when that is provable ----
+    // dynamicBlock / huffmanBlock store a block iff stored_size < size + (size >> 4) (:418-426, :553-561), monotone in
+    // size.  Every prefix code costs at least the entropy of the literal frequencies, so when the inequality already
+    // holds for that lower bound the reference's choice is known without constructing the length-limited code (the
+    // serial part of this kernel; incompressible slices of a huffman-only stream are the case that matters).
+    if (pl.kind != kWrite && pl.has_input && pl.in_len <= kMaxStore) {
+        double acc = 0.0;
+        uint32_t tot = 0;
+        for (uint32_t i = lane; i < kNumLit; i += 32) {
+            const uint32_t f = sh.lit_freq[i];
+            if (f) {
+                acc += (double)f * log2((double)f);
+                tot += f;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        }
+        const double h = (double)tot * log2((double)tot) - acc;  // bits; the margin below dwarfs any rounding error
+        const uint64_t lower = h > 256.0 ? (uint64_t)h - 128 : 0;
+        const uint64_t stored_size = ((uint64_t)pl.in_len + 5) * 8;
+        if (stored_size < lower + (lower >> 4)) {  // uniform over the warp
+            if (lane == 0) {
+                d.type = kStored;
+                d.hdr_bits = 3;  // :283-286
+                d.body_bits = 0;
+            }
+            for (uint32_t i = lane; i < kHdrWords; i += 32) d.hdr[i] = i == 0 ? (pl.eof ? 1u : 0u) : 0u;
+            return;
+        }
+    }
+
     // ---- code construction ----
     huff_generate_warp(sh.hs, sh.lit_freq, kNumLit, 15, sh.lit_code);
     if (pl.kind == kHuffmanBlock) {  // huffmanDistanceEncoder, huffman_encoder.zig:340-348: one 1-bit code
@@ -501,64 +534,72 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
 // K5b: block bit offsets.  Huffman blocks are not byte aligned; a stored block pads after its
 // 3 header bits (block_writer.zig:283-291), so the offset recurrence is sequential.
 // ------------------------------------------------------------------------------------------
-__global__ void scan_block_offsets_kernel(BlockDesc* __restrict__ descs, const uint32_t* __restrict__ nblocks_dev,
+// A run of blocks moves the write position x to  has ? align8(x + pre) + post : x + pre  (pre ends with the 3 header
+// bits of the run's first stored block, post counts from the byte boundary that block aligns to).  Runs compose, so
+// the recurrence is a scan: every thread summarises a contiguous range of blocks, one thread chains the 1024
+// summaries, every thread then walks its range again from its start position.
+struct RunBits {
+    uint64_t pre, post;
+    uint32_t has;
+};
+__device__ __forceinline__ uint64_t run_apply(uint64_t x, const RunBits& r) {
+    return r.has ? ((x + r.pre + 7) & ~(uint64_t)7) + r.post : x + r.pre;
+}
+__device__ __forceinline__ void run_append(RunBits& a, uint32_t type, uint32_t in_len, uint64_t bits) {  // a := a then one block
+    if (type == kStored) {
+        if (a.has) a.post = ((a.post + 3 + 7) & ~(uint64_t)7) + 32 + 8ull * in_len;
+        else { a.pre += 3; a.has = 1; a.post = 32 + 8ull * in_len; }
+    } else if (a.has) {
+        a.post += bits;
+    } else {
+        a.pre += bits;
+    }
+}
+constexpr uint32_t kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+scan_block_offsets_kernel(BlockDesc* __restrict__ descs, const uint32_t* __restrict__ nblocks_dev,
                                           uint64_t start_bits, uint64_t* __restrict__ total_bits) {
-    // One warp: descriptors are fetched 32 at a time (the loads overlap), the recurrence itself is run
-    // redundantly by all lanes on shuffled values.
-    // total_bits[1] = number of blocks, total_bits[2 + i] = start bit of block nb * (i + 1) / kPackParts
-    // (lets the host overlap the device-to-host copy of finished parts with the packing of later ones)
-    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
-    const uint32_t lane = threadIdx.x;
+    // total_bits[0] = end of the stream in bits, [1] = number of blocks, [2 + i] = start bit of block
+    // nb * (i + 1) / kPackParts (lets the host overlap the device-to-host copy of finished parts with the packing of
+    // later ones), [16..18] = (pre, has, post) of the whole run (block-range sharded streams)
+    __shared__ RunBits runs[kScanThreads];
+    __shared__ uint64_t starts[kScanThreads];
     const uint32_t nb = *nblocks_dev;
+    const uint32_t per = (nb + kScanThreads - 1) / kScanThreads;
+    const uint32_t b0 = min(threadIdx.x * per, nb), b1 = min(b0 + per, nb);
+    RunBits mine{0, 0, 0};
+    for (uint32_t b = b0; b < b1; b++) run_append(mine, descs[b].type, descs[b].in_len, (uint64_t)descs[b].hdr_bits + descs[b].body_bits);
+    runs[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t x = start_bits;
+        RunBits all{0, 0, 0};
+        for (uint32_t t = 0; t < kScanThreads; t++) {
+            const RunBits r = runs[t];
+            starts[t] = x;
+            x = run_apply(x, r);
+            if (!all.has) { all.pre += r.pre; all.has = r.has; all.post = r.post; }
+            else if (r.has) all.post = ((all.post + r.pre + 7) & ~(uint64_t)7) + r.post;
+            else all.post += r.pre;
+        }
+        total_bits[0] = x;
+        total_bits[1] = nb;
+        total_bits[16] = all.pre;
+        total_bits[17] = all.has;
+        total_bits[18] = all.has ? all.post : 0;
+    }
+    __syncthreads();
     uint32_t mark[kPackParts - 1];
 #pragma unroll
     for (uint32_t i = 0; i + 1 < kPackParts; i++) mark[i] = (uint32_t)(((uint64_t)nb * (i + 1)) / kPackParts);
-    uint64_t off = start_bits;
-    // shard summary (block-range sharded streams): bits up to and including the 3 header bits of the first stored
-    // block, and the bits from the byte boundary that block aligns to up to the end; total_bits[16..18]
-    uint64_t pre = 0, aligned_at = 0;
-    bool seen_stored = false;
-    for (uint32_t base = 0; base < nb; base += 32) {
-        const uint32_t b = base + lane;
-        uint32_t type = kFixed, in_len = 0;
-        uint64_t bits = 0;
-        if (b < nb) {
-            type = descs[b].type;
-            in_len = descs[b].in_len;
-            bits = descs[b].hdr_bits + descs[b].body_bits;
-        }
-        const uint32_t cnt = min(32u, nb - base);
-        uint64_t my_off = 0;
-        for (uint32_t j = 0; j < cnt; j++) {
-            const uint32_t t = __shfl_sync(0xffffffffu, type, j);
-            const uint32_t len_j = __shfl_sync(0xffffffffu, in_len, j);
-            const uint64_t bits_j = __shfl_sync(0xffffffffu, (unsigned long long)bits, j);
-            if (j == lane) my_off = off;
-            if (t == kStored) {
-                if (!seen_stored) {
-                    seen_stored = true;
-                    pre = off + 3 - start_bits;
-                    aligned_at = (off + 3 + 7) & ~(uint64_t)7;
-                }
-                off = (off + 3 + 7) & ~(uint64_t)7;
-                off += 32 + 8ull * len_j;
-            } else {
-                off += bits_j;
-            }
-        }
-        if (b < nb) {
-            descs[b].bit_offset = my_off;
+    uint64_t off = starts[threadIdx.x];
+    for (uint32_t b = b0; b < b1; b++) {
+        descs[b].bit_offset = off;
 #pragma unroll
-            for (uint32_t i = 0; i + 1 < kPackParts; i++)
-                if (b == mark[i]) total_bits[2 + i] = my_off;
-        }
-    }
-    if (lane == 0) {
-        total_bits[0] = off;
-        total_bits[1] = nb;
-        total_bits[16] = seen_stored ? pre : off - start_bits;
-        total_bits[17] = seen_stored ? 1 : 0;
-        total_bits[18] = seen_stored ? off - aligned_at : 0;
+        for (uint32_t i = 0; i + 1 < kPackParts; i++)
+            if (b == mark[i]) total_bits[2 + i] = off;
+        if (descs[b].type == kStored) off = ((off + 3 + 7) & ~(uint64_t)7) + 32 + 8ull * descs[b].in_len;
+        else off += (uint64_t)descs[b].hdr_bits + descs[b].body_bits;
     }
 }
 
@@ -604,6 +645,7 @@ __device__ __forceinline__ uint32_t token_bits(uint32_t t, const uint32_t* lit, 
     return (lit[257 + lc] >> 16) + leb + (dist[dc] >> 16) + deb;
 }
 
+template <bool kBytes>  // kBytes: huffman-only / store streams (no token list)
 __global__ void __launch_bounds__(kPackThreads)
 pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ tokens, const BlockDesc* __restrict__ descs,
                    const uint32_t* __restrict__ nblocks_dev, uint32_t first_block, uint32_t* __restrict__ out) {
@@ -670,16 +712,40 @@ pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
     }
     __syncthreads();
 
-    const uint32_t items = (tokens == nullptr ? d.in_len : d.tok_count) + 1;  // + end-of-block
+    const uint32_t items = ((kBytes || tokens == nullptr) ? d.in_len : d.tok_count) + 1;  // + end-of-block
     const uint32_t per = (items + kPackThreads - 1) / kPackThreads;
     const uint32_t i0 = min(threadIdx.x * per, items), i1 = min(i0 + per, items);
-    const uint32_t* tk = tokens ? tokens + d.tok_begin : nullptr;
+    const uint32_t* tk = (!kBytes && tokens) ? tokens + d.tok_begin : nullptr;
     const uint8_t* src = in ? in + d.in_begin : nullptr;
+    // huffman-only slices (no token list): a thread walks its run of bytes as aligned words (a byte-wise walk asks
+    // the L1 for 32 different sectors with every load); the second pass finds them in the L1
+    const bool word_bytes = kBytes && tk == nullptr;
+    uint32_t nbytes = 0, mis = 0, nwords = 0;
+    const uint32_t* pw = nullptr;
+    if (word_bytes) {
+        nbytes = min(i1, items - 1) - min(i0, items - 1);  // the last item is the end-of-block symbol, not a byte
+        const uint8_t* p = src + i0;
+        mis = (uint32_t)((uintptr_t)p & 3);
+        pw = reinterpret_cast<const uint32_t*>(p - mis);
+        nwords = nbytes ? (nbytes + mis + 3) / 4 : 0;
+    }
     uint32_t mybits = 0;
-    for (uint32_t i = i0; i < i1; i++) {
-        if (i == items - 1) mybits += lit[kEndBlock] >> 16;
-        else if (tk) mybits += token_bits(tk[i], lit, dist);
-        else mybits += lit[src[i]] >> 16;
+    if (word_bytes) {
+        for (uint32_t w = 0; w < nwords; w++) {
+            const uint32_t v = pw[w];
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t bi = w * 4 + k - mis;  // wraps for the bytes before the run
+                if (bi < nbytes) mybits += lit[(v >> (8 * k)) & 255u] >> 16;
+            }
+        }
+        if (i1 == items && i0 < i1) mybits += lit[kEndBlock] >> 16;
+    } else {
+        for (uint32_t i = i0; i < i1; i++) {
+            if (i == items - 1) mybits += lit[kEndBlock] >> 16;
+            else if (tk) mybits += token_bits(tk[i], lit, dist);
+            else mybits += lit[src[i]] >> 16;
+        }
     }
     // block-wide exclusive scan of mybits
     uint32_t x = mybits;
@@ -702,6 +768,22 @@ pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
     if (i0 >= i1) return;
     BitSink bs;
     bs.init(out, o + hdr_bits + excl);
+    if (word_bytes) {
+        for (uint32_t w = 0; w < nwords; w++) {
+            const uint32_t v = pw[w];
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t bi = w * 4 + k - mis;
+                if (bi < nbytes) {
+                    const uint32_t c = lit[(v >> (8 * k)) & 255u];
+                    bs.put(c & 0xffffu, c >> 16);
+                }
+            }
+        }
+        if (i1 == items) bs.put(lit[kEndBlock] & 0xffffu, lit[kEndBlock] >> 16);
+        bs.finish();
+        return;
+    }
     for (uint32_t i = i0; i < i1; i++) {
         if (i == items - 1) {
             bs.put(lit[kEndBlock] & 0xffffu, lit[kEndBlock] >> 16);
@@ -754,18 +836,20 @@ cudaError_t build_blocks(const BlockPlan* plans, const uint32_t* nblocks_dev, ui
 }
 cudaError_t scan_block_offsets(BlockDesc* descs, const uint32_t* nblocks_dev, uint64_t start_bits, uint64_t* total_bits,
                                cudaStream_t st) {
-    scan_block_offsets_kernel<<<1, 32, 0, st>>>(descs, nblocks_dev, start_bits, total_bits);
+    scan_block_offsets_kernel<<<1, kScanThreads, 0, st>>>(descs, nblocks_dev, start_bits, total_bits);
     return cudaGetLastError();
 }
 cudaError_t pack_blocks(const uint8_t* in, const uint32_t* tokens, const BlockDesc* descs, const uint32_t* nblocks_dev,
                         uint32_t max_blocks, uint32_t* out_words, cudaStream_t st) {
-    pack_blocks_kernel<<<max_blocks, kPackThreads, 0, st>>>(in, tokens, descs, nblocks_dev, 0, out_words);
+    if (tokens) pack_blocks_kernel<false><<<max_blocks, kPackThreads, 0, st>>>(in, tokens, descs, nblocks_dev, 0, out_words);
+    else pack_blocks_kernel<true><<<max_blocks, kPackThreads, 0, st>>>(in, tokens, descs, nblocks_dev, 0, out_words);
     return cudaGetLastError();
 }
 cudaError_t pack_blocks_range(const uint8_t* in, const uint32_t* tokens, const BlockDesc* descs, const uint32_t* nblocks_dev,
                               uint32_t first_block, uint32_t count, uint32_t* out_words, cudaStream_t st) {
     if (count == 0) return cudaSuccess;
-    pack_blocks_kernel<<<count, kPackThreads, 0, st>>>(in, tokens, descs, nblocks_dev, first_block, out_words);
+    if (tokens) pack_blocks_kernel<false><<<count, kPackThreads, 0, st>>>(in, tokens, descs, nblocks_dev, first_block, out_words);
+    else pack_blocks_kernel<true><<<count, kPackThreads, 0, st>>>(in, tokens, descs, nblocks_dev, first_block, out_words);
     return cudaGetLastError();
 }
 

@@ -216,8 +216,9 @@ void fb200_ctx_destroy(fb200_ctx* c) {
 
 size_t fb200_compress_bound(size_t n, int mode) {
     (void)mode;
-    // stored blocks cost 5 bytes each; an unstorable Huffman block of incompressible bytes < 9/8 n + header
-    return n + (n >> 3) + (n / 32768 + 2) * 640 + 64;
+    // stored blocks cost 5 bytes each; an unstorable Huffman block of incompressible bytes < 9/8 n + header;
+    // the last term covers the container header and footer of any container (gzip: 10 + 8 bytes)
+    return n + (n >> 3) + (n / 32768 + 2) * 640 + 64 + 32;
 }
 
 }  // extern "C"
@@ -268,6 +269,7 @@ static inline size_t footer_size(int container) { return container == FB200_GZIP
 // Device flags of the sparse parse (u32 index 20 of d_scalars): bit 0 = an orbit left its span unjoined,
 // bit 1 = the token emitter met an entry that was never evaluated.  Non-zero => redo with dense tables.
 constexpr int kSparseFlagIdx = 20;
+constexpr int kRunCounterIdx = 21;  // run hand-out of the rolling sparse parse
 constexpr size_t kSpHaloPlus = 256 + 272;  // lz77_sparse_lookahead() = overlap + lazy halo + compare look-ahead
 static int sparse_begin(fb200_ctx* c, const Lz77Buffers& b, size_t count, cudaStream_t st) {
     FB_CUDA_CHECK(cudaMemsetAsync(b.nx, 0xFF, count * sizeof(uint32_t), st));
@@ -287,7 +289,7 @@ static int sparse_tokenize(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_
     const uint32_t T = lz77_sparse_chunk();
     FB_CUDA_CHECK(lz77_link_range(b, d_in, (uint32_t)begin, (uint32_t)n, (uint32_t)n, st, &c->timer, d_skip, nskip));
     FB_CUDA_CHECK(lz77_sparse_range(b, d_in, (uint32_t)(begin / T), (uint32_t)((n + T - 1) / T), (uint32_t)n, lv, c->chunk_fail.p,
-                                    c->d_scalars + kSparseFlagIdx, st, &c->timer, (uint32_t)begin));
+                                    c->d_scalars + kSparseFlagIdx, st, &c->timer, (uint32_t)begin, c->d_scalars + kRunCounterIdx));
     FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in + begin, (uint32_t)(n - begin), lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
     c->launches += 9;
     return FB200_OK;
@@ -348,8 +350,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     if (container < 0 || container > 2 || begin > n) return FB200_INVALID_ARGUMENT;
     if (((uintptr_t)d_out & 15) != 0) return FB200_INVALID_ARGUMENT;
     const size_t hdr = with_header ? header_size(container) : 0;
-    const size_t bound = fb200_compress_bound(n - begin, mode) + header_size(container) + footer_size(container);
-    if (cap < bound) return FB200_NO_SPACE_LEFT;
+    if (cap < fb200_compress_bound(n - begin, mode)) return FB200_NO_SPACE_LEFT;  // the bound includes the container overhead
     uint32_t* nblocks_dev = c->d_scalars + 1;
     uint64_t* total_bits_dev = reinterpret_cast<uint64_t*>(c->d_scalars + 2);
     uint32_t max_blocks;
@@ -393,7 +394,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
             // slab-overlapped copy: links follow the copy front one hash tile behind, the sparse parse follows the
             // links by its look-ahead
             if ((rc = sparse_begin(c, b, n, st))) return rc;
-            const uint32_t T = lz77_sparse_chunk(), ahead = lz77_sparse_lookahead();
+            const uint32_t T = lz77_sparse_chunk(), ahead = lz77_sparse_link_ahead();
             size_t copied = 0, linked = 0;
             uint32_t chunks_done = 0;
             int k = 0;
@@ -410,7 +411,8 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
                 const uint32_t chunks_end = range_end == n ? (uint32_t)((n + T - 1) / T)
                                                            : (uint32_t)(range_end > ahead ? (range_end - ahead) / T : 0);
                 if (chunks_end > chunks_done) {
-                    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, chunks_done, chunks_end, (uint32_t)n, lv, c->chunk_fail.p, c->d_scalars + kSparseFlagIdx, st, &c->timer));
+                    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, chunks_done, chunks_end, (uint32_t)n, lv, c->chunk_fail.p, c->d_scalars + kSparseFlagIdx, st, &c->timer, 0,
+                                                    c->d_scalars + kRunCounterIdx));
                     chunks_done = chunks_end;
                 }
                 c->launches += 2;
@@ -487,13 +489,18 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     if (h_dst) {
         // one small read-back tells the host the block count, the total size and the part boundaries
         FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8 * (2 + kPackParts - 1), cudaMemcpyDeviceToHost, st));
+        c->h_scalars[9] = 0;
+        if (sparse || d_nx_given) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 9, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
         FB_CUDA_CHECK(cudaStreamSynchronize(st));
         const uint64_t total_bits = c->h_scalars[0];
         const uint32_t nb = (uint32_t)c->h_scalars[1];
         const size_t out_bytes = (size_t)((total_bits + 7) >> 3);
-        if (out_bytes + footer_size(container) > h_cap) return FB200_NO_SPACE_LEFT;
+        // a failed speculation is known by now (both flag bits are set before the block writer runs): nothing of
+        // this attempt is packed or copied back, the repair / dense redo below produces the stream
+        const bool speculation_failed = (uint32_t)c->h_scalars[9] != 0;
+        if (!speculation_failed && out_bytes + footer_size(container) > h_cap) return FB200_NO_SPACE_LEFT;
         size_t byte_lo = 0;
-        for (uint32_t i = 0; i < kPackParts; i++) {
+        for (uint32_t i = 0; i < kPackParts && !speculation_failed; i++) {
             const uint32_t b_lo = (uint32_t)(((uint64_t)nb * i) / kPackParts), b_hi = (uint32_t)(((uint64_t)nb * (i + 1)) / kPackParts);
             FB_CUDA_CHECK(pack_blocks_range(d_in, tokens, c->descs.p, nblocks_dev, b_lo, b_hi - b_lo, reinterpret_cast<uint32_t*>(d_out), st));
             // bytes below the next part's first bit are final once this part is packed (a shared byte goes with the next part)
@@ -623,12 +630,12 @@ int fb200_deflate_shard_search(fb200_ctx* c, int level, const void* d_in, size_t
         const size_t nx_end = to + W < n ? to + W : n;
         FB_CUDA_CHECK(cudaMemsetAsync(b.nx + from, 0xFF, (nx_end - from) * sizeof(uint32_t), st));
         FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
-        const size_t need = to + lz77_sparse_lookahead();
+        const size_t need = to + lz77_sparse_link_ahead();
         const size_t link_end = need >= n ? n : (need + 8191) / 8192 * 8192 < n ? (need + 8191) / 8192 * 8192 : n;
         FB_CUDA_CHECK(lz77_link_range(b, (const uint8_t*)d_in, (uint32_t)(from >= kHist ? from - kHist : 0), (uint32_t)link_end,
                                       (uint32_t)n, st, &c->timer));
         FB_CUDA_CHECK(lz77_sparse_range(b, (const uint8_t*)d_in, (uint32_t)(from / T), (uint32_t)((to + T - 1) / T), (uint32_t)n, lv,
-                                        c->chunk_fail.p, c->d_scalars + kSparseFlagIdx, st, &c->timer));
+                                        c->chunk_fail.p, c->d_scalars + kSparseFlagIdx, st, &c->timer, 0, c->d_scalars + kRunCounterIdx));
         c->launches += 2;
         uint32_t bad = 0;
         FB_CUDA_CHECK(cudaMemcpyAsync(&bad, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));

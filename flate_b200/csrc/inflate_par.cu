@@ -766,6 +766,7 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
     bool fixed_ready = false;
     int status = S.c.status;
     while (status == FB200_OK) {  // inflate.zig:251-280 step: one deflate block per iteration
+        __syncthreads();  // every warp has read the control block of the previous block before warp 0 rewrites it
         if (warp == 0) block_header(S, bc, md, fixed_ready);
         __syncthreads();
         status = S.c.status;

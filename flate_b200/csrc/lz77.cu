@@ -1083,6 +1083,426 @@ sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t fir
 }
 
 // ------------------------------------------------------------------------------------------
+// K2s, rolling form (opt-in with FB200_SPARSE_ROLL=16; measured slower than the chunk kernel).
+//
+// Same orbits, same claims, same result as sparse_parse_kernel, but a persistent CTA walks a RUN of many
+// chunks with one window that rolls forward, so lanes never wait for the slowest orbit of a chunk: a lane
+// whose orbit ended takes the next seed at once.  The window is a ring of 65536 positions addressed by the
+// low 16 bits of the stream position (bytes, links, one claim bit per position); it is loaded by TMA bulk
+// copies in epochs of 4096 positions.  Seeds are handed out in ascending order, one every kG positions.
+//   resident positions      [lb - 65536, lb)          lb = load front (shared, only ever grows)
+//   a search at p needs     [p - 32768, p + 272)      (candidates reach 32768 back, compares 258 + slack ahead)
+// An orbit is registered in the epoch of the arrival it is evaluating (live[epoch & 15]; the seeds of an
+// epoch are counted in when the epoch is loaded), `tail` is the oldest epoch that still has a registered
+// orbit or an unclaimed seed, and the front moves by one epoch when tail * 4096 - 32768 >= lb - 65536 + 4096.
+// A lane whose next position is not resident yet simply waits in place (its registration is within two
+// epochs of the front, so it never holds the tail back); the slowest orbits are far behind the front and
+// always free to move, hence progress.  Inside a run there is no hand-over: all orbits share the claim
+// bitmap.  At the end of the run the overlap of kW positions is evaluated as in the chunk kernel and the
+// same exact check decides chunk_fail of the run's last chunk.
+// Preconditions (the launcher sends everything else to the chunk kernel): `in` and `link` 16-byte aligned,
+// every run at least two chunks long, run end + kW + 256 + 272 rounded up to an epoch <= n.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kSrRing = 65536, kSrEpoch = 4096, kSrLook = 272, kSrMirror = 288;
+constexpr uint32_t kSrBytes = kSrRing + kSrMirror;
+constexpr uint32_t kSrSmem = kSrBytes + kSrRing * 2 + kSrRing / 8;
+constexpr uint32_t kSrChunk = 32768;  // granularity of runs and of chunk_fail (= kSparseT)
+
+struct SrShared {
+    uint32_t live[16];
+    uint32_t cross[kMaxCross];
+    uint32_t safe[32];  // kW / 32 words: arrivals of the run's overlap that lie on an overlap seed's orbit
+    uint32_t seed_next, cross_cnt, failed, run, lb, tail, inflight, parity, warps_done;
+    // the run being worked on
+    uint32_t s0, s1, span_end, load_end, seed_lo, has_begin, nseeds;
+};
+
+// seeds of epoch e that will be handed out (regular ones at or past seed_lo, plus the segment start)
+__device__ __forceinline__ uint32_t sr_epoch_seeds(const SrShared& S, uint32_t e, uint32_t kG, uint32_t begin) {
+    const uint32_t lo = max(e * kSrEpoch, S.seed_lo), hi = min((e + 1) * kSrEpoch, S.span_end);
+    uint32_t c = hi > lo ? (hi - lo + kG - 1) / kG : 0;  // lo is a multiple of kG
+    if (S.has_begin && (begin >> 12) == e) c++;
+    return c;
+}
+
+__device__ __forceinline__ void sr_load_epoch(uint32_t bar, uint8_t* sb, uint16_t* sl, const uint8_t* in, const uint16_t* link, uint32_t pos) {
+    const uint32_t slot = pos & (kSrRing - 1);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(sb + slot)), "l"(in + pos), "r"(kSrEpoch), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(sl + slot)), "l"(link + pos), "r"(kSrEpoch * 2), "r"(bar) : "memory");
+    if (slot == 0)  // the first bytes of the ring again behind its end: compares read across the wrap
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(sb + kSrRing)), "l"(in + pos), "r"(kSrMirror), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t sr_epoch_tx(uint32_t pos) { return kSrEpoch * 3 + ((pos & (kSrRing - 1)) == 0 ? kSrMirror : 0); }
+__device__ __forceinline__ bool sr_bar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// Load front duty, warp 0 once per round: retire finished epochs, start the next epoch's load when its ring
+// slots are free, publish it when it has landed.
+__device__ __noinline__ void sr_loader(SrShared& S, uint32_t bar, uint8_t* sb, uint16_t* sl, uint32_t* valid, const uint8_t* in,
+                                       const uint16_t* link, uint32_t kG, uint32_t begin) {
+    const uint32_t lane = threadIdx.x & 31;
+    volatile SrShared& V = S;
+    const uint32_t lb = V.lb;
+    uint32_t go = 0;
+    if (lane == 0) {
+        if (V.inflight) {
+            if (sr_bar_test(bar, V.parity)) {
+                V.parity = V.parity ^ 1u;
+                V.inflight = 0;
+                __threadfence_block();
+                V.lb = lb + kSrEpoch;  // publish: the epoch's bytes, links, cleared claim bits and seed count are in place
+            }
+        } else if (lb < V.load_end) {
+            uint32_t tail = V.tail;
+            while (tail * kSrEpoch + 32768 < lb + kSrEpoch && V.live[tail & 15] == 0) tail++;
+            V.tail = tail;
+            if (tail * kSrEpoch + 32768 >= lb + kSrEpoch) go = 1;
+        }
+    }
+    go = __shfl_sync(0xffffffffu, go, 0);
+    if (go) {
+        // epoch lb / 4096 replaces epoch lb / 4096 - 16, which nobody can reach any more
+        const uint32_t w0 = (lb & (kSrRing - 1)) >> 5;
+        for (uint32_t i = lane; i < kSrEpoch / 32; i += 32) valid[w0 + i] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            V.live[(lb >> 12) & 15] = sr_epoch_seeds(S, lb >> 12, kG, begin);
+            __threadfence_block();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(sr_epoch_tx(lb)) : "memory");
+            sr_load_epoch(bar, sb, sl, in, link, lb);
+            V.inflight = 1;
+        }
+    }
+}
+
+template <uint32_t kW, uint32_t kG, uint32_t kThreads, int kSteps>
+__global__ void __launch_bounds__(kThreads, 1)
+sparse_roll_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t first_chunk, uint32_t end_chunk, uint32_t nruns, uint32_t n,
+                   const uint16_t* __restrict__ link, LevelArgs lv, uint32_t* __restrict__ nx, uint32_t* __restrict__ chunk_fail,
+                   uint32_t* __restrict__ flags, uint32_t* __restrict__ run_counter, uint32_t prio) {
+    // prio > 0: a warp none of whose orbits is registered within `prio` epochs of the tail yields issue slots (short sleep)
+    static_assert(kW == 1024 && kSrEpoch % kG == 0 && kSrChunk % kSrEpoch == 0, "layout");
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ SrShared S;
+    __shared__ __align__(8) uint64_t stage_bar;
+    uint8_t* sb = smem_raw;                                                    // byte of position p at p & 0xffff
+    uint16_t* sl = reinterpret_cast<uint16_t*>(smem_raw + kSrBytes);           // link of position p at p & 0xffff
+    uint32_t* valid = reinterpret_cast<uint32_t*>(smem_raw + kSrBytes + kSrRing * 2);  // claim bit of position p at p & 0xffff
+    volatile SrShared& V = S;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ltmask = (1u << lane) - 1;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+    constexpr uint32_t kWarps = kThreads / 32;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.parity = 0;
+    }
+    const uint32_t slide_J = max(n >> 15, 1u) - 1;
+    const uint32_t quarter = lv.chain >> 2;
+    uint32_t sb_addr = (uint32_t)__cvta_generic_to_shared(sb);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sb_addr));
+    const uint32_t sl_addr = sb_addr + kSrBytes;
+    const uint32_t nch = end_chunk - first_chunk;
+
+    for (;;) {
+        // ---- next run ----
+        __syncthreads();  // the previous run is over for every thread (and the barrier is initialised)
+        if (threadIdx.x == 0) {
+            const uint32_t r = atomicAdd(run_counter, 1u);
+            S.run = r;
+            if (r < nruns) {
+                const uint32_t c0 = first_chunk + (uint32_t)(((uint64_t)nch * r) / nruns);
+                const uint32_t c1 = first_chunk + (uint32_t)(((uint64_t)nch * (r + 1)) / nruns);
+                S.s0 = c0 * kSrChunk;
+                S.s1 = c1 * kSrChunk;
+                S.span_end = S.s1 + kW;
+                S.load_end = (S.span_end + kSpHalo + kSrLook + kSrEpoch - 1) / kSrEpoch * kSrEpoch;
+                S.has_begin = (begin > S.s0 && begin < S.s1) ? 1u : 0u;
+                S.seed_lo = begin > S.s0 ? (begin + kG - 1) / kG * kG : S.s0;  // regular seeds before the segment start are not seeds
+                S.nseeds = (S.span_end - S.s0) / kG + S.has_begin;
+                S.seed_next = 0;
+                S.cross_cnt = 0;
+                S.failed = 0;
+                S.warps_done = 0;
+                S.inflight = 0;
+            }
+        }
+        __syncthreads();
+        if (S.run >= nruns) break;
+        const uint32_t s0 = S.s0, s1 = S.s1, span_end = S.span_end, nseeds = S.nseeds, has_begin = S.has_begin;
+        const uint32_t lb0 = max(s0 + 32768u, kSrRing);  // first load: the whole ring
+        for (uint32_t i = threadIdx.x; i < kSrRing / 32; i += kThreads) valid[i] = 0;
+        if (threadIdx.x < 32) S.safe[threadIdx.x] = 0;
+        if (threadIdx.x < 16) {
+            const uint32_t e = (lb0 >> 12) - 16 + threadIdx.x;
+            S.live[e & 15] = sr_epoch_seeds(S, e, kG, begin);
+        }
+        if (threadIdx.x == 0) {
+            S.tail = s0 >> 12;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            uint32_t tx = 0;
+            for (uint32_t e = 0; e < 16; e++) tx += sr_epoch_tx(lb0 - kSrRing + e * kSrEpoch);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+            for (uint32_t e = 0; e < 16; e++) sr_load_epoch(bar, sb, sl, in, link, lb0 - kSrRing + e * kSrEpoch);
+        }
+        __syncthreads();
+        {
+            const uint32_t par = S.parity;
+            while (!sr_bar_test(bar, par)) {}
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            S.parity ^= 1u;
+            S.lb = lb0;
+        }
+        __syncthreads();
+
+        uint32_t st = kIdle, left = 0, saved = 0;
+        uint32_t pi = 0, qi = 0, lim = 0, best_len = 0, best_dist = 0, ro_addr = 0, cb = 0, first4 = 0, max_len = 0;
+        uint32_t p0 = 0, curk = 0, cur_len = 0, cur_dist = 0;  // the arrival being evaluated and its pending match
+        uint32_t a_pos = 0;                                    // stream position of the next arrival / search
+        bool from_overlap = false;
+
+        // findMatch(pos = a_pos, min_len = best_len) with `saved` candidates (deflate.zig:233-266)
+        auto start_search = [&]() {
+            const uint32_t p = a_pos;
+            if (p + kSrLook > V.lb) return;  // not resident yet: stays in kStart
+            const uint32_t min_len = best_len, budget = saved;
+            best_dist = 0;
+            left = 0;
+            st = kSearchDone;
+            if (p >= n) return;
+            const uint32_t remaining = n - p;
+            if (remaining < kMinMatch) return;     // Lookup.zig:24
+            max_len = min(remaining, kMaxMatch);   // SlidingWindow.zig:82
+            if (min_len >= max_len || budget == 0) return;
+            pi = p;
+            qi = p;
+            const uint32_t jj = max((p + kMinLookahead) >> 15, 1u) - 1;
+            const int32_t base = (int32_t)(min(jj, slide_J) << 15);
+            lim = (uint32_t)max((int32_t)p - (int32_t)kMaxDist, base + 1);
+            left = budget;
+            const uint32_t ps = p & (kSrRing - 1);
+            first4 = lds_u32_unaligned(sb, ps);
+            const uint32_t ro = max(min_len, 3u);  // a longer match agrees on byte max(best_len, 3)
+            ro_addr = sb_addr + ro;
+            cb = sb[ps + ro];
+            st = kStepping;
+        };
+        // the orbit reaches the clean arrival a_pos (p0 still holds the arrival it is registered at)
+        auto arrive = [&]() {
+            const uint32_t a = a_pos;
+            bool ended = false;
+            if (a >= span_end) {
+                if (!from_overlap) {  // must have joined an overlap seed's orbit: checked after the run
+                    const uint32_t idx = atomicAdd(&S.cross_cnt, 1u);
+                    if (idx < kMaxCross) S.cross[idx] = p0;
+                }
+                ended = true;
+            } else {
+                if (a + kSrLook > V.lb) return;  // not resident yet: stays in kArrive
+                const uint32_t w = (a & (kSrRing - 1)) >> 5, bit = 1u << (a & 31);
+                const uint32_t old = atomicOr(&valid[w], bit);
+                if (from_overlap) {
+                    const uint32_t o = a - s1;  // an overlap seed's orbit never leaves [s1, span_end) alive
+                    if (atomicOr(&S.safe[o >> 5], 1u << (o & 31)) & (1u << (o & 31))) ended = true;  // another overlap seed's lane carries on
+                } else if (old & bit) {
+                    ended = true;  // somebody carries on from here
+                }
+            }
+            if (ended) {
+                atomicSub(&S.live[(p0 >> 12) & 15], 1u);
+                st = kIdle;
+                return;
+            }
+            if ((a ^ p0) >> 12) {  // register in the new epoch first, so that the orbit is never unaccounted for
+                atomicAdd(&S.live[(a >> 12) & 15], 1u);
+                atomicSub(&S.live[(p0 >> 12) & 15], 1u);
+            }
+            p0 = a;
+            curk = 0;
+            cur_len = 0;
+            cur_dist = 0;
+            best_len = 0;
+            saved = lv.chain;
+            st = kStart;
+        };
+        // a walk ended: apply the lazy rule (deflate.zig:166-190)
+        auto decide = [&]() {
+            const bool found = best_dist != 0;
+            bool fin = false;
+            if (cur_len == 0) {
+                if (found) {
+                    cur_len = best_len;
+                    cur_dist = best_dist;
+                } else {
+                    fin = true;  // plain literal
+                }
+            } else if (found) {  // better match one byte later: the pending one becomes a literal
+                curk++;
+                cur_len = best_len;
+                cur_dist = best_dist;
+            } else {
+                fin = true;      // emit the pending match
+            }
+            if (!fin && cur_len >= lv.lazy) fin = true;  // deflate.zig:171
+            if (!fin) {
+                a_pos = p0 + curk + 1;
+                best_len = cur_len;
+                saved = cur_len >= lv.good ? quarter : lv.chain;  // deflate.zig:241-245
+                st = kStart;
+            } else {
+                uint32_t out = 0, step = 1;
+                if (cur_len) {
+                    out = curk | ((cur_len - 3) << 8) | (cur_dist << 16);
+                    step = curk + cur_len;
+                }
+                nx[p0] = out;
+                a_pos = p0 + step;
+                st = kArrive;
+            }
+        };
+
+        bool exhausted = false, counted = false;
+        while (true) {
+            // ---- phase A: chain steps (deflate.zig:248 "Hot path loop!") ----
+            uint32_t nl = left ? lds_shared_u16(sl_addr + 2 * (qi & (kSrRing - 1))) : 0;
+#pragma unroll
+            for (int u = 0; u < kSteps; u++) {
+                if (left) {
+                    qi -= nl;
+                    const bool in_range = (int32_t)qi >= (int32_t)lim;
+                    const uint32_t qs = (in_range ? qi : pi) & (kSrRing - 1);  // a slot that is always safe to read
+                    const uint32_t b = lds_shared_u8(ro_addr + qs);
+                    nl = lds_shared_u16(sl_addr + 2 * qs);
+                    if (!in_range) {  // end of chain (kNoLink), too far, or at/below the slide base
+                        st = kSearchDone;
+                        left = 0;
+                    } else if (b == cb) {  // may beat the best so far: needs the full compare
+                        st = kPending;
+                        saved = left;
+                        left = 0;
+                    } else {
+                        left--;
+                    }
+                }
+            }
+            if (st == kStepping && left == 0) st = kSearchDone;
+            // ---- phase B: full compares (SlidingWindow.match with the running best as min_len) ----
+            if (__any_sync(0xffffffffu, st == kPending)) {
+                if (st == kPending) {
+                    st = kStepping;
+                    left = saved - 1;  // this candidate is paid for either way
+                    const uint32_t qs = qi & (kSrRing - 1), ps = pi & (kSrRing - 1);
+                    if (lds_u32_unaligned(sb, qs) == first4) {
+                        uint32_t i = 4;
+                        while (i < max_len) {
+                            const uint32_t x = lds_u32_unaligned(sb, qs + i) ^ lds_u32_unaligned(sb, ps + i);
+                            if (x) {
+                                i += (__ffs(x) - 1) >> 3;
+                                break;
+                            }
+                            i += 4;
+                        }
+                        if (i > max_len) i = max_len;
+                        if (i > best_len) {
+                            best_len = i;
+                            best_dist = pi - qi;
+                            if (i >= lv.nice || i >= max_len) {  // deflate.zig:256-259, or nothing can be longer
+                                st = kSearchDone;
+                                left = 0;
+                            } else {
+                                ro_addr = sb_addr + i;
+                                cb = sb[ps + i];
+                            }
+                        }
+                    }
+                    if (st == kStepping && left == 0) st = kSearchDone;
+                }
+            }
+            // ---- phase C: lazy decisions of finished walks, next arrival of the orbit ----
+            if (__any_sync(0xffffffffu, st == kSearchDone)) {
+                if (st == kSearchDone) decide();
+            }
+            // ---- phase D: new seeds for idle lanes, ascending ----
+            const uint32_t idle = __ballot_sync(0xffffffffu, st == kIdle);
+            if (idle && !exhausted) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&S.seed_next, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= nseeds) {
+                    exhausted = true;
+                } else if (st == kIdle) {
+                    const uint32_t t = base + __popc(idle & ltmask);
+                    if (t < nseeds) {
+                        // the segment's first position (where the true orbit starts) goes first: it lies in the run's first chunk
+                        const uint32_t x = (has_begin && t == 0) ? begin : s0 + (t - has_begin) * kG;
+                        if (x >= begin) {  // positions before the segment are history, not seeds
+                            a_pos = x;
+                            p0 = x;  // registered where its epoch counted it in
+                            from_overlap = x >= s1;
+                            st = kArrive;
+                        }
+                    }
+                }
+            }
+            // ---- phase E: arrivals (claim, or stop at somebody's trail), phase F: walks begin ----
+            if (__any_sync(0xffffffffu, st == kArrive)) {
+                if (st == kArrive) arrive();
+            }
+            if (__any_sync(0xffffffffu, st == kStart)) {
+                if (st == kStart) start_search();
+            }
+            if (warp == 0) sr_loader(S, bar, sb, sl, valid, in, link, kG, begin);
+            const uint32_t working = __ballot_sync(0xffffffffu, st == kStepping || st == kPending || st == kSearchDone);
+            if (exhausted && __ballot_sync(0xffffffffu, st != kIdle) == 0) {
+                if (warp != 0) {
+                    if (lane == 0) atomicAdd(&S.warps_done, 1u);
+                    break;
+                }
+                if (V.warps_done == kWarps - 1) break;  // warp 0 serves the load front until everybody is done
+                __nanosleep(200);
+            } else if (working == 0) {
+                __nanosleep(100);  // everybody here waits for the load front (or for seeds): leave the issue slots to the others
+            } else if (prio) {
+                const uint32_t near_tail = __ballot_sync(0xffffffffu, st != kIdle && (p0 >> 12) < V.tail + prio);
+                if (near_tail == 0) __nanosleep(prio >> 8 ? prio >> 8 : 200);
+            }
+            (void)counted;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && S.inflight) {  // a look-ahead epoch nobody needed is still landing
+            const uint32_t par = S.parity;
+            while (!sr_bar_test(bar, par)) {}
+            S.parity ^= 1u;
+            S.inflight = 0;
+        }
+        {
+            const uint32_t cnt = S.cross_cnt;
+            if (threadIdx.x < min(cnt, kMaxCross)) {
+                const uint32_t o = S.cross[threadIdx.x] - s1;  // the last arrival before the span end lies in the overlap
+                if (o >= kW || !((S.safe[o >> 5] >> (o & 31)) & 1u)) S.failed = 1;
+            }
+            if (threadIdx.x == 0 && cnt > kMaxCross) S.failed = 1;
+        }
+        __syncthreads();
+        for (uint32_t c = s0 / kSrChunk + threadIdx.x; c < s1 / kSrChunk; c += kThreads)
+            chunk_fail[c] = (c + 1 == s1 / kSrChunk) ? S.failed : 0u;  // orbits of the run's own range may arrive anywhere in the next chunk
+        if (threadIdx.x == 0 && S.failed) atomicOr(flags, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K3a: lazy step.  deflate.zig:160-193 restricted to arrivals with no pending match.
 // From such an arrival at p the reference emits k literals p..p+k-1 (each displaced by a strictly
 // longer match one byte later) and then one match at p+k, or a single literal if nothing matches.
@@ -1092,7 +1512,8 @@ sparse_parse_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t fir
 // of kChunk positions, the offset (into the next chunk) of the first arrival past the chunk end.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kLazyHalo = 256;  // a lazy run looks at most 255 positions ahead of its arrival
-__global__ void __launch_bounds__(1024)
+constexpr uint32_t kLazyThreads = 256;
+__global__ void __launch_bounds__(kLazyThreads)
 lazy_exit_kernel(const uint32_t* __restrict__ r_full, const uint32_t* __restrict__ r_quarter, uint32_t n, LevelArgs lv,
                  uint32_t* __restrict__ nx, uint16_t* __restrict__ exits) {
     // K3a + K3b fused: the chunk's match tables are staged once in shared memory, every thread
@@ -1137,15 +1558,21 @@ lazy_exit_kernel(const uint32_t* __restrict__ r_full, const uint32_t* __restrict
         nxt[i] = (uint16_t)t;
     }
     __syncthreads();
-    while (true) {
+    while (true) {  // pointer jumping: a read phase and a write phase per round (kLazyThreads threads)
         bool pending = false;
-        for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
-            const uint32_t t = nxt[i];
+        uint32_t nv[kChunk / kLazyThreads];
+#pragma unroll
+        for (uint32_t k = 0; k < kChunk / kLazyThreads; k++) {
+            uint32_t t = nxt[threadIdx.x + k * kLazyThreads];
             if (t < kChunk) {
-                nxt[i] = nxt[t];  // racing reads see some power of f: still correct
+                t = nxt[t];
                 pending = true;
             }
+            nv[k] = t;
         }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t k = 0; k < kChunk / kLazyThreads; k++) nxt[threadIdx.x + k * kLazyThreads] = (uint16_t)nv[k];
         if (!__syncthreads_or(pending)) break;
     }
     for (uint32_t i = threadIdx.x; i < kEntries; i += blockDim.x) exits[(size_t)c * kEntries + i] = nxt[i] - kChunk;
@@ -1196,12 +1623,17 @@ chunk_exit_kernel(const uint32_t* __restrict__ nx, uint32_t n, uint16_t* __restr
         jump[i] = (uint16_t)(p < n ? i + nx_step(nx_clean(nx[p])) : kChunk);  // <= 4095 + 515
     }
     __syncthreads();
+    // Pointer jumping in place.  A thread may read jump[t] while its owner replaces it: 16-bit shared-memory accesses
+    // are single transactions, and both the old and the new value are "first arrival at or past some point of t's
+    // sub-chunk reached from t", so whichever is seen the invariant holds and the rounds only end when nothing moved
+    // (racecheck reports the read/write pair; a barrier-separated variant costs 0.2 - 1.2 ms per 256 MiB, measured).
+    volatile uint16_t* vj = jump;
     while (true) {
         bool pending = false;
         for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
-            const uint32_t t = jump[i];
+            const uint32_t t = vj[i];
             if (t < (i | (kSub - 1)) + 1) {  // still inside i's sub-chunk
-                jump[i] = jump[t];           // racing reads see some power of f: still correct
+                vj[i] = vj[t];
                 pending = true;
             }
         }
@@ -1284,15 +1716,22 @@ orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* _
     }
     for (uint32_t i = threadIdx.x; i < kChunk / 32; i += kMarkThreads) bits[i] = 0;
     __syncthreads();
-    while (!jumps) {
+    while (!jumps) {  // one read phase and one write phase per round
         bool pending = false;
-        for (uint32_t i = threadIdx.x; i < kChunk; i += kMarkThreads) {
-            const uint32_t t = jump[i];
+        uint32_t nv[kChunk / kMarkThreads];
+#pragma unroll
+        for (uint32_t k = 0; k < kChunk / kMarkThreads; k++) {
+            const uint32_t i = threadIdx.x + k * kMarkThreads;
+            uint32_t t = jump[i];
             if (t < (i | (kSub - 1)) + 1) {  // still inside i's sub-chunk
-                jump[i] = jump[t];           // racing reads see some power of f: still correct
+                t = jump[t];
                 pending = true;
             }
+            nv[k] = t;
         }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t k = 0; k < kChunk / kMarkThreads; k++) jump[threadIdx.x + k * kMarkThreads] = (uint16_t)nv[k];
         if (!__syncthreads_or(pending)) break;
     }
     if (threadIdx.x == 0) {
@@ -1442,6 +1881,9 @@ static int g_sparse_variant = 0;  // see lz77_sparse_range
 static uint32_t g_link_run = 128;  // longest run of hash tiles per CTA (FB200_LINK_RUN): each run pays 4 warm-up tiles
 static int g_exit_threads = 128;   // chunk_exit_kernel block size (FB200_EXIT_THREADS): small blocks hide the load latency better
 static SparseTune g_sparse_tune{1, 1, 1};
+static int g_sparse_roll = 0;      // FB200_SPARSE_ROLL: 0 = chunk kernel only (default: faster), 16 / 32 = rolling kernel with a seed every 16 / 32 positions
+static uint32_t g_sparse_roll_k = 1;  // runs per SM (dynamic hand-out when > 1)
+static uint32_t g_sparse_roll_prio = 0;  // see sparse_roll_kernel
 static void lz77_init_once() {
     // function attributes are per device: a process may hold contexts on several GPUs
     static bool done[64] = {};
@@ -1463,6 +1905,8 @@ static void lz77_init_once() {
     FB_SPARSE_ATTR(16, 8, false);
     FB_SPARSE_ATTR(32, 8, true);
 #undef FB_SPARSE_ATTR
+    cudaFuncSetAttribute(sparse_roll_kernel<kSparseW, 16, kSparseThreads, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSrSmem);
+    cudaFuncSetAttribute(sparse_roll_kernel<kSparseW, 32, kSparseThreads, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSrSmem);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (knobs_read) return;
     knobs_read = true;
@@ -1480,6 +1924,13 @@ static void lz77_init_once() {
     // FB200_SPARSE="variant[,pend_at,done_at,refill_at]": shape and pacing of the sparse parse kernel
     if (const char* lr = getenv("FB200_LINK_RUN")) g_link_run = atoi(lr) >= 4 && atoi(lr) <= 4096 ? (uint32_t)atoi(lr) : 128;
     if (const char* et = getenv("FB200_EXIT_THREADS")) g_exit_threads = atoi(et) >= 128 && atoi(et) <= 1024 ? atoi(et) : 128;
+    if (const char* sr = getenv("FB200_SPARSE_ROLL")) {  // "G[,runs per SM]"
+        int g = 16, k = 1, pr = 0;
+        const int got = sscanf(sr, "%d,%d,%d", &g, &k, &pr);
+        if (got == 3 && pr >= 0) g_sparse_roll_prio = (uint32_t)pr;
+        if (got >= 1) g_sparse_roll = (g == 0 || g == 16 || g == 32) ? g : 16;
+        if (got >= 2 && k >= 1 && k <= 16) g_sparse_roll_k = (uint32_t)k;
+    }
     if (const char* sp = getenv("FB200_SPARSE")) {
         int v = 0, p = 0, d = 0, r = 0;
         const int got = sscanf(sp, "%d,%d,%d,%d", &v, &p, &d, &r);
@@ -1550,17 +2001,40 @@ cudaError_t lz77_link_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t 
 // chunk_fail[c] is set when orbits leaving chunk c were not seen to join the next chunk's seeds.
 uint32_t lz77_sparse_chunk() { return kSparseT; }
 uint32_t lz77_sparse_lookahead() { return kSparseW + kSpHalo + 272; }
+uint32_t lz77_sparse_link_ahead() { return kSparseW + kSpHalo + kSrLook + kSrEpoch; }
 cudaError_t lz77_sparse_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t first_chunk, uint32_t end_chunk, uint32_t n,
                               const LevelArgs& lv, uint32_t* chunk_fail, uint32_t* flags, cudaStream_t st, PhaseTimer* pt,
-                              uint32_t begin) {
+                              uint32_t begin, uint32_t* run_counter) {
     // begin > 0: b.nx is relative to the segment start (like every table after the match search)
     lz77_init_once();
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
     if (end_chunk <= first_chunk) return cudaSuccess;
+    // The interior of the stream goes to the rolling kernel (runs of whole chunks, one persistent CTA per SM); the
+    // chunks whose window would reach past the end of the stream, unaligned buffers and very short ranges keep the
+    // chunk kernel.  Both evaluate the same seeds with the same hand-over check, so they mix freely.
+    if (g_sparse_roll && run_counter && (((uintptr_t)d_in | (uintptr_t)b.link) & 15) == 0) {
+        const uint64_t need = (uint64_t)kSparseW + kSpHalo + kSrLook + kSrEpoch;  // keeps the last epoch load inside the stream
+        const uint32_t roll_end = n > need ? min(end_chunk, (uint32_t)((n - need) / kSparseT)) : 0;
+        if (roll_end >= first_chunk + 2) {
+            const uint32_t nch = roll_end - first_chunk;
+            uint32_t nruns = min(nch / 2, (uint32_t)g_num_sms * g_sparse_roll_k);
+            if (nruns > (uint32_t)g_num_sms && nch / nruns < 8) nruns = min(nch / 2, (uint32_t)g_num_sms);  // short runs: one per SM
+            cudaMemsetAsync(run_counter, 0, sizeof(uint32_t), st);
+            const uint32_t rgrid = min(nruns, (uint32_t)g_num_sms);
+            if (g_sparse_roll == 32) sparse_roll_kernel<kSparseW, 32, kSparseThreads, 8><<<rgrid, kSparseThreads, kSrSmem, st>>>(d_in, begin, first_chunk, roll_end, nruns, n, b.link, lv, b.nx - begin, chunk_fail, flags, run_counter, g_sparse_roll_prio);
+            else sparse_roll_kernel<kSparseW, 16, kSparseThreads, 8><<<rgrid, kSparseThreads, kSrSmem, st>>>(d_in, begin, first_chunk, roll_end, nruns, n, b.link, lv, b.nx - begin, chunk_fail, flags, run_counter, g_sparse_roll_prio);
+            first_chunk = roll_end;
+            if (end_chunk <= first_chunk) {
+                pt->mark(st, kPhSparse);
+                return cudaGetLastError();
+            }
+        }
+    }
     const uint32_t grid = end_chunk - first_chunk;
 #define FB_SPARSE(G, ST) sparse_parse_kernel<kSparseT, kSparseW, G, kSparseThreads, 1, ST, false><<<grid, kSparseThreads, SparseCfg<kSparseT, kSparseW>::kSmem, st>>>(d_in, begin, first_chunk, nullptr, n, b.link, lv, g_sparse_tune, b.nx - begin, chunk_fail, flags)
-    switch (g_sparse_variant) {
+    // the seeds of a run's overlap must be seeds of whatever evaluates the next chunk: same spacing as the rolling kernel
+    switch (g_sparse_variant == 0 && g_sparse_roll == 16 && run_counter ? 2 : g_sparse_variant) {
         case 1: FB_SPARSE(32, 4); break;
         case 2: FB_SPARSE(16, 8); break;
         default: FB_SPARSE(32, 8); break;
@@ -1597,7 +2071,7 @@ cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin
     n -= begin;
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
     const uint32_t ngroups = (nchunks + kGroup - 1) / kGroup;
-    lazy_exit_kernel<<<nchunks, 256, 0, st>>>(b.r_full, b.r_quarter, n, lv, b.nx, b.exits);
+    lazy_exit_kernel<<<nchunks, kLazyThreads, 0, st>>>(b.r_full, b.r_quarter, n, lv, b.nx, b.exits);
     pt->mark(st, kPhChunkExit);
     group_exit_kernel<<<ngroups, 544, 0, st>>>(b.exits, nchunks, b.gexits);
     group_entry_kernel<<<1, 32, 0, st>>>(b.gexits, ngroups, b.gentry);

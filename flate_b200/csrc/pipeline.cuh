@@ -102,10 +102,12 @@ cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32
 cudaError_t lz77_link_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t link_from, uint32_t range_end, uint32_t n,
                             cudaStream_t st, PhaseTimer* pt = nullptr, const uint32_t* d_skip = nullptr, uint32_t nskip = 0);
 uint32_t lz77_sparse_chunk();      // positions per sparse-parse CTA
-uint32_t lz77_sparse_lookahead();  // positions past a chunk's end that must be linked and resident
+uint32_t lz77_sparse_lookahead();  // positions past a chunk's end that the chunk's CTA reads (overlap + lazy halo + compare slack)
+uint32_t lz77_sparse_link_ahead(); // positions past a chunk range's end that must be linked and resident (whole load epochs)
+// run_counter: one device word for the rolling kernel's run hand-out (nullptr: chunk kernel only)
 cudaError_t lz77_sparse_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_t first_chunk, uint32_t end_chunk, uint32_t n,
                               const LevelArgs& lv, uint32_t* chunk_fail, uint32_t* flags, cudaStream_t st, PhaseTimer* pt = nullptr,
-                              uint32_t begin = 0);
+                              uint32_t begin = 0, uint32_t* run_counter = nullptr);
 // repair after a failed coverage check: evaluate every position of the listed chunks
 cudaError_t lz77_sparse_dense_chunks(const Lz77Buffers& b, const uint8_t* d_in, const uint32_t* chunk_list, uint32_t count, uint32_t n,
                                      const LevelArgs& lv, uint32_t* chunk_fail, uint32_t* flags, cudaStream_t st,

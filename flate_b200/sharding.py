@@ -81,34 +81,52 @@ def compress_stream_sharded(ctx, d_in, n, d_out, level=6, container=0, root=0, k
     # the legacy default stream has handle 0, which the C ABI reads as "the context's own stream": make sure
     # torch's work on the inputs is complete before the library touches them (and again before stage 2)
     cur.synchronize()
-    ok = ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level, stream=sp)
-    if world > 1:
-        flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=d_in.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        ok = int(flag.item()) == 0
-    if not ok:  # periodic data somewhere: every rank falls back to the dense tables for its range
-        ctx.set_parse_mode(1)
+    from .api import RetryDense
+    out_len = 0
+    for dense in (False, True):   # second pass only when the sparse parse could not vouch for its coverage
+        if dense:
+            ctx.set_parse_mode(1)
         try:
             cur.synchronize()
-            ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level, stream=sp)
+            ok = ctx.shard_search(d_in.data_ptr(), n, lo, hi, nx.data_ptr(), level=level, stream=sp)
         finally:
-            ctx.set_parse_mode(0)
-    if world > 1:
-        tail = nx[rank * per + per: rank * per + per + ov].clone()   # this rank's entries past its range
-        tails = torch.empty(world * ov, dtype=torch.int32, device=d_in.device)
-        dist.all_gather_into_tensor(tails, tail)
-        dist.all_gather_into_tensor(nx[:world * per], nx[rank * per:(rank + 1) * per].clone())
-        if rank == root and ok:
-            for r in range(world - 1):
-                merge_overlap(nx[(r + 1) * per:(r + 1) * per + ov], tails[r * ov:(r + 1) * ov])
-    if keep is not None:
-        keep["nx"], keep["per"] = nx, per   # development aid
-    if rank != root:
-        return 0
-    cur.synchronize()
-    cap = d_out.numel()
-    return ctx.shard_finish(d_in.data_ptr(), n, nx.data_ptr(), d_out.data_ptr(), cap, level=level, container=container,
-                            stream=sp)
+            if dense:
+                ctx.set_parse_mode(0)
+        if world > 1:
+            flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=d_in.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            ok = int(flag.item()) == 0
+        if not ok and not dense:
+            continue   # periodic data somewhere: every rank falls back to the dense tables for its range
+        if world > 1:
+            tail = nx[rank * per + per: rank * per + per + ov].clone()   # this rank's entries past its range
+            tails = torch.empty(world * ov, dtype=torch.int32, device=d_in.device)
+            dist.all_gather_into_tensor(tails, tail)
+            dist.all_gather_into_tensor(nx[:world * per], nx[rank * per:(rank + 1) * per].clone())
+            if rank == root and not dense:
+                for r in range(world - 1):
+                    merge_overlap(nx[(r + 1) * per:(r + 1) * per + ov], tails[r * ov:(r + 1) * ov])
+        if keep is not None:
+            keep["nx"], keep["per"] = nx, per   # development aid
+        # stage 2 on the root; it may still find the joined table incomplete (FB200_RETRY_DENSE), in which case
+        # every rank has to repeat stage 1 densely: the verdict is broadcast so that the ranks stay in step
+        retry = 0
+        if rank == root:
+            cur.synchronize()
+            try:
+                out_len = ctx.shard_finish(d_in.data_ptr(), n, nx.data_ptr(), d_out.data_ptr(), d_out.numel(), level=level,
+                                           container=container, stream=sp)
+            except RetryDense:
+                if dense:
+                    raise
+                retry = 1
+        if world > 1:
+            flag = torch.tensor([retry], dtype=torch.int32, device=d_in.device)
+            dist.broadcast(flag, src=root)
+            retry = int(flag.item())
+        if not retry:
+            break
+    return out_len if rank == root else 0
 
 
 # ---- huffman-only / store: ONE stream sharded by 65535-byte block ranges ----

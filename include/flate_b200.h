@@ -93,6 +93,7 @@ const char* fb200_profile_phase_name(int phase);
 int fb200_profile_read(const fb200_ctx* ctx, double* ms, uint64_t* count, int n);
 
 /* ---- one-shot, host buffers (H2D and D2H inside) ---- */
+/* Upper bound of the compressed size of n bytes in any mode, container header and footer included. */
 size_t fb200_compress_bound(size_t n, int mode);
 int fb200_compress(fb200_ctx* ctx, int container, int mode, const uint8_t* in, size_t n, uint8_t* out, size_t cap,
                    size_t* out_len);
@@ -102,7 +103,8 @@ int fb200_decompress(fb200_ctx* ctx, int container, const uint8_t* in, size_t n,
                      size_t* out_len, size_t* consumed);
 
 /* ---- device-resident variants: d_in/d_out are device pointers on ctx's GPU; `stream` is a
- * cudaStream_t (NULL = the context's own stream).  d_out must hold fb200_compress_bound() bytes. ---- */
+ * cudaStream_t (NULL = the context's own stream).  d_out must hold fb200_compress_bound() bytes and be 16-byte
+ * aligned (any cudaMalloc pointer is; FB200_INVALID_ARGUMENT otherwise: the packer writes whole words). ---- */
 int fb200_compress_device(fb200_ctx* ctx, int container, int mode, const void* d_in, size_t n, void* d_out, size_t cap,
                           size_t* out_len, void* stream);
 /* k independent members (e.g. a multi-member gzip file with a member index): member i occupies
@@ -125,9 +127,10 @@ int fb200_decompress_members(fb200_ctx* ctx, int container, const uint8_t* in, c
  *   - `from` and `to` multiples of fb200_shard_align() (`to` may also be n): the sparse parse runs; it writes
  *     d_nx[from .. min(n, to + fb200_shard_overlap())).  The entries past `to` continue this range's orbits into
  *     the next rank's range until they join orbits the next rank evaluates itself.
- *     d_in must be readable on [max(0, from - 32768), min(n, to + fb200_shard_overlap() + 8720)).
+ *     d_in must be readable on [max(0, from - 65536), min(n, to + fb200_shard_overlap() + 8720)): matches reach 32 KiB
+ *     back, and the hash chains of that history are rebuilt from another 32 KiB before it.
  *   - otherwise (`from` a multiple of 8192), or after fb200_ctx_set_parse_mode(ctx, 1): dense tables, writes
- *     d_nx[from .. to); d_in readable on [max(0, from - 32768), min(n, to + 8464)).
+ *     d_nx[from .. to); d_in readable on [max(0, from - 65536), min(n, to + 8464)).
  * The ranks exchange their tables (NCCL all-gather of the [from, to) parts; for a position covered by two ranks
  * any evaluated entry is the right one) and stage 2 runs on one rank over the joined table: lazy-parse orbit,
  * block cut, Huffman construction, bit-pack.  The result is byte-identical to fb200_compress_device on the

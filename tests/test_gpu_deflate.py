@@ -8,7 +8,7 @@ import zlib
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, read_golden
+from conftest import GOLDEN, ROOT, read_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -528,3 +528,25 @@ def test_block_range_sharded_stream_equals_whole(ctx, o, mode):
                     total.to_bytes(4, "little") + (n & 0xffffffff).to_bytes(4, "little") if container == 1 else total.to_bytes(4, "big"))
                 got = final.cpu().numpy().tobytes() + footer
                 assert got == want, (n, container, world, first_diff(got, want))
+
+
+@pytest.mark.gpu
+def test_rolling_sparse_parse_is_bit_exact():
+    """The opt-in rolling form of the sparse parse (FB200_SPARSE_ROLL, read once per process) gives the oracle's bytes:
+    text with a zero run and a random burst, long enough for several runs per CTA plus a chunk-kernel tail."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "import flate_b200; from flate_b200 import synth; from oracle import oracle as o\n"
+        "d = synth.enwik_like(6 << 20, seed=77).copy()\n"
+        "d[1000000:1300000] = 0\n"
+        "d[3000000:3100000] = np.random.default_rng(5).integers(0, 256, 100000, dtype=np.uint8)\n"
+        "d = d.tobytes()[:6 * 1024 * 1024 - 12345]\n"
+        "ctx = flate_b200.Context(0)\n"
+        "for lvl in (6, 4, 9):\n"
+        "    assert ctx.compress(d, flate_b200.RAW, lvl) == o.compress(d, o.RAW, lvl), lvl\n"
+        "print('rolling ok')\n" % ROOT)
+    env = dict(os.environ, FB200_SPARSE_ROLL="16,2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "rolling ok" in r.stdout, r.stderr[-2000:]

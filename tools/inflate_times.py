@@ -64,4 +64,10 @@ for nmem in counts:
     kms = ph[0] / max(1, ph[1])
     print("inflate %4d members x 1 MiB: %.3f ms/call, kernel %.3f ms -> %.1f MB/s out (kernel %.1f MB/s)"
           % (nmem, dt, kms, nmem * MB / dt / 1e3, nmem * MB / kms / 1e3), flush=True)
+    if os.environ.get("FB200_PROFILE_RANGE"):  # ncu --profile-from-start off: capture exactly this launch
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        ctx.decompress_members_device(d_blob.data_ptr(), offs, lens, d_plain.data_ptr(), ooff, ocap, flate_b200.GZIP, stream=sp)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     del d_blob, d_plain
