@@ -230,6 +230,7 @@ def main():
     ap.add_argument("--skip-c4", action="store_true")
     ap.add_argument("--skip-c5", action="store_true")
     ap.add_argument("--skip-mixed", action="store_true")
+    ap.add_argument("--skip-stream", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -597,6 +598,56 @@ def main():
                                      "sample": "the whole stream, one pass; output identical"}
         del d_tar
 
+    # =====================================================================================================
+    # streaming: the same bytes through Compressor.write in 1 MiB pieces
+    # =====================================================================================================
+    streaming = None
+    if world == 1 and not args.skip_stream:
+        import psutil
+        from flate_b200 import _lib as fb_lib
+        sink = torch.empty(4 * cap + 64, dtype=torch.uint8)   # where the writer puts what it is handed
+        sink_ptr, sink_len = sink.data_ptr(), [0]
+
+        def on_write(_user, data, nbytes):
+            C.memmove(sink_ptr + sink_len[0], data, nbytes)
+            sink_len[0] += nbytes
+            return 0
+
+        cb = fb_lib.WRITE_FN(on_write)
+        piece = MIB
+
+        def stream_once(passes):
+            sink_len[0] = 0
+            h = C.c_void_p()
+            rc = lib.fb200_deflate_create(ctx.h, flate_b200.RAW, level, cb, None, C.byref(h))
+            assert rc == 0, rc
+            for _ in range(passes):
+                for pos in range(0, n, piece):
+                    rc = lib.fb200_deflate_write(h, h_in.data_ptr() + pos, min(piece, n - pos))
+                    assert rc == 0, rc
+            rc = lib.fb200_deflate_finish(h)
+            assert rc == 0, rc
+            lib.fb200_deflate_destroy(h)
+            return sink_len[0]
+
+        got1 = stream_once(1)   # warm-up, and the parity check: the stream equals the one-shot stream (itself equal to the oracle's)
+        same = got1 == out_len and sink[:got1].numpy().tobytes() == compressed
+        assert same, "streaming compressor: output differs from the one-shot stream"
+        proc = psutil.Process()
+        rss0 = proc.memory_info().rss
+        passes = max(1, (1 << 30) // n)
+        t0 = time.perf_counter()
+        got4 = stream_once(passes)
+        dt = time.perf_counter() - t0
+        rss1 = proc.memory_info().rss
+        streaming = {"metric": "deflate L6 MB/s in, Compressor.write in 1 MiB pieces", "value": round(passes * n / 1e6 / dt, 1), "unit": "MB/s",
+                     "workload": "%d MiB (the C2 text %d times) through fb200_deflate_write in 1 MiB pieces from pinned host memory, "
+                                 "output handed to a writer callback that copies it away" % (passes * n // MIB, passes),
+                     "compressed_bytes": got4, "fraction_of_one_shot_e2e": round(passes * n / 1e6 / dt / e2e_value, 3),
+                     "host_rss_growth_mib": round((rss1 - rss0) / MIB, 1),
+                     "identical_to_one_shot_stream": bool(same), "checked_on": "%d MiB, one pass" % (n // MIB)}
+        del sink
+
     # free the C2 buffers before the 4 GiB leg
     del d_outs, gather_bufs
 
@@ -736,6 +787,7 @@ def main():
         "c4_level9": c4,
         "c5_huffman": c5,
         "mixed": mixed,
+        "streaming": streaming,
         "single_stream": single,
     }
     emit(line)

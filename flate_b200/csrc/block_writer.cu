@@ -19,9 +19,10 @@ __constant__ uint8_t c_codegen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11
 // ------------------------------------------------------------------------------------------
 __global__ void plan_level_blocks_kernel(const uint32_t* __restrict__ total_tokens, const uint32_t* __restrict__ cut_rp,
                                          uint32_t begin, uint32_t n, uint32_t max_blocks, uint32_t final_flush, BlockPlan* __restrict__ plans,
-                                         uint32_t* __restrict__ nblocks_out) {
+                                         uint32_t* __restrict__ nblocks_out, uint32_t fp0) {
     const uint32_t T = *total_tokens;
-    const uint32_t ntok_blocks = T / kTokensPerBlock + 1;  // last one may be empty (deflate.zig:227-230,344)
+    // last one may be empty (deflate.zig:227-230,344); a part of a stream only writes the blocks that are complete
+    const uint32_t ntok_blocks = final_flush == 2 ? T / kTokensPerBlock : T / kTokensPerBlock + 1;
     const uint32_t nblocks = ntok_blocks + (final_flush ? 0 : 1);
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) *nblocks_out = nblocks < max_blocks ? nblocks : max_blocks;
@@ -31,12 +32,12 @@ __global__ void plan_level_blocks_kernel(const uint32_t* __restrict__ total_toke
         pl.tok_begin = b * kTokensPerBlock;
         pl.tok_count = min(kTokensPerBlock, T - pl.tok_begin);
         // cut_rp is relative to the segment start; fp after a flush is the flush point (SlidingWindow.zig:113)
-        const uint32_t rp = (b + 1 < ntok_blocks) ? begin + cut_rp[b] : n;
-        const uint32_t fp = b == 0 ? begin : begin + cut_rp[b - 1];
+        const uint32_t rp = (b + 1 < ntok_blocks || final_flush == 2) ? begin + cut_rp[b] : n;
+        const uint32_t fp = b == 0 ? fp0 : begin + cut_rp[b - 1];
         pl.in_begin = fp;
         pl.in_len = rp - fp;
         pl.has_input = fp >= slide_base(rp, n);  // fp < 0 after a slide => null (SlidingWindow.zig:121)
-        pl.eof = (b + 1 == ntok_blocks) && final_flush;
+        pl.eof = (b + 1 == ntok_blocks) && final_flush == 1;
         pl.kind = kWrite;
     } else {  // sync marker: empty stored block (deflate.zig:276-278)
         pl.tok_begin = 0; pl.tok_count = 0; pl.in_begin = 0; pl.in_len = 0; pl.has_input = 1; pl.eof = 0; pl.kind = 3;
@@ -813,9 +814,10 @@ pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
 // launchers
 // ------------------------------------------------------------------------------------------
 cudaError_t plan_level_blocks(const uint32_t* total_tokens, const uint32_t* cut_rp, uint32_t begin, uint32_t n,
-                              uint32_t max_blocks, uint32_t final_flush, BlockPlan* plans, uint32_t* nblocks, cudaStream_t st) {
+                              uint32_t max_blocks, uint32_t final_flush, BlockPlan* plans, uint32_t* nblocks, cudaStream_t st,
+                              uint32_t fp0) {
     plan_level_blocks_kernel<<<(max_blocks + 127) / 128, 128, 0, st>>>(total_tokens, cut_rp, begin, n, max_blocks, final_flush,
-                                                                       plans, nblocks);
+                                                                       plans, nblocks, fp0);
     return cudaGetLastError();
 }
 cudaError_t histogram_tokens(const uint32_t* tokens, const BlockPlan* plans, const uint32_t* nblocks_dev,

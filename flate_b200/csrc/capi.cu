@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -115,6 +117,9 @@ struct fb200_ctx {
     DevBuf<uint64_t> m_desc;        // member descriptors / results
     DevBuf<uint8_t> m_scratch;      // work counter + per-CTA match queues of the member-parallel inflate kernel
     int sm_count = 148;
+    // One call at a time works on a context's buffers: every entry point that uses them takes this lock, and so does
+    // the worker thread of a streaming compressor while a part of its stream is being compressed.
+    std::recursive_mutex mu;
     // block-range sharded simple stream: state between the plan and the pack stage
     const uint8_t* shard_in = nullptr;
     uint32_t shard_blocks = 0;
@@ -330,6 +335,31 @@ static int sparse_repair(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in
     return FB200_OK;
 }
 
+// State a streaming compressor carries from one part of its stream to the next (level modes), all positions relative
+// to the device window that d_in points at.  A part starts at a clean arrival of the lazy parse (so its parse starts
+// at offset 0), ends on its own 4096-position chunk grid at parse_end, and writes complete 32768-token blocks only:
+// the tokens of the block left open stay at the front of the context's token buffer, the output continues at the
+// bit where the previous part stopped.
+struct PartCarry {
+    // in
+    uint32_t* nx = nullptr;      // the stream's lazy-step table, entry of position p at nx[p] (kept across parts)
+    uint32_t carry_tok = 0;      // tokens of the open block at the front of the token buffer
+    bool has_fp = false;         // fp0 valid (else the tokens start a segment: fp = begin)
+    uint32_t fp0 = 0;            // position of the last block cut
+    uint32_t bit_phase = 0;      // the output starts at this bit of its first byte (bits below it stay zero)
+    size_t link_from = SIZE_MAX; // links are in place below this position (SIZE_MAX: from `begin`)
+    size_t chunks_from = SIZE_MAX;  // sparse-parse chunks below this one are evaluated (SIZE_MAX: from begin's chunk)
+    size_t parse_end = 0;        // 0: flush / finish over [begin, n).  Else a part: tokens of the arrivals in
+    size_t chunk_end = 0;        //    [begin, parse_end), sparse chunks up to chunk_end, links up to link_to
+    size_t link_to = 0;
+    // out
+    uint32_t exit = 0;           // first arrival at or past parse_end, relative to it
+    uint32_t leftover = 0;       // tokens of the open block (already moved to the front of the token buffer)
+    bool cut = false;            // a block was completed ...
+    uint32_t last_rp = 0;        // ... and this is the position of the last cut
+    uint64_t total_bits = 0;     // end of the written bits, counted from bit 0 of the output's first byte
+};
+
 // Runs the deflate body of stream positions [begin, n) on the device.  One-shot calls pass begin = 0
 // and get the container header in front; the streaming compressor passes the flush point and gets
 // just the blocks of the segment (plus the sync marker when !final_flush).  Returns the end of the
@@ -338,7 +368,9 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
                                const uint32_t* d_skip, uint32_t nskip, uint8_t* d_out, size_t cap, size_t* end_bytes,
                                bool final_flush, bool with_header, cudaStream_t st, const uint8_t* h_src = nullptr,
                                uint8_t* h_dst = nullptr, size_t h_cap = 0, const uint32_t* d_nx_given = nullptr,
-                               int redo = 0) {
+                               int redo = 0, PartCarry* carry = nullptr) {
+    // carry != nullptr: streaming compressor (see PartCarry); redo == 3 then means "evaluate every position of the
+    // chunks concerned" (the coverage check of the sparse parse failed on the first attempt).
     // redo: 1 = links and a repaired nx table are in place, only parse again; 2 = dense match tables
     // d_nx_given != nullptr: the lazy-step table of the whole stream was produced elsewhere (position-sharded
     // search on several GPUs); only the parse and the block writer run here.
@@ -357,11 +389,14 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     const uint32_t* tokens = nullptr;
     LevelArgs lv;
     bool sparse = false;
+    const bool part = carry && carry->parse_end != 0;
+    const uint32_t fmode = part ? 2u : final_flush ? 1u : 0u;  // plan_level_blocks / plan_simple_blocks_kernel
+    uint32_t carry_groups = 0;
     if (level_args(mode, lv)) {
         if (n > (1ull << 31)) return FB200_INVALID_ARGUMENT;  // single-stream position space is 32-bit
         int rc = ensure_lz77(c, n);
         if (rc) return rc;
-        max_blocks = (uint32_t)((n - begin) / kTokensPerBlock + 3);
+        max_blocks = (uint32_t)((n - begin + (carry ? carry->carry_tok : 0)) / kTokensPerBlock + 3);
         if ((rc = ensure_blocks(c, max_blocks))) return rc;
         Lz77Buffers b = lz77_view(c);
         c->timer.begin(st);
@@ -377,7 +412,48 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
                 kSlab = (size_t)b2 << 20;
             }
         }
-        if (redo == 1) {
+        if (carry) {
+            const uint32_t T = lz77_sparse_chunk();
+            const size_t pend = part ? carry->parse_end : n;
+            const size_t c_from = carry->chunks_from == SIZE_MAX ? begin / T : carry->chunks_from;
+            const size_t c_to = part ? carry->chunk_end : (n + T - 1) / T;
+            uint32_t* flags = c->d_scalars + kSparseFlagIdx;
+            sparse = true;
+            b.nx = carry->nx + begin;  // the kernels index the table from the segment start
+            FB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(uint32_t), st));
+            if (pend == begin) {
+                // an empty segment: only the carried tokens, if any
+            } else if (redo != 3) {
+                // entries below the previous run's overlap are in place; what this run can write starts out "not evaluated"
+                const size_t ms_from = carry->chunks_from == SIZE_MAX ? begin : c_from * T + 1024;
+                const size_t ms_to = part ? (c_to * T + 1024 < n ? c_to * T + 1024 : n) : n;
+                if (ms_to > ms_from) FB_CUDA_CHECK(cudaMemsetAsync(carry->nx + ms_from, 0xFF, (ms_to - ms_from) * sizeof(uint32_t), st));
+                const size_t l_from = carry->link_from == SIZE_MAX ? begin : carry->link_from;
+                const size_t l_to = part ? carry->link_to : n;
+                if (l_to > l_from) FB_CUDA_CHECK(lz77_link_range(b, d_in, (uint32_t)l_from, (uint32_t)l_to, (uint32_t)n, st, &c->timer, d_skip, nskip));
+                if (c_to > c_from)
+                    FB_CUDA_CHECK(lz77_sparse_range(b, d_in, (uint32_t)c_from, (uint32_t)c_to, (uint32_t)n, lv, c->chunk_fail.p, flags, st, &c->timer,
+                                                    (uint32_t)begin, c->d_scalars + kRunCounterIdx));
+                c->launches += 2;
+            } else {
+                // every position of the chunks the parse walks: nothing is left to the speculation
+                std::vector<uint32_t> list;
+                for (size_t ch = begin / T; ch < c_to; ch++) list.push_back((uint32_t)ch);
+                if (!list.empty()) {
+                    FB_CUDA_CHECK(c->chunk_list.ensure(list.size()));
+                    FB_CUDA_CHECK(cudaMemcpyAsync(c->chunk_list.p, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+                    FB_CUDA_CHECK(cudaStreamSynchronize(st));  // `list` is pageable and about to go out of scope
+                    FB_CUDA_CHECK(lz77_sparse_dense_chunks(b, d_in, c->chunk_list.p, (uint32_t)list.size(), (uint32_t)n, lv, c->chunk_fail.p, flags, st,
+                                                           &c->timer, (uint32_t)begin));
+                    FB_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(uint32_t), st));  // hand-over failures between dense chunks mean nothing
+                }
+                c->launches += 1;
+            }
+            FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in + begin, (uint32_t)(pend - begin), lv, st, &c->timer, flags, carry->carry_tok));
+            const uint32_t nchunks = (uint32_t)((pend - begin + kChunk - 1) / kChunk);
+            carry_groups = (nchunks + kGroup - 1) / kGroup;
+            c->launches += pend > begin ? 7 : 0;
+        } else if (redo == 1) {
             sparse = true;
             FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
             FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in + begin, (uint32_t)(n - begin), lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
@@ -449,24 +525,26 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
             FB_CUDA_CHECK(lz77_tokenize(b, d_in, (uint32_t)begin, (uint32_t)n, d_skip, nskip, lv, st, &c->timer));
             c->launches += n > begin ? 9 : 0;
         }
-        FB_CUDA_CHECK(plan_level_blocks(b.total_tokens, b.cut_rp, (uint32_t)begin, (uint32_t)n, max_blocks,
-                                        final_flush ? 1 : 0, c->plans.p, nblocks_dev, st));
+        FB_CUDA_CHECK(plan_level_blocks(b.total_tokens, b.cut_rp, (uint32_t)begin, (uint32_t)n, max_blocks, fmode, c->plans.p, nblocks_dev, st,
+                                        carry && carry->has_fp ? carry->fp0 : (uint32_t)begin));
         FB_CUDA_CHECK(histogram_tokens(b.tokens, c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, st));
         c->launches += 2;
         c->timer.mark(st, kPhHist);
         tokens = b.tokens;
     } else if (mode == FB200_MODE_HUFFMAN || mode == FB200_MODE_STORE) {
-        const uint64_t nb64 = (n - begin) / kMaxStore + 1;
-        if (nb64 > 0x7ffffff0ull) return FB200_INVALID_ARGUMENT;
+        // a part of a stream is a whole number of slices; flush and finish close the segment with its last, shorter
+        // (possibly empty) slice
+        const uint64_t nb64 = part ? (n - begin) / kMaxStore : (n - begin) / kMaxStore + 1;
+        if (nb64 > 0x7ffffff0ull || (part && (nb64 == 0 || (n - begin) % kMaxStore))) return FB200_INVALID_ARGUMENT;
         const uint32_t nslices = (uint32_t)nb64;
-        max_blocks = nslices + (final_flush ? 0 : 1);
+        max_blocks = nslices + (fmode ? 0 : 1);
         int rc = ensure_blocks(c, max_blocks);
         if (rc) return rc;
         if (h_src && n > begin) FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in) + begin, h_src, n - begin, cudaMemcpyHostToDevice, st));
         c->timer.begin(st);
         plan_simple_blocks_kernel<<<(max_blocks + 255) / 256, 256, 0, st>>>(begin, n, nslices,
                                                                             mode == FB200_MODE_HUFFMAN ? kHuffmanBlock : 3u,
-                                                                            final_flush ? 1 : 0, c->plans.p, nblocks_dev);
+                                                                            fmode, c->plans.p, nblocks_dev);
         FB_CUDA_CHECK(cudaGetLastError());
         c->launches += 1;
         if (mode == FB200_MODE_HUFFMAN) {
@@ -479,7 +557,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     }
     FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, c->descs.p, st));
     c->timer.mark(st, kPhBuild);
-    FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, hdr * 8, total_bits_dev, st));
+    FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, hdr * 8 + (carry ? carry->bit_phase : 0), total_bits_dev, st));
     zero_output_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<uint32_t*>(d_out), total_bits_dev, cap / 4);
     FB_CUDA_CHECK(cudaGetLastError());
     if (hdr && container == FB200_GZIP) FB_CUDA_CHECK(cudaMemcpyAsync(d_out, kGzipHeader, 10, cudaMemcpyHostToDevice, st));
@@ -519,8 +597,8 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     c->launches += 4;
     // container checksum of the plain bytes on the device (container.zig:168-206), SURVEY.md §8(f) rank 1
     uint32_t* sum_dev = c->d_scalars + 16;
-    if (!final_flush) {
-        // the footer is only written by finish()
+    if (!final_flush || carry) {
+        // the footer is only written by finish(); a streaming compressor sums its stream part by part itself
     } else if (container == FB200_GZIP) {
         FB_CUDA_CHECK(crc32_device(d_in, n, sum_dev, st));
         c->launches += n ? 1 : 0;
@@ -528,12 +606,45 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         FB_CUDA_CHECK(adler32_device(d_in, n, sum_dev, reinterpret_cast<uint64_t*>(c->d_scalars + 24), st));
         c->launches += n ? 2 : 1;
     }
-    if (container != FB200_RAW && final_flush) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 8, sum_dev, 4, cudaMemcpyDeviceToHost, st));
+    if (container != FB200_RAW && final_flush && !carry) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 8, sum_dev, 4, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, total_bits_dev, 8, cudaMemcpyDeviceToHost, st));
     if (sparse || d_nx_given) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 9, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
+    if (carry) {  // token count | block count, and where the orbit left the part
+        FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 10, c->d_scalars, 8, cudaMemcpyDeviceToHost, st));
+        c->h_scalars[11] = 0;
+        if (tokens) FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 11, c->gentry.p + carry_groups, 2, cudaMemcpyDeviceToHost, st));
+    }
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
     if (copied_out) FB_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
     c->timer.collect();
+    if (carry && sparse && (uint32_t)c->h_scalars[9] != 0) {
+        if (redo == 3) return FB200_RETRY_DENSE;  // cannot happen: every entry the parse can meet was evaluated
+        c->sparse_repairs++;
+        return deflate_body_device(c, container, mode, d_in, begin, n, d_skip, nskip, d_out, cap, end_bytes, final_flush, with_header, st,
+                                   nullptr, nullptr, 0, nullptr, 3, carry);
+    }
+    if (carry) {
+        carry->total_bits = c->h_scalars[0];
+        const uint32_t ntok = (uint32_t)c->h_scalars[10], nb = (uint32_t)(c->h_scalars[10] >> 32);
+        carry->exit = (uint32_t)(c->h_scalars[11] & 0xffffu);
+        carry->leftover = 0;
+        carry->cut = false;
+        if (part && tokens) {
+            carry->leftover = ntok - nb * kTokensPerBlock;
+            if (nb) {
+                carry->cut = true;
+                FB_CUDA_CHECK(cudaMemcpyAsync(&carry->last_rp, c->cut_rp.p + nb - 1, 4, cudaMemcpyDeviceToHost, st));
+                // the open block's tokens move to the front (no overlap: fewer than one block's worth, from at least one block up)
+                if (carry->leftover)
+                    FB_CUDA_CHECK(cudaMemcpyAsync(c->tokens.p, c->tokens.p + (size_t)nb * kTokensPerBlock, (size_t)carry->leftover * 4,
+                                                  cudaMemcpyDeviceToDevice, st));
+                FB_CUDA_CHECK(cudaStreamSynchronize(st));
+                carry->last_rp += (uint32_t)begin;  // cut_rp is relative to the segment start
+            }
+        }
+        *end_bytes = (size_t)((carry->total_bits + 7) >> 3);
+        return FB200_OK;
+    }
     if (d_nx_given && (uint32_t)c->h_scalars[9] != 0) return FB200_RETRY_DENSE;  // the given table does not cover the orbit
     if (sparse && (uint32_t)c->h_scalars[9] != 0) {
         // The speculation did not cover the true orbit (periodic data, where parses started at different
@@ -574,6 +685,7 @@ extern "C" {
 int fb200_compress_device(fb200_ctx* c, int container, int mode, const void* d_in, size_t n, void* d_out, size_t cap,
                           size_t* out_len, void* stream) {
     if (!c || !out_len || (!d_in && n)) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     size_t end = 0;
@@ -590,6 +702,7 @@ int fb200_compress_device(fb200_ctx* c, int container, int mode, const void* d_i
 int fb200_compress(fb200_ctx* c, int container, int mode, const uint8_t* in, size_t n, uint8_t* out, size_t cap,
                    size_t* out_len) {
     if (!c || !out_len || (!in && n) || !out) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     const size_t bound = fb200_compress_bound(n, mode) + 32;
     FB_CUDA_CHECK(c->d_in.ensure(n + 512));
@@ -615,6 +728,7 @@ int fb200_deflate_shard_search(fb200_ctx* c, int level, const void* d_in, size_t
     LevelArgs lv;
     if (!c || !level_args(level, lv) || !d_nx || n > (1ull << 31) || from > to || to > n || (from % 8192) != 0)
         return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     if (to == from) return FB200_OK;
@@ -660,6 +774,7 @@ int fb200_deflate_shard_finish(fb200_ctx* c, int container, int level, const voi
                                void* d_out, size_t cap, size_t* out_len, void* stream) {
     LevelArgs lv;
     if (!c || !level_args(level, lv) || !out_len || (!d_nx && n) || n > (1ull << 31)) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     size_t end = 0;
@@ -681,6 +796,7 @@ int fb200_simple_shard_plan(fb200_ctx* c, int container, int mode, const void* d
     if (!c || (mode != FB200_MODE_HUFFMAN && mode != FB200_MODE_STORE) || container < 0 || container > 2 || (!d_in && shard_bytes) ||
         !pre_bits || !has_stored || !post_bits)
         return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     if (!is_last && (shard_bytes == 0 || shard_bytes % kMaxStore != 0)) return FB200_INVALID_ARGUMENT;  // whole slices only
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
@@ -731,6 +847,7 @@ int fb200_simple_shard_plan(fb200_ctx* c, int container, int mode, const void* d
 int fb200_simple_shard_pack(fb200_ctx* c, uint64_t start_bit, void* d_out, size_t cap, uint64_t* byte_lo, size_t* nbytes,
                             uint64_t* end_bit, void* stream) {
     if (!c || !d_out || !byte_lo || !nbytes || !end_bit || c->shard_blocks == 0 || ((uintptr_t)d_out & 15) != 0) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const uint64_t lo = (start_bit >> 3) & ~15ull;  // stream byte held by d_out[0]; 16-byte steps keep word alignment
@@ -806,6 +923,7 @@ uint32_t fb200_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2) 
 int fb200_debug_tokens(fb200_ctx* c, int level, const uint8_t* in, size_t n, uint32_t* tokens, size_t cap, size_t* ntok) {
     LevelArgs lv;
     if (!c || !level_args(level, lv) || !ntok || n > (1ull << 31)) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     FB_CUDA_CHECK(c->d_in.ensure(n + 512));
     int rc = ensure_lz77(c, n);
@@ -846,6 +964,7 @@ int fb200_debug_tokens(fb200_ctx* c, int level, const uint8_t* in, size_t n, uin
 int fb200_debug_match_tables(fb200_ctx* c, int level, const uint8_t* in, size_t n, uint32_t* r_full, uint32_t* r_quarter) {
     LevelArgs lv;
     if (!c || !level_args(level, lv) || n > (1ull << 31) || n == 0) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     FB_CUDA_CHECK(c->d_in.ensure(n + 512));
     int rc = ensure_lz77(c, n);
@@ -864,6 +983,7 @@ int fb200_debug_match_tables(fb200_ctx* c, int level, const uint8_t* in, size_t 
 int fb200_debug_block_write(fb200_ctx* c, int kind, const uint32_t* tokens, size_t ntok, int eof, const uint8_t* input,
                             size_t input_len, int has_input, uint8_t* out, size_t cap, size_t* out_len) {
     if (!c || kind < 0 || kind > 2 || !out_len || ntok > (1u << 20)) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     if (kind == 2 && !has_input) return FB200_INVALID_ARGUMENT;
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -946,6 +1066,7 @@ int fb200_decompress_members_device(fb200_ctx* c, int container, const void* d_i
                                     const uint64_t* out_cap, uint64_t* out_len, uint64_t* consumed, int* status,
                                     void* stream) {
     if (!c || container < 0 || container > 2 || (k && (!in_off || !in_len || !out_off || !out_cap))) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     if (k > 0x7fffffffu) return FB200_INVALID_ARGUMENT;
     FB_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
@@ -969,6 +1090,7 @@ int fb200_decompress_members(fb200_ctx* c, int container, const uint8_t* in, con
                              uint64_t* consumed, int* status) {
     if (!c || container < 0 || container > 2 || k > 0x7fffffffu || (k && (!in || !out || !in_off || !in_len || !out_off || !out_cap || !out_len)))
         return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     for (size_t i = 0; i < k; i++) {  // nothing below may leave these unwritten
         out_len[i] = 0;
         if (consumed) consumed[i] = 0;
@@ -1035,6 +1157,7 @@ int fb200_decompress_members(fb200_ctx* c, int container, const uint8_t* in, con
 int fb200_decompress(fb200_ctx* c, int container, const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len,
                      size_t* consumed) {
     if (!c || (!in && n) || (!out && cap)) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     uint64_t in_off = 0, in_len = n, out_off = 0, out_cap = cap, olen = 0, used = 0;
     int status = 0;
     uint8_t dummy_in = 0, dummy_out = 0;
@@ -1047,118 +1170,389 @@ int fb200_decompress(fb200_ctx* c, int container, const uint8_t* in, size_t n, u
 
 // =============================================================================================
 // streaming compressor: Compressor / SimpleCompressor (deflate.zig:121-373, 449-529).
-// write() accumulates; flush() and finish() run the device pipeline over the segment since the last
-// flush point, with the whole earlier stream kept in HBM as match history.
+//
+// write() copies the caller's bytes straight into a device window (no host copy of the stream is kept).  Once a
+// part's worth of bytes has arrived, the part of the stream whose look-ahead is complete is compressed and its
+// finished blocks go to the writer (deflate.zig:363-371 emits blocks as they fill; the bytes do not depend on how
+// the input was cut into write() calls).  What is carried from part to part: the clean arrival where the parse
+// goes on, the tokens of the open block, the position of the last block cut and the bits of the last, partial output
+// byte (PartCarry).  The window keeps 64 KiB of history before the next parse position and slides by multiples of
+// 32768, so that the reference's slide schedule (a function of position) reads the same in window coordinates.
+// A part runs on a worker thread while the caller goes on writing into the window behind it; the writer is only
+// ever called on the caller's thread.  flush() / finish() close the segment with the existing segment pipeline.
 // =============================================================================================
 struct fb200_deflate {
     fb200_ctx* ctx;
     int device = 0;                 // the context may be destroyed before us: never dereference it in destroy()
     int container, mode;
+    bool level_mode = false;
     fb200_write_fn writer;
     void* user;
-    std::vector<uint8_t> pending;   // bytes written since the last flush: stream positions [begin, begin + pending.size())
-    size_t begin = 0;               // flush point: everything before it has been emitted
-    DevBuf<uint8_t> stream;         // device copy of the whole stream so far (history for later segments)
-    DevBuf<uint16_t> link;          // hash links of the whole stream (private: the context's are per call)
-    std::vector<uint32_t> skip;     // positions never inserted into the chains (3 before every flush point)
+    // device window, two sets (a slide copies into the other one); index 0 is stream position wbase
+    DevBuf<uint8_t> win[2];
+    DevBuf<uint16_t> link[2];
+    DevBuf<uint32_t> nx[2];
+    DevBuf<uint32_t> tokbuf;        // tokens of the open block between parts (the context's token buffer is per call)
+    int cur = 0;
+    size_t cap = 0;                 // positions a window holds
+    size_t part = 0;                // bytes per part
+    uint64_t wbase = 0;             // stream position of window index 0 (multiple of 32768)
+    size_t filled = 0;              // bytes in the window
+    size_t seg_begin = 0;           // where the parse goes on: a clean arrival (or the segment start)
+    bool seg_fresh = true;          // nothing of the current segment has been linked / evaluated yet
+    size_t linked = 0, chunks_done = 0;
+    uint32_t carry_tok = 0, fp0 = 0, bit_phase = 0;
+    bool has_fp = true;             // fp0 = position of the last block cut, or the start of the segment
+    uint8_t carry_byte = 0;
+    std::vector<uint64_t> skip;     // stream positions never inserted into the chains (3 before every flush point)
     DevBuf<uint32_t> d_skip;
+    // container checksum of everything written, summed part by part on the device and combined here
+    uint32_t sum = 0;
+    size_t sum_done = 0;            // window bytes below this are in `sum`
+    uint64_t total_in = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev = nullptr;
+    uint8_t* h_out = nullptr;       // pinned: a part's output on its way to the writer
+    size_t h_out_cap = 0;
+    size_t last_trigger = 0;        // value of `filled` when the last part was started (or the segment began)
+    // the part in flight (worker thread).  The worker only reads the stream state; what it found is applied by the
+    // caller's thread when it joins (stream_apply), so that write() never races with it.
+    std::thread worker;
+    bool job_running = false;
+    int job_rc = 0;
+    size_t job_out = 0;             // bytes of h_out to hand to the writer
+    struct Result {
+        bool part = false;
+        uint32_t bit_phase = 0, carry_tok = 0, fp0 = 0;
+        uint8_t carry_byte = 0;
+        bool cut = false;
+        size_t seg_begin = 0, linked = 0, chunks_done = 0;
+    } res;
     bool finished = false;
     int err = 0;
 };
+
+namespace {
+constexpr size_t kStreamHist = 65536;  // 32 KiB of match history and 32 KiB before it to rebuild that history's chains
+
+int stream_alloc(fb200_deflate* d) {
+    for (int i = 0; i < 2; i++) {
+        FB_CUDA_CHECK(d->win[i].ensure(d->cap + 1024));
+        if (d->level_mode) {
+            FB_CUDA_CHECK(d->link[i].ensure(d->cap + 1024));
+            FB_CUDA_CHECK(d->nx[i].ensure(d->cap + 1024));
+        }
+    }
+    if (d->level_mode) FB_CUDA_CHECK(d->tokbuf.ensure(kTokensPerBlock));
+    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&d->copy_ev, cudaEventDisableTiming));
+    return FB200_OK;
+}
+
+// container checksum of the window bytes [sum_done, upto), folded into d->sum (stream `st` is synchronized)
+int stream_sum(fb200_deflate* d, size_t upto, cudaStream_t st) {
+    if (d->container == FB200_RAW || upto <= d->sum_done) {
+        d->sum_done = upto > d->sum_done ? upto : d->sum_done;
+        return FB200_OK;
+    }
+    fb200_ctx* c = d->ctx;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
+    const size_t len = upto - d->sum_done;
+    uint32_t* sum_dev = c->d_scalars + 16;
+    uint32_t got = 0;
+    if (d->container == FB200_GZIP) FB_CUDA_CHECK(crc32_device(d->win[d->cur].p + d->sum_done, len, sum_dev, st));
+    else FB_CUDA_CHECK(adler32_device(d->win[d->cur].p + d->sum_done, len, sum_dev, reinterpret_cast<uint64_t*>(c->d_scalars + 24), st));
+    FB_CUDA_CHECK(cudaMemcpyAsync(&got, sum_dev, 4, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    d->sum = d->container == FB200_GZIP ? fb200_crc32_combine(d->sum, got, len) : fb200_adler32_combine(d->sum, got, len);
+    d->sum_done = upto;
+    return FB200_OK;
+}
+
+// Slides the window so that it starts 64 KiB (rounded down to 32768) before the next parse position.
+int stream_slide(fb200_deflate* d, cudaStream_t st) {
+    if (d->seg_begin < kStreamHist + 32768) return FB200_OK;
+    const size_t shift = (d->seg_begin - kStreamHist) / 32768 * 32768;
+    int rc = stream_sum(d, d->filled, st);  // bytes about to leave the window are summed first
+    if (rc) return rc;
+    const int o = d->cur ^ 1;
+    const size_t keep = d->filled - shift;
+    FB_CUDA_CHECK(cudaStreamSynchronize(d->copy_stream));
+    FB_CUDA_CHECK(cudaMemcpyAsync(d->win[o].p, d->win[d->cur].p + shift, keep, cudaMemcpyDeviceToDevice, st));
+    if (d->level_mode) {
+        FB_CUDA_CHECK(cudaMemcpyAsync(d->link[o].p, d->link[d->cur].p + shift, keep * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
+        FB_CUDA_CHECK(cudaMemcpyAsync(d->nx[o].p, d->nx[d->cur].p + shift, keep * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    d->cur = o;
+    d->wbase += shift;
+    d->filled -= shift;
+    d->seg_begin -= shift;
+    d->sum_done -= shift;
+    d->last_trigger = d->last_trigger > shift ? d->last_trigger - shift : 0;
+    if (!d->seg_fresh) {
+        d->linked -= shift;
+        d->chunks_done -= shift / 32768;
+    }
+    if (d->has_fp) d->fp0 = d->fp0 > shift ? d->fp0 - (uint32_t)shift : 0;  // a cut that far back cannot be stored anyway (> 65535 bytes)
+    return FB200_OK;
+}
+
+// Uploads the skip list in window coordinates; returns the count.
+int stream_skip(fb200_deflate* d, cudaStream_t st, uint32_t* count) {
+    std::vector<uint32_t> rel;
+    for (uint64_t p : d->skip)
+        if (p >= d->wbase) rel.push_back((uint32_t)(p - d->wbase));
+    *count = (uint32_t)rel.size();
+    if (rel.empty()) return FB200_OK;
+    FB_CUDA_CHECK(d->d_skip.ensure(rel.size()));
+    FB_CUDA_CHECK(cudaMemcpyAsync(d->d_skip.p, rel.data(), rel.size() * 4, cudaMemcpyHostToDevice, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return FB200_OK;
+}
+
+// One call of the segment pipeline over window positions [seg_begin, n): a part when parse_end != 0, else the
+// closing flush / finish.  Leaves the output bytes in d->h_out (job_out of them are final) and updates the carry.
+int stream_run(fb200_deflate* d, size_t n, size_t parse_end, size_t chunk_end, size_t link_to, bool final_flush) {
+    fb200_ctx* c = d->ctx;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    FB_CUDA_CHECK(cudaStreamWaitEvent(st, d->copy_ev, 0));  // the window bytes below n have landed
+    uint32_t nskip = 0;
+    int rc = d->level_mode ? stream_skip(d, st, &nskip) : FB200_OK;
+    if (rc) return rc;
+    const size_t begin = d->seg_begin;
+    const size_t bound = round_up(fb200_compress_bound(n - begin, d->mode) + 64, 16);
+    FB_CUDA_CHECK(c->d_out.ensure(bound));
+    if (bound + 16 > d->h_out_cap) {
+        if (d->h_out) cudaFreeHost(d->h_out);
+        d->h_out = nullptr;
+        d->h_out_cap = 0;
+        FB_CUDA_CHECK(cudaMallocHost(&d->h_out, bound + 16));
+        d->h_out_cap = bound + 16;
+    }
+    PartCarry carry;
+    carry.bit_phase = d->bit_phase;
+    carry.parse_end = parse_end;
+    carry.chunk_end = chunk_end;
+    carry.link_to = link_to;
+    if (d->level_mode) {
+        if ((rc = ensure_lz77(c, n))) return rc;  // before the open block's tokens go to the front of the token buffer
+        carry.nx = d->nx[d->cur].p;
+        carry.carry_tok = d->carry_tok;
+        carry.has_fp = d->has_fp;
+        carry.fp0 = d->fp0;
+        if (!d->seg_fresh) {
+            carry.link_from = d->linked;
+            carry.chunks_from = d->chunks_done;
+        }
+        if (d->carry_tok) FB_CUDA_CHECK(cudaMemcpyAsync(c->tokens.p, d->tokbuf.p, (size_t)d->carry_tok * 4, cudaMemcpyDeviceToDevice, st));
+        std::swap(c->link, d->link[d->cur]);  // the pipeline uses the context's link buffer: lend it ours for the call
+    }
+    size_t out_end = 0;
+    rc = deflate_body_device(c, d->container, d->mode, d->win[d->cur].p, begin, n, d->d_skip.p, nskip, c->d_out.p, c->d_out.cap, &out_end,
+                             final_flush, false, st, nullptr, nullptr, 0, nullptr, 0, &carry);
+    if (d->level_mode) std::swap(c->link, d->link[d->cur]);
+    if (rc) return rc;
+    // output: whole bytes go to the writer, the bits of the last partial byte wait for the next part
+    const size_t nfull = parse_end ? (size_t)(carry.total_bits >> 3) : out_end;
+    const size_t ncopy = (size_t)((carry.total_bits + 7) >> 3);
+    if (ncopy) FB_CUDA_CHECK(cudaMemcpyAsync(d->h_out, c->d_out.p, ncopy, cudaMemcpyDeviceToHost, st));
+    if (d->level_mode && carry.leftover) FB_CUDA_CHECK(cudaMemcpyAsync(d->tokbuf.p, c->tokens.p, (size_t)carry.leftover * 4, cudaMemcpyDeviceToDevice, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (ncopy == 0) d->h_out[0] = 0;
+    d->h_out[0] |= d->carry_byte;
+    d->job_out = nfull;
+    fb200_deflate::Result& r = d->res;
+    r.part = parse_end != 0;
+    r.bit_phase = parse_end ? (uint32_t)(carry.total_bits & 7) : 0;
+    r.carry_byte = r.bit_phase ? d->h_out[nfull] : 0;
+    r.carry_tok = carry.leftover;
+    r.cut = carry.cut;
+    r.fp0 = carry.last_rp;
+    r.seg_begin = (parse_end && d->level_mode) ? parse_end + carry.exit : n;
+    r.linked = link_to;
+    r.chunks_done = chunk_end;
+    return FB200_OK;
+}
+
+// the stream state after a finished stream_run (caller's thread)
+void stream_apply(fb200_deflate* d) {
+    const fb200_deflate::Result& r = d->res;
+    d->bit_phase = r.bit_phase;
+    d->carry_byte = r.carry_byte;
+    d->carry_tok = r.carry_tok;
+    d->seg_begin = r.seg_begin;
+    if (r.part) {
+        if (r.cut) {
+            d->has_fp = true;
+            d->fp0 = r.fp0;
+        }
+        if (d->level_mode) {
+            d->linked = r.linked;
+            d->chunks_done = r.chunks_done;
+            d->seg_fresh = false;
+        }
+    } else {
+        d->has_fp = true;  // the next block's stored-input candidate starts at the flush point (SlidingWindow.zig:113)
+        d->fp0 = (uint32_t)r.seg_begin;
+        d->seg_fresh = true;
+    }
+}
+
+// waits for the part in flight and hands its bytes to the writer (caller's thread)
+int stream_join(fb200_deflate* d) {
+    if (!d->job_running) return FB200_OK;
+    d->worker.join();
+    d->job_running = false;
+    if (d->job_rc) return d->job_rc;
+    stream_apply(d);
+    if (d->job_out && d->writer(d->user, d->h_out, d->job_out)) return FB200_NO_SPACE_LEFT;
+    d->job_out = 0;
+    return FB200_OK;
+}
+
+// Starts a part if a part's worth of input is waiting.  force: the window is full, a part must make room.
+int stream_maybe_part(fb200_deflate* d, bool force) {
+    int rc = stream_join(d);
+    if (rc) return rc;
+    const size_t pending = d->filled - d->seg_begin;
+    if (pending < d->part / 2 && !force) return FB200_OK;
+    size_t n, parse_end, chunk_end = 0, link_to = 0;
+    if (d->level_mode) {
+        if (d->filled < 2 * 32768) return FB200_OK;
+        chunk_end = d->filled / 32768 - 1;  // the chunks whose look-ahead (and slide schedule) no later byte can change
+        const size_t limit = chunk_end * 32768;
+        if (limit <= d->seg_begin + kChunk || (!d->seg_fresh && chunk_end <= d->chunks_done)) return FB200_OK;
+        parse_end = d->seg_begin + (limit - d->seg_begin) / kChunk * kChunk;
+        link_to = limit + 8192;
+        n = d->filled;
+    } else {
+        const size_t slices = pending / kMaxStore;
+        if (slices == 0) return FB200_OK;
+        n = d->seg_begin + slices * kMaxStore;
+        parse_end = n;
+    }
+    FB_CUDA_CHECK(cudaEventRecord(d->copy_ev, d->copy_stream));
+    d->last_trigger = d->filled;
+    d->job_running = true;
+    d->job_rc = 0;
+    d->worker = std::thread([d, n, parse_end, chunk_end, link_to] { d->job_rc = stream_run(d, n, parse_end, chunk_end, link_to, false); });
+    return FB200_OK;
+}
+}  // namespace
 
 int fb200_deflate_create(fb200_ctx* ctx, int container, int mode, fb200_write_fn writer, void* user, fb200_deflate** out) {
     LevelArgs lv;
     if (!ctx || !out || !writer || container < 0 || container > 2) return FB200_INVALID_ARGUMENT;
     if (mode != FB200_MODE_STORE && mode != FB200_MODE_HUFFMAN && !level_args(mode, lv)) return FB200_INVALID_ARGUMENT;
+    *out = nullptr;
     fb200_deflate* d = new (std::nothrow) fb200_deflate();
     if (!d) return FB200_INVALID_ARGUMENT;
     d->ctx = ctx;
     d->device = ctx->device;
     d->container = container;
     d->mode = mode;
+    d->level_mode = mode >= 4;
     d->writer = writer;
     d->user = user;
+    d->sum = container == FB200_ZLIB ? 1u : 0u;  // Adler-32 / CRC-32 of nothing
+    // bytes per part: FB200_STREAM_PART (KiB) for tests and tuning; 32 MiB keeps every kernel's grid full
+    size_t part_kib = 32768;
+    if (const char* e = getenv("FB200_STREAM_PART")) {
+        const long v = atol(e);
+        if (v >= 128 && v <= (1 << 20)) part_kib = (size_t)v;
+    }
+    d->part = part_kib << 10;
+    d->cap = kStreamHist + 2 * d->part + (1u << 20);
+    if (cudaSetDevice(ctx->device) != cudaSuccess || stream_alloc(d) != FB200_OK) {
+        fb200_deflate_destroy(d);
+        return FB200_ERR_CUDA;
+    }
     // the reference writes the container header in init (deflate.zig:144, :470)
     int rc = 0;
     if (container == FB200_GZIP) rc = writer(user, kGzipHeader, 10);
     else if (container == FB200_ZLIB) rc = writer(user, kZlibHeader, 2);
     if (rc) {
-        delete d;
+        fb200_deflate_destroy(d);
         return FB200_NO_SPACE_LEFT;
     }
     *out = d;
     return FB200_OK;
 }
+
 int fb200_deflate_write(fb200_deflate* d, const uint8_t* data, size_t n) {
     if (!d || (!data && n)) return FB200_INVALID_ARGUMENT;
     if (d->err) return d->err;
     if (d->finished) return d->err = FB200_INVALID_STATE;
-    d->pending.insert(d->pending.end(), data, data + n);
+    if (cudaSetDevice(d->device) != cudaSuccess) return d->err = FB200_ERR_CUDA;
+    while (n) {
+        if (d->filled == d->cap) {  // make room: finish the part in flight, run another if need be, slide
+            int rc = stream_maybe_part(d, true);
+            if (!rc) rc = stream_join(d);
+            if (!rc) rc = stream_slide(d, d->ctx->stream);
+            if (rc) return d->err = rc;
+            if (d->filled == d->cap) return d->err = FB200_NO_SPACE_LEFT;  // cannot happen: a part always frees more than it keeps
+        }
+        const size_t take = n < d->cap - d->filled ? n : d->cap - d->filled;
+        if (cudaMemcpyAsync(d->win[d->cur].p + d->filled, data, take, cudaMemcpyHostToDevice, d->copy_stream) != cudaSuccess) {
+            fb::set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
+            return d->err = FB200_ERR_CUDA;
+        }
+        d->filled += take;
+        d->total_in += take;
+        data += take;
+        n -= take;
+        if (d->filled - d->last_trigger >= d->part) {  // a part's worth since the last one: take its results, start the next
+            int rc = stream_join(d);
+            if (!rc) rc = stream_slide(d, d->ctx->stream);  // between parts: nothing reads the window
+            if (!rc) rc = stream_maybe_part(d, false);
+            if (rc) return d->err = rc;
+        }
+    }
+    // the caller may reuse `data` at once: the copy has to be out of it
+    if (cudaStreamSynchronize(d->copy_stream) != cudaSuccess) return d->err = FB200_ERR_CUDA;
     return FB200_OK;
 }
 
-// Emits the segment [begin, begin + pending) -- non-final + sync marker for flush (deflate.zig:335-337,
-// :268-288), final + footer for finish (:344-347).  Chunking of write() calls inside a segment is not
-// observable in the reference's output (the slide schedule depends on stream position only).
-static int deflate_emit_segment(fb200_deflate* d, bool final_flush) {
-    fb200_ctx* c = d->ctx;
-    FB_CUDA_CHECK(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
-    const size_t begin = d->begin, end = begin + d->pending.size();
-    if (end > (1ull << 31) && d->mode >= 4) return FB200_INVALID_ARGUMENT;
-    // grow the device copy of the stream, keeping the history
-    if (end + 512 > d->stream.cap) {
-        DevBuf<uint8_t> bigger;
-        FB_CUDA_CHECK(bigger.ensure(end + end / 2 + (1 << 20)));
-        if (begin) FB_CUDA_CHECK(cudaMemcpyAsync(bigger.p, d->stream.p, begin, cudaMemcpyDeviceToDevice, st));
-        FB_CUDA_CHECK(cudaStreamSynchronize(st));
-        d->stream.release();
-        d->stream = bigger;
-    }
-    if (d->mode >= 4 && end + 64 > d->link.cap) {
-        DevBuf<uint16_t> bigger;
-        FB_CUDA_CHECK(bigger.ensure(end + end / 2 + (1 << 20)));
-        if (begin) FB_CUDA_CHECK(cudaMemcpyAsync(bigger.p, d->link.p, begin * 2, cudaMemcpyDeviceToDevice, st));
-        FB_CUDA_CHECK(cudaStreamSynchronize(st));
-        d->link.release();
-        d->link = bigger;
-    }
-    if (end > begin) FB_CUDA_CHECK(cudaMemcpyAsync(d->stream.p + begin, d->pending.data(), end - begin, cudaMemcpyHostToDevice, st));
-    const uint32_t nskip = d->mode >= 4 ? (uint32_t)d->skip.size() : 0;
-    if (nskip) {
-        FB_CUDA_CHECK(d->d_skip.ensure(nskip));
-        FB_CUDA_CHECK(cudaMemcpyAsync(d->d_skip.p, d->skip.data(), nskip * 4, cudaMemcpyHostToDevice, st));
-    }
-    const size_t bound = round_up(fb200_compress_bound(end - begin, d->mode) + 64, 16);
-    FB_CUDA_CHECK(c->d_out.ensure(bound));
-    // the pipeline uses the context's link buffer: lend it ours for the call
-    std::swap(c->link, d->link);
-    size_t out_end = 0;
-    int rc = deflate_body_device(c, d->container, d->mode, d->stream.p, begin, end, d->d_skip.p, nskip, c->d_out.p,
-                                 c->d_out.cap, &out_end, final_flush, false, st);
-    std::swap(c->link, d->link);
+// Closes the segment: non-final + sync marker for flush (deflate.zig:335-337, :268-288), final + footer for finish
+// (:344-347).  How the input was cut into write() calls is not observable in the reference's output (the slide
+// schedule depends on stream position only).
+static int deflate_close_segment(fb200_deflate* d, bool final_flush) {
+    if (cudaSetDevice(d->device) != cudaSuccess) return FB200_ERR_CUDA;
+    int rc = stream_join(d);
     if (rc) return rc;
-    std::vector<uint8_t> out(out_end + 8);
-    if (out_end) FB_CUDA_CHECK(cudaMemcpy(out.data(), c->d_out.p, out_end, cudaMemcpyDeviceToHost));
-    size_t total = out_end;
-    if (final_flush) total += make_footer(d->container, (uint32_t)c->h_scalars[8], end, out.data() + out_end);
-    if (total && d->writer(d->user, out.data(), total)) return FB200_NO_SPACE_LEFT;
+    fb200_ctx* c = d->ctx;
+    FB_CUDA_CHECK(cudaStreamSynchronize(d->copy_stream));
+    FB_CUDA_CHECK(cudaEventRecord(d->copy_ev, d->copy_stream));
+    const size_t end = d->filled;
+    if ((rc = stream_run(d, end, 0, 0, 0, final_flush))) return rc;
+    stream_apply(d);
+    d->last_trigger = d->filled;
+    size_t total = d->job_out;
+    d->job_out = 0;
+    if (final_flush) {
+        if ((rc = stream_sum(d, d->filled, c->stream))) return rc;
+        total += make_footer(d->container, d->sum, (size_t)d->total_in, d->h_out + total);
+    }
+    if (total && d->writer(d->user, d->h_out, total)) return FB200_NO_SPACE_LEFT;
     // positions with fewer than 4 bytes before the flush point were never hashed (Lookup.zig:24) and
     // stay that way for later segments
-    if (!final_flush && d->mode >= 4)
-        for (size_t p = end >= 3 ? end - 3 : 0; p < end; p++)
-            if (p >= begin || d->skip.empty() || d->skip.back() < p) d->skip.push_back((uint32_t)p);
+    if (!final_flush && d->level_mode) {
+        const uint64_t aend = d->wbase + end;
+        for (uint64_t p = aend >= 3 ? aend - 3 : 0; p < aend; p++)
+            if (d->skip.empty() || d->skip.back() < p) d->skip.push_back(p);
+    }
     // only flush points within the last 32 KiB + one tile can matter again
-    while (!d->skip.empty() && (size_t)d->skip.front() + 2 * kHist < end) d->skip.erase(d->skip.begin());
-    d->begin = end;
-    d->pending.clear();
+    while (!d->skip.empty() && d->skip.front() + 2 * kHist < d->wbase + end) d->skip.erase(d->skip.begin());
     return FB200_OK;
 }
 int fb200_deflate_flush(fb200_deflate* d) {
     if (!d) return FB200_INVALID_ARGUMENT;
     if (d->err) return d->err;
     if (d->finished) return d->err = FB200_INVALID_STATE;
-    int rc = deflate_emit_segment(d, false);
+    int rc = deflate_close_segment(d, false);
     if (rc) d->err = rc;
     return rc;
 }
@@ -1166,7 +1560,7 @@ int fb200_deflate_finish(fb200_deflate* d) {
     if (!d) return FB200_INVALID_ARGUMENT;
     if (d->err) return d->err;
     if (d->finished) return d->err = FB200_INVALID_STATE;
-    int rc = deflate_emit_segment(d, true);
+    int rc = deflate_close_segment(d, true);
     if (rc) return d->err = rc;
     d->finished = true;
     return FB200_OK;
@@ -1178,10 +1572,18 @@ void fb200_deflate_set_writer(fb200_deflate* d, fb200_write_fn writer, void* use
 }
 void fb200_deflate_destroy(fb200_deflate* d) {
     if (!d) return;
+    if (d->job_running) d->worker.join();
     if (cudaSetDevice(d->device) != cudaSuccess) (void)cudaGetLastError();
-    d->stream.release();
-    d->link.release();
+    for (int i = 0; i < 2; i++) {
+        d->win[i].release();
+        d->link[i].release();
+        d->nx[i].release();
+    }
+    d->tokbuf.release();
     d->d_skip.release();
+    if (d->h_out) cudaFreeHost(d->h_out);
+    if (d->copy_ev) cudaEventDestroy(d->copy_ev);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     delete d;
 }
 

@@ -1659,12 +1659,15 @@ __global__ void group_exit_kernel(const uint16_t* __restrict__ exits, uint32_t n
     gexits[(size_t)g * kEntries + e] = (uint16_t)cur;
 }
 __global__ void group_entry_kernel(const uint16_t* __restrict__ gexits, uint32_t ngroups, uint16_t* __restrict__ gentry) {
+    // gentry[ngroups] = where the orbit leaves the last group: the first arrival past the chunk grid, relative to its end
+    // (a streaming compressor continues the parse from there with the next part of the stream)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint32_t cur = 0;
     for (uint32_t g = 0; g < ngroups; g++) {
         gentry[g] = (uint16_t)cur;
         cur = gexits[(size_t)g * kEntries + cur];
     }
+    gentry[ngroups] = (uint16_t)cur;
 }
 __global__ void chunk_entry_kernel(const uint16_t* __restrict__ exits, const uint16_t* __restrict__ gentry,
                                    uint32_t nchunks, uint16_t* __restrict__ entry) {
@@ -1773,10 +1776,11 @@ orbit_mark_kernel(const uint32_t* __restrict__ nx, uint32_t n, const uint16_t* _
 // exclusive scan of per-chunk token counts (single block; nchunks is at most ~1M)
 __global__ void __launch_bounds__(1024)
 scan_tokens_kernel(const uint32_t* __restrict__ counts, uint32_t nchunks, uint32_t* __restrict__ offsets,
-                   uint32_t* __restrict__ total_out) {
+                   uint32_t* __restrict__ total_out, uint32_t carry0) {
+    // carry0: tokens already in the token buffer (the open block a streaming compressor carries from part to part)
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x == 0) carry = carry0;
     __syncthreads();
     for (uint32_t base = 0; base < nchunks; base += 1024) {
         const uint32_t i = base + threadIdx.x;
@@ -2079,7 +2083,7 @@ cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin
     pt->mark(st, kPhResolve);
     orbit_mark_kernel<<<nchunks, kMarkThreads, 0, st>>>(b.nx, n, b.entry, nullptr, b.bitmap, b.chunk_tokens);
     pt->mark(st, kPhMark);
-    scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
+    scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens, 0);
     pt->mark(st, kPhScan);
     emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_seg, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp, nullptr);
     pt->mark(st, kPhEmit);
@@ -2106,11 +2110,14 @@ cudaError_t lz77_shard_search(const Lz77Buffers& b, const uint8_t* d_in, uint32_
 
 // Stage 2 on one rank: parse + token emission from a complete nx table (b.nx).
 cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
-                               PhaseTimer* pt, uint32_t* flags) {
+                               PhaseTimer* pt, uint32_t* flags, uint32_t tok_carry) {
+    // tok_carry: tokens already at the front of b.tokens (they open the first block); the new ones follow them.
+    // b.gentry[number of groups] receives the first arrival past the chunk grid (relative to its end).
     PhaseTimer dummy;
     if (!pt) pt = &dummy;
     if (n == 0) {
-        cudaMemsetAsync(b.total_tokens, 0, sizeof(uint32_t), st);
+        cudaMemcpyAsync(b.total_tokens, &tok_carry, sizeof(uint32_t), cudaMemcpyHostToDevice, st);  // pageable source: staged at once
+        cudaMemsetAsync(b.gentry, 0, sizeof(uint16_t), st);
         return cudaGetLastError();
     }
     const uint32_t nchunks = (n + kChunk - 1) / kChunk;
@@ -2123,7 +2130,7 @@ cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32
     pt->mark(st, kPhResolve);
     orbit_mark_kernel<<<nchunks, kMarkThreads, 0, st>>>(b.nx, n, b.entry, b.jumps, b.bitmap, b.chunk_tokens);
     pt->mark(st, kPhMark);
-    scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens);
+    scan_tokens_kernel<<<1, 1024, 0, st>>>(b.chunk_tokens, nchunks, b.tok_offset, b.total_tokens, tok_carry);
     pt->mark(st, kPhScan);
     emit_tokens_kernel<<<nchunks, kEmitThreads, 0, st>>>(d_in, b.nx, n, b.bitmap, b.tok_offset, lv, b.tokens, b.cut_rp, flags);
     pt->mark(st, kPhEmit);

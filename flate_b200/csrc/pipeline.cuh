@@ -92,7 +92,7 @@ cudaError_t lz77_parse(const Lz77Buffers& b, const uint8_t* d_in, uint32_t begin
 cudaError_t lz77_shard_search(const Lz77Buffers& b, const uint8_t* d_in, uint32_t from, uint32_t to, uint32_t n,
                               const LevelArgs& lv, uint32_t* nx_out, cudaStream_t st, PhaseTimer* pt = nullptr);
 cudaError_t lz77_parse_from_nx(const Lz77Buffers& b, const uint8_t* d_in, uint32_t n, const LevelArgs& lv, cudaStream_t st,
-                               PhaseTimer* pt = nullptr, uint32_t* flags = nullptr);
+                               PhaseTimer* pt = nullptr, uint32_t* flags = nullptr, uint32_t tok_carry = 0);
 
 // sparse parse (whole streams, begin = 0): links, then the speculative sparse kernel writes nx directly;
 // lz77_parse_from_nx finishes.  *flags != 0 afterwards means the speculation did not cover the true
@@ -126,9 +126,11 @@ struct BlockPlan {           // per-block inputs of the build kernel (device arr
 };
 
 // plans for the level modes are derived on the device from the token count and cut_rp
+// final_flush: 0 = sync flush (open block closed, marker appended), 1 = finish, 2 = a part in the middle of a stream
+// (complete blocks only; the open one is carried).  fp0: position of the last cut before these tokens (the first
+// block's stored-input candidate starts there); pass `begin` when the tokens start a segment.
 cudaError_t plan_level_blocks(const uint32_t* total_tokens, const uint32_t* cut_rp, uint32_t begin, uint32_t n, uint32_t max_blocks,
-                              uint32_t final_flush /*0 none(sync flush) 1 final*/, BlockPlan* plans, uint32_t* nblocks,
-                              cudaStream_t st);
+                              uint32_t final_flush, BlockPlan* plans, uint32_t* nblocks, cudaStream_t st, uint32_t fp0);
 cudaError_t histogram_tokens(const uint32_t* tokens, const BlockPlan* plans, const uint32_t* nblocks_dev,
                              uint32_t max_blocks, uint32_t* lit_freq, uint32_t* dist_freq, cudaStream_t st);
 cudaError_t histogram_bytes(const uint8_t* in, const BlockPlan* plans, uint32_t nblocks, uint32_t* lit_freq,

@@ -550,3 +550,63 @@ def test_rolling_sparse_parse_is_bit_exact():
     env = dict(os.environ, FB200_SPARSE_ROLL="16,2")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "rolling ok" in r.stdout, r.stderr[-2000:]
+
+
+def _stream_data(n, seed):
+    from flate_b200 import synth
+    d = synth.enwik_like(n, seed=seed).copy()
+    rng = np.random.default_rng(seed)
+    d[n // 5:n // 5 + 300000] = 0                                                  # periodic: the coverage check fails here
+    d[n // 2:n // 2 + 200000] = rng.integers(0, 256, 200000, dtype=np.uint8)      # incompressible: stored blocks
+    d[n // 2 + 400000:n // 2 + 400000 + 70000] = d[1000:71000]                    # a long repeat from far back
+    return d.tobytes()
+
+
+@pytest.mark.parametrize("mode", [6, 4, 9, 1, 0])
+def test_streaming_in_parts_is_bit_exact(ctx, o, mode, monkeypatch):
+    """deflate.zig:363-371: write() emits blocks as they fill, and the bytes do not depend on how the input was cut
+    into write() calls.  With a small part size the stream below goes through many parts (window slides, carried
+    open blocks, carried partial bytes, a part whose speculation fails) and must still equal the one-shot stream."""
+    import flate_b200
+    monkeypatch.setenv("FB200_STREAM_PART", "256")
+    data = _stream_data(5 * 1024 * 1024 + 4321, seed=90 + mode)
+    for container in (0, 1, 2):
+        want = o.compress(data, container, mode)
+        w = io.BytesIO()
+        c = flate_b200.Compressor(container, w, mode, ctx=ctx)
+        pos, k, emitted_early = 0, 0, 0
+        while pos < len(data):
+            step = (37 + 7919 * k) % 150000 + 1
+            c.write(data[pos:pos + step])
+            pos += step
+            k += 1
+            if pos < len(data) // 2:
+                emitted_early = len(w.getvalue())
+        c.finish()
+        got = w.getvalue()
+        assert got == want, (mode, container, first_diff(got, want))
+        assert emitted_early > len(want) // 8, "nothing left the compressor before finish()"
+        c.close()
+
+
+@pytest.mark.parametrize("mode", [6, 1])
+def test_streaming_parts_with_flushes(ctx, o, mode, monkeypatch):
+    """flush points in the middle of a stream that is otherwise compressed part by part (deflate.zig:335-337)."""
+    import flate_b200
+    monkeypatch.setenv("FB200_STREAM_PART", "128")
+    data = _stream_data(2 * 1024 * 1024 + 99, seed=7)
+    cuts = [0, 400001, 400003, 1300000, 1300000, 1900000, len(data)]
+    w = io.BytesIO()
+    c = flate_b200.Compressor(1, w, mode, ctx=ctx)
+    d = o.Deflate(1, mode)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        for p in range(a, b, 50000):
+            c.write(data[p:min(p + 50000, b)])
+        d.write(data[a:b])
+        if b != len(data):
+            c.flush()
+            d.flush()
+    c.finish()
+    d.finish()
+    got, want = w.getvalue(), d.output()
+    assert got == want, (mode, first_diff(got, want))
