@@ -605,7 +605,7 @@ def main():
     if world == 1 and not args.skip_stream:
         import psutil
         from flate_b200 import _lib as fb_lib
-        sink = torch.empty(4 * cap + 64, dtype=torch.uint8)   # where the writer puts what it is handed
+        sink = torch.zeros(4 * cap + 64, dtype=torch.uint8)   # where the writer puts what it is handed (touched: no page faults later)
         sink_ptr, sink_len = sink.data_ptr(), [0]
 
         def on_write(_user, data, nbytes):

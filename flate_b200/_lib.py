@@ -53,6 +53,7 @@ SIGNATURES = {
     "fb200_inflate_reset": (_I, [_P]),
     "fb200_inflate_set_reader": (None, [_P, READ_FN, _P]),
     "fb200_inflate_rebind": (None, [_P, READ_FN, _P]),
+    "fb200_inflate_unused": (_I, [_P, C.POINTER(_P), _SZP]),
     "fb200_inflate_destroy": (None, [_P]),
     "fb200_debug_tokens": (_I, [_P, _I, _P, _SZ, _P, _SZ, _SZP]),
     "fb200_debug_match_tables": (_I, [_P, _I, _P, _SZ, _P, _P]),

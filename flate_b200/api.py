@@ -366,6 +366,12 @@ class Decompressor:
     def reset(self):  # inflate.zig:301
         _check(self.lib.fb200_inflate_reset(self.h))
 
+    def unread_bytes(self):
+        """Bytes pulled from the reader past the end of the current member (the reader is read a chunk at a time)."""
+        p, n = C.c_void_p(), C.c_size_t(0)
+        _check(self.lib.fb200_inflate_unused(self.h, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value) if n.value else b""
+
     def set_reader(self, reader):  # inflate.zig:283
         self._reader = io.BytesIO(reader) if isinstance(reader, (bytes, bytearray)) else reader
 

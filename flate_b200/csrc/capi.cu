@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -85,7 +86,69 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
     }
+    // the same from the device's stream-ordered memory pool (kept warm: a streaming compressor is created and
+    // destroyed per stream, and cudaMalloc / cudaFree of its windows would cost more than compressing a short stream)
+    cudaError_t ensure_pool(size_t n, cudaStream_t st) {
+        if (n <= cap) return cudaSuccess;
+        release_pool(st);
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), st);
+        if (e == cudaSuccess) cap = n;
+        else p = nullptr;
+        return e;
+    }
+    void release_pool(cudaStream_t st) {
+        if (p) cudaFreeAsync(p, st);
+        p = nullptr;
+        cap = 0;
+    }
 };
+// Pinned host buffers are expensive to create (the pages are locked one by one): a few are kept for the next stream.
+struct PinnedCache {
+    std::mutex mu;
+    struct Entry { uint8_t* p; size_t cap; } slot[4] = {};
+    uint8_t* get(size_t want, size_t* cap) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (auto& e : slot)
+                if (e.p && e.cap >= want) {
+                    uint8_t* p = e.p;
+                    *cap = e.cap;
+                    e.p = nullptr;
+                    return p;
+                }
+        }
+        uint8_t* p = nullptr;
+        if (cudaMallocHost(&p, want) != cudaSuccess) return nullptr;
+        *cap = want;
+        return p;
+    }
+    void put(uint8_t* p, size_t cap) {
+        if (!p) return;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (auto& e : slot)
+                if (!e.p) {
+                    e.p = p;
+                    e.cap = cap;
+                    return;
+                }
+        }
+        cudaFreeHost(p);
+    }
+};
+inline PinnedCache& pinned_cache() {
+    static PinnedCache* c = new PinnedCache();  // never destroyed: the CUDA runtime may be gone before static destructors run
+    return *c;
+}
+inline void keep_pool_warm(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    done[device] = true;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return;
+    uint64_t keep = ~0ull;  // freed blocks stay in the pool instead of going back to the driver at every synchronisation
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+}
 }  // namespace
 
 struct fb200_ctx {
@@ -1194,7 +1257,8 @@ struct fb200_deflate {
     DevBuf<uint32_t> nx[2];
     DevBuf<uint32_t> tokbuf;        // tokens of the open block between parts (the context's token buffer is per call)
     int cur = 0;
-    size_t cap = 0;                 // positions a window holds
+    size_t cap = 0;                 // positions a window holds now (grows with the stream up to cap_full)
+    size_t cap_full = 0;            // history + two parts + slack
     size_t part = 0;                // bytes per part
     uint64_t wbase = 0;             // stream position of window index 0 (multiple of 32768)
     size_t filled = 0;              // bytes in the window
@@ -1212,8 +1276,17 @@ struct fb200_deflate {
     uint64_t total_in = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_ev = nullptr;
-    uint8_t* h_out = nullptr;       // pinned: a part's output on its way to the writer
-    size_t h_out_cap = 0;
+    uint8_t* h_outs[2] = {nullptr, nullptr};  // pinned: a part's output on its way to the writer (one being filled, one being emitted)
+    size_t h_out_caps[2] = {0, 0};
+    int h_cur = 0;                  // the buffer the next stream_run fills
+    uint8_t* h_out = nullptr;       // = h_outs[h_cur] during a stream_run
+    const uint8_t* pend_ptr = nullptr;  // a finished part's bytes, not yet handed to the writer
+    size_t pend_len = 0;
+    int pend_buf = 0;
+    DevBuf<uint8_t> d_outs[2];      // a part's packed bytes on the device: copied back while the next part is being compressed
+    cudaStream_t out_stream = nullptr;
+    cudaEvent_t body_ev = nullptr, out_ev[2] = {nullptr, nullptr};
+    uint8_t carry_in[2] = {0, 0};   // bits of the previous part that share the first byte of the buffer's bytes
     size_t last_trigger = 0;        // value of `filled` when the last part was started (or the segment began)
     // the part in flight (worker thread).  The worker only reads the stream state; what it found is applied by the
     // caller's thread when it joins (stream_apply), so that write() never races with it.
@@ -1236,16 +1309,45 @@ namespace {
 constexpr size_t kStreamHist = 65536;  // 32 KiB of match history and 32 KiB before it to rebuild that history's chains
 
 int stream_alloc(fb200_deflate* d) {
-    for (int i = 0; i < 2; i++) {
-        FB_CUDA_CHECK(d->win[i].ensure(d->cap + 1024));
-        if (d->level_mode) {
-            FB_CUDA_CHECK(d->link[i].ensure(d->cap + 1024));
-            FB_CUDA_CHECK(d->nx[i].ensure(d->cap + 1024));
+    keep_pool_warm(d->device);
+    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&d->out_stream, cudaStreamNonBlocking));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&d->copy_ev, cudaEventDisableTiming));
+    FB_CUDA_CHECK(cudaEventCreateWithFlags(&d->body_ev, cudaEventDisableTiming));
+    for (auto& e : d->out_ev) FB_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    FB_CUDA_CHECK(d->win[0].ensure_pool(d->cap + 1024, d->copy_stream));
+    if (d->level_mode) {
+        FB_CUDA_CHECK(d->link[0].ensure_pool(d->cap + 1024, d->copy_stream));
+        FB_CUDA_CHECK(d->nx[0].ensure_pool(d->cap + 1024, d->copy_stream));
+        FB_CUDA_CHECK(d->tokbuf.ensure_pool(kTokensPerBlock, d->copy_stream));
+    }
+    FB_CUDA_CHECK(cudaStreamSynchronize(d->copy_stream));
+    return FB200_OK;
+}
+
+// Moves the window contents [from, filled) to the start of the other buffer set, which gets room for `newcap` positions.
+int stream_move(fb200_deflate* d, size_t from, size_t newcap, cudaStream_t st) {
+    const int o = d->cur ^ 1;
+    const size_t keep = d->filled - from;
+    FB_CUDA_CHECK(cudaStreamSynchronize(d->copy_stream));  // the caller's bytes have landed; nothing else writes the window
+    FB_CUDA_CHECK(d->win[o].ensure_pool(newcap + 1024, st));
+    if (keep) FB_CUDA_CHECK(cudaMemcpyAsync(d->win[o].p, d->win[d->cur].p + from, keep, cudaMemcpyDeviceToDevice, st));
+    if (d->level_mode) {
+        FB_CUDA_CHECK(d->link[o].ensure_pool(newcap + 1024, st));
+        FB_CUDA_CHECK(d->nx[o].ensure_pool(newcap + 1024, st));
+        if (keep) {
+            FB_CUDA_CHECK(cudaMemcpyAsync(d->link[o].p, d->link[d->cur].p + from, keep * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
+            FB_CUDA_CHECK(cudaMemcpyAsync(d->nx[o].p, d->nx[d->cur].p + from, keep * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         }
     }
-    if (d->level_mode) FB_CUDA_CHECK(d->tokbuf.ensure(kTokensPerBlock));
-    FB_CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
-    FB_CUDA_CHECK(cudaEventCreateWithFlags(&d->copy_ev, cudaEventDisableTiming));
+    if (newcap != d->cap) {  // growing: the old, smaller set goes back to the pool
+        d->win[d->cur].release_pool(st);
+        d->link[d->cur].release_pool(st);
+        d->nx[d->cur].release_pool(st);
+    }
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    d->cur = o;
+    d->cap = newcap;
     return FB200_OK;
 }
 
@@ -1275,16 +1377,7 @@ int stream_slide(fb200_deflate* d, cudaStream_t st) {
     const size_t shift = (d->seg_begin - kStreamHist) / 32768 * 32768;
     int rc = stream_sum(d, d->filled, st);  // bytes about to leave the window are summed first
     if (rc) return rc;
-    const int o = d->cur ^ 1;
-    const size_t keep = d->filled - shift;
-    FB_CUDA_CHECK(cudaStreamSynchronize(d->copy_stream));
-    FB_CUDA_CHECK(cudaMemcpyAsync(d->win[o].p, d->win[d->cur].p + shift, keep, cudaMemcpyDeviceToDevice, st));
-    if (d->level_mode) {
-        FB_CUDA_CHECK(cudaMemcpyAsync(d->link[o].p, d->link[d->cur].p + shift, keep * sizeof(uint16_t), cudaMemcpyDeviceToDevice, st));
-        FB_CUDA_CHECK(cudaMemcpyAsync(d->nx[o].p, d->nx[d->cur].p + shift, keep * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    }
-    FB_CUDA_CHECK(cudaStreamSynchronize(st));
-    d->cur = o;
+    if ((rc = stream_move(d, shift, d->cap, st))) return rc;
     d->wbase += shift;
     d->filled -= shift;
     d->seg_begin -= shift;
@@ -1324,14 +1417,18 @@ int stream_run(fb200_deflate* d, size_t n, size_t parse_end, size_t chunk_end, s
     if (rc) return rc;
     const size_t begin = d->seg_begin;
     const size_t bound = round_up(fb200_compress_bound(n - begin, d->mode) + 64, 16);
-    FB_CUDA_CHECK(c->d_out.ensure(bound));
-    if (bound + 16 > d->h_out_cap) {
-        if (d->h_out) cudaFreeHost(d->h_out);
-        d->h_out = nullptr;
-        d->h_out_cap = 0;
-        FB_CUDA_CHECK(cudaMallocHost(&d->h_out, bound + 16));
-        d->h_out_cap = bound + 16;
+    const int hb = d->h_cur;
+    FB_CUDA_CHECK(d->d_outs[hb].ensure_pool(bound + bound / 8, st));
+    if (bound + 16 > d->h_out_caps[hb]) {
+        pinned_cache().put(d->h_outs[hb], d->h_out_caps[hb]);
+        d->h_out_caps[hb] = 0;
+        d->h_outs[hb] = pinned_cache().get(bound + bound / 8 + 16, &d->h_out_caps[hb]);
+        if (!d->h_outs[hb]) {
+            fb::set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
+            return FB200_ERR_CUDA;
+        }
     }
+    d->h_out = d->h_outs[hb];
     PartCarry carry;
     carry.bit_phase = d->bit_phase;
     carry.parse_end = parse_end;
@@ -1351,23 +1448,41 @@ int stream_run(fb200_deflate* d, size_t n, size_t parse_end, size_t chunk_end, s
         std::swap(c->link, d->link[d->cur]);  // the pipeline uses the context's link buffer: lend it ours for the call
     }
     size_t out_end = 0;
-    rc = deflate_body_device(c, d->container, d->mode, d->win[d->cur].p, begin, n, d->d_skip.p, nskip, c->d_out.p, c->d_out.cap, &out_end,
-                             final_flush, false, st, nullptr, nullptr, 0, nullptr, 0, &carry);
+    static const bool trace = getenv("FB200_STREAM_TRACE") != nullptr;  // development: host-side times of every part
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = deflate_body_device(c, d->container, d->mode, d->win[d->cur].p, begin, n, d->d_skip.p, nskip, d->d_outs[hb].p, d->d_outs[hb].cap,
+                             &out_end, final_flush, false, st, nullptr, nullptr, 0, nullptr, 0, &carry);
+    const auto t1 = std::chrono::steady_clock::now();
     if (d->level_mode) std::swap(c->link, d->link[d->cur]);
     if (rc) return rc;
     // output: whole bytes go to the writer, the bits of the last partial byte wait for the next part
     const size_t nfull = parse_end ? (size_t)(carry.total_bits >> 3) : out_end;
     const size_t ncopy = (size_t)((carry.total_bits + 7) >> 3);
-    if (ncopy) FB_CUDA_CHECK(cudaMemcpyAsync(d->h_out, c->d_out.p, ncopy, cudaMemcpyDeviceToHost, st));
+    // the packed bytes go back on their own stream (the pipeline has synchronized `st`, so they are complete): a part
+    // returns as soon as its carry is known, and the copy runs while the next part is being compressed
+    if (ncopy) FB_CUDA_CHECK(cudaMemcpyAsync(d->h_out, d->d_outs[hb].p, ncopy, cudaMemcpyDeviceToHost, d->out_stream));
+    FB_CUDA_CHECK(cudaEventRecord(d->out_ev[hb], d->out_stream));
     if (d->level_mode && carry.leftover) FB_CUDA_CHECK(cudaMemcpyAsync(d->tokbuf.p, c->tokens.p, (size_t)carry.leftover * 4, cudaMemcpyDeviceToDevice, st));
+    uint8_t last = 0;  // the byte the next part's bits share
+    const uint32_t phase = parse_end ? (uint32_t)(carry.total_bits & 7) : 0;
+    if (phase) FB_CUDA_CHECK(cudaMemcpyAsync(&last, d->d_outs[hb].p + nfull, 1, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (ncopy == 0) d->h_out[0] = 0;
-    d->h_out[0] |= d->carry_byte;
+    if (!parse_end) FB_CUDA_CHECK(cudaEventSynchronize(d->out_ev[hb]));  // flush / finish hand their bytes out at once
+    if (trace) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "stream part: begin %zu n %zu parse_end %zu: body %.3f ms, carry %.3f ms, %zu bytes on their way back\n", begin, n, parse_end,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count(), ncopy);
+    }
+    d->carry_in[hb] = d->carry_byte;
+    if (!parse_end) {
+        if (ncopy == 0) d->h_out[0] = 0;
+        d->h_out[0] |= d->carry_byte;
+    }
     d->job_out = nfull;
     fb200_deflate::Result& r = d->res;
     r.part = parse_end != 0;
-    r.bit_phase = parse_end ? (uint32_t)(carry.total_bits & 7) : 0;
-    r.carry_byte = r.bit_phase ? d->h_out[nfull] : 0;
+    r.bit_phase = phase;
+    r.carry_byte = phase ? (uint8_t)(last | (nfull == 0 ? d->carry_byte : 0)) : 0;
     r.carry_tok = carry.leftover;
     r.cut = carry.cut;
     r.fp0 = carry.last_rp;
@@ -1401,15 +1516,30 @@ void stream_apply(fb200_deflate* d) {
     }
 }
 
-// waits for the part in flight and hands its bytes to the writer (caller's thread)
+// waits for the part in flight and takes its results (caller's thread); its bytes wait for stream_emit
 int stream_join(fb200_deflate* d) {
     if (!d->job_running) return FB200_OK;
+    static const bool trace = getenv("FB200_STREAM_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     d->worker.join();
+    if (trace) fprintf(stderr, "stream join: waited %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     d->job_running = false;
     if (d->job_rc) return d->job_rc;
     stream_apply(d);
-    if (d->job_out && d->writer(d->user, d->h_out, d->job_out)) return FB200_NO_SPACE_LEFT;
+    d->pend_ptr = d->h_out;  // handed to the writer by stream_emit, after the next part has been started
+    d->pend_len = d->job_out;
+    d->pend_buf = d->h_cur;
     d->job_out = 0;
+    d->h_cur ^= 1;
+    return FB200_OK;
+}
+int stream_emit(fb200_deflate* d) {
+    const size_t n = d->pend_len;
+    d->pend_len = 0;
+    if (n == 0) return FB200_OK;
+    FB_CUDA_CHECK(cudaEventSynchronize(d->out_ev[d->pend_buf]));  // the part's bytes have arrived in pinned memory
+    d->h_outs[d->pend_buf][0] |= d->carry_in[d->pend_buf];
+    if (d->writer(d->user, d->pend_ptr, n)) return FB200_NO_SPACE_LEFT;
     return FB200_OK;
 }
 
@@ -1458,14 +1588,16 @@ int fb200_deflate_create(fb200_ctx* ctx, int container, int mode, fb200_write_fn
     d->writer = writer;
     d->user = user;
     d->sum = container == FB200_ZLIB ? 1u : 0u;  // Adler-32 / CRC-32 of nothing
-    // bytes per part: FB200_STREAM_PART (KiB) for tests and tuning; 32 MiB keeps every kernel's grid full
-    size_t part_kib = 32768;
+    // bytes per part: FB200_STREAM_PART (KiB) for tests and tuning; 64 MiB parts run at 0.8 of the one-shot rate (the
+    // fixed cost of a part, its synchronisations and short kernels, is about 0.8 ms)
+    size_t part_kib = 65536;
     if (const char* e = getenv("FB200_STREAM_PART")) {
         const long v = atol(e);
         if (v >= 128 && v <= (1 << 20)) part_kib = (size_t)v;
     }
     d->part = part_kib << 10;
-    d->cap = kStreamHist + 2 * d->part + (1u << 20);
+    d->cap_full = kStreamHist + 2 * d->part + (1u << 20);
+    d->cap = d->cap_full < kStreamHist + (3u << 20) ? d->cap_full : kStreamHist + (3u << 20);  // short streams stay small
     if (cudaSetDevice(ctx->device) != cudaSuccess || stream_alloc(d) != FB200_OK) {
         fb200_deflate_destroy(d);
         return FB200_ERR_CUDA;
@@ -1488,9 +1620,17 @@ int fb200_deflate_write(fb200_deflate* d, const uint8_t* data, size_t n) {
     if (d->finished) return d->err = FB200_INVALID_STATE;
     if (cudaSetDevice(d->device) != cudaSuccess) return d->err = FB200_ERR_CUDA;
     while (n) {
-        if (d->filled == d->cap) {  // make room: finish the part in flight, run another if need be, slide
+        if (d->filled == d->cap && d->cap < d->cap_full) {  // a stream that keeps coming gets a bigger window
+            int rc = stream_join(d);
+            if (!rc) rc = stream_emit(d);
+            const size_t bigger = d->cap * 4 < d->cap_full ? d->cap * 4 : d->cap_full;
+            if (!rc) rc = stream_move(d, 0, bigger, d->ctx->stream);
+            if (rc) return d->err = rc;
+        } else if (d->filled == d->cap) {  // make room: finish the part in flight, run another if need be, slide
             int rc = stream_maybe_part(d, true);
+            if (!rc) rc = stream_emit(d);
             if (!rc) rc = stream_join(d);
+            if (!rc) rc = stream_emit(d);
             if (!rc) rc = stream_slide(d, d->ctx->stream);
             if (rc) return d->err = rc;
             if (d->filled == d->cap) return d->err = FB200_NO_SPACE_LEFT;  // cannot happen: a part always frees more than it keeps
@@ -1505,9 +1645,22 @@ int fb200_deflate_write(fb200_deflate* d, const uint8_t* data, size_t n) {
         data += take;
         n -= take;
         if (d->filled - d->last_trigger >= d->part) {  // a part's worth since the last one: take its results, start the next
+            static const bool trace = getenv("FB200_STREAM_TRACE") != nullptr;
+            const auto t0 = std::chrono::steady_clock::now();
             int rc = stream_join(d);
+            const auto t1 = std::chrono::steady_clock::now();
             if (!rc) rc = stream_slide(d, d->ctx->stream);  // between parts: nothing reads the window
+            const auto t2 = std::chrono::steady_clock::now();
             if (!rc) rc = stream_maybe_part(d, false);
+            if (!rc) rc = stream_emit(d);  // the finished part's bytes go out while the next one is being compressed
+            if (trace) {
+                const auto t3 = std::chrono::steady_clock::now();
+                static std::chrono::steady_clock::time_point last = t0;
+                fprintf(stderr, "stream trigger: since last %.3f ms | join+writer %.3f ms, slide %.3f ms, launch %.3f ms\n",
+                        std::chrono::duration<double, std::milli>(t0 - last).count(), std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                        std::chrono::duration<double, std::milli>(t2 - t1).count(), std::chrono::duration<double, std::milli>(t3 - t2).count());
+                last = t3;
+            }
             if (rc) return d->err = rc;
         }
     }
@@ -1522,6 +1675,7 @@ int fb200_deflate_write(fb200_deflate* d, const uint8_t* data, size_t n) {
 static int deflate_close_segment(fb200_deflate* d, bool final_flush) {
     if (cudaSetDevice(d->device) != cudaSuccess) return FB200_ERR_CUDA;
     int rc = stream_join(d);
+    if (!rc) rc = stream_emit(d);
     if (rc) return rc;
     fb200_ctx* c = d->ctx;
     FB_CUDA_CHECK(cudaStreamSynchronize(d->copy_stream));
@@ -1574,14 +1728,22 @@ void fb200_deflate_destroy(fb200_deflate* d) {
     if (!d) return;
     if (d->job_running) d->worker.join();
     if (cudaSetDevice(d->device) != cudaSuccess) (void)cudaGetLastError();
+    if (d->out_stream) cudaStreamSynchronize(d->out_stream);  // a part's bytes may still be on their way back
     for (int i = 0; i < 2; i++) {
-        d->win[i].release();
-        d->link[i].release();
-        d->nx[i].release();
+        d->win[i].release_pool(d->copy_stream);
+        d->link[i].release_pool(d->copy_stream);
+        d->nx[i].release_pool(d->copy_stream);
+        pinned_cache().put(d->h_outs[i], d->h_out_caps[i]);
     }
-    d->tokbuf.release();
+    d->tokbuf.release_pool(d->copy_stream);
+    for (auto& b : d->d_outs) b.release_pool(d->copy_stream);
+    if (d->out_stream) cudaStreamSynchronize(d->out_stream);
+    for (auto& e : d->out_ev)
+        if (e) cudaEventDestroy(e);
+    if (d->body_ev) cudaEventDestroy(d->body_ev);
+    if (d->out_stream) cudaStreamDestroy(d->out_stream);
     d->d_skip.release();
-    if (d->h_out) cudaFreeHost(d->h_out);
+    if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
     if (d->copy_ev) cudaEventDestroy(d->copy_ev);
     if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     delete d;
@@ -1591,19 +1753,31 @@ void fb200_deflate_destroy(fb200_deflate* d) {
 // streaming decompressor: Decompressor (inflate.zig:43-355).  One member per decompress()/next()
 // sequence; reset() continues with the next member of the same reader, keeping the history
 // (CircularBuffer.wp is not reset, so later members may reach into earlier output).
+//
+// The reader is pulled on demand, a chunk at a time, and a member is decoded piece by piece: every call of the
+// kernel takes the input read so far and decodes whole deflate blocks until the input, or the room for output, runs
+// out inside a block; it then stops at the start of that block (kMemberPartial) and the next call resumes there
+// with more input, the last 32 KiB of output as history.  Output is handed out as soon as a piece is decoded, so
+// memory stays bounded by the piece size whatever the member's size.  Reading stops once the member's footer has
+// been seen; what was read past it stays available (next member after reset(), or fb200_inflate_unused).
 // =============================================================================================
 struct fb200_inflate {
     fb200_ctx* ctx;
     int container;
     fb200_read_fn reader;
     void* user;
-    std::vector<uint8_t> in;     // everything read so far and not yet consumed
-    size_t in_pos = 0;           // start of the current member inside `in`
-    std::vector<uint8_t> hist;   // last <= 32768 bytes of earlier members' output
-    uint64_t total_out = 0;      // bytes produced by earlier members (CircularBuffer.wp)
-    std::vector<uint8_t> out;    // current member's plain bytes
+    std::vector<uint8_t> in;     // input read and not yet consumed; decoding goes on at bit `start_bit` of in[0]
+    uint32_t start_bit = 0;
+    bool reader_eof = false;
+    bool started = false;        // the current member's container header has been consumed
+    std::vector<uint8_t> hist;   // last <= 32768 bytes of output (earlier members included)
+    uint64_t member_out = 0;     // plain bytes of the current member so far
+    uint32_t sum = 0;            // their CRC-32 / Adler-32
+    std::vector<uint8_t> out;    // the decoded piece being handed out
     size_t out_pos = 0;
-    enum { kHeader, kDecoded, kEnd } state = kHeader;
+    size_t read_chunk = 65536;   // grows to 8 MiB while a member keeps asking for more
+    size_t out_cap = 32u << 20;  // room for one piece's output
+    enum { kDecoding, kEnd } state = kDecoding;
     int err = 0;
 };
 
@@ -1615,48 +1789,102 @@ int fb200_inflate_create(fb200_ctx* ctx, int container, fb200_read_fn reader, vo
     s->container = container;
     s->reader = reader;
     s->user = user;
+    s->sum = container == FB200_ZLIB ? 1u : 0u;
     *out = s;
     return FB200_OK;
 }
-static void inflate_slurp(fb200_inflate* s) {
-    if (!s->reader) return;
-    uint8_t buf[65536];
-    for (;;) {
-        const size_t got = s->reader(s->user, buf, sizeof buf);
-        if (got == 0) break;
-        s->in.insert(s->in.end(), buf, buf + got);
+// reads until `want` bytes are buffered or the reader is exhausted
+static void inflate_fill(fb200_inflate* s, size_t want) {
+    while (!s->reader_eof && s->in.size() < want) {
+        if (!s->reader) { s->reader_eof = true; break; }
+        const size_t have = s->in.size(), ask = want - have < 65536 ? 65536 : want - have;
+        s->in.resize(have + ask);
+        const size_t got = s->reader(s->user, s->in.data() + have, ask);
+        s->in.resize(have + (got <= ask ? got : ask));
+        if (got == 0) s->reader_eof = true;
     }
 }
-static int inflate_decode_member(fb200_inflate* s) {
-    inflate_slurp(s);
+// container footer after the final block (inflate.zig:271-275, container.zig:154-166): same order of checks
+static int inflate_footer(fb200_inflate* s) {
+    const size_t at = s->start_bit ? 1 : 0;  // the footer starts at the next byte boundary
+    const size_t need = s->container == FB200_GZIP ? 8 : s->container == FB200_ZLIB ? 4 : 0;
+    inflate_fill(s, at + need);
+    const size_t have = s->in.size() > at ? s->in.size() - at : 0;
+    const uint8_t* f = s->in.data() + at;
+    if (need) {
+        if (have < 4) return FB200_END_OF_STREAM;
+        if (s->container == FB200_GZIP) {
+            const uint32_t crc = (uint32_t)f[0] | ((uint32_t)f[1] << 8) | ((uint32_t)f[2] << 16) | ((uint32_t)f[3] << 24);
+            if (crc != s->sum) return FB200_WRONG_GZIP_CHECKSUM;
+            if (have < 8) return FB200_END_OF_STREAM;
+            const uint32_t sz = (uint32_t)f[4] | ((uint32_t)f[5] << 8) | ((uint32_t)f[6] << 16) | ((uint32_t)f[7] << 24);
+            if (sz != (uint32_t)s->member_out) return FB200_WRONG_GZIP_SIZE;
+        } else {
+            const uint32_t ad = ((uint32_t)f[0] << 24) | ((uint32_t)f[1] << 16) | ((uint32_t)f[2] << 8) | (uint32_t)f[3];
+            if (ad != s->sum) return FB200_WRONG_ZLIB_CHECKSUM;
+        }
+    }
+    const size_t used = (at + need) < s->in.size() ? at + need : s->in.size();
+    s->in.erase(s->in.begin(), s->in.begin() + used);
+    s->start_bit = 0;
+    return FB200_OK;
+}
+// Decodes the next piece of the current member into s->out (possibly nothing, when the member ends).
+static int inflate_decode_piece(fb200_inflate* s) {
     fb200_ctx* c = s->ctx;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
     FB_CUDA_CHECK(cudaSetDevice(c->device));
-    const size_t n = s->in.size() - s->in_pos;
-    const size_t hist = s->hist.size();
-    size_t cap = n * 8 + 65536;
+    cudaStream_t st = c->stream;
+    s->out.clear();
+    s->out_pos = 0;
+    if (s->in.size() < s->read_chunk / 2) inflate_fill(s, s->read_chunk);
     for (;;) {
+        const size_t n = s->in.size(), hist = s->hist.size();
         FB_CUDA_CHECK(c->d_in.ensure(n + 512));
-        FB_CUDA_CHECK(c->d_out.ensure(hist + cap + 512));
-        cudaStream_t st = c->stream;
-        if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, s->in.data() + s->in_pos, n, cudaMemcpyHostToDevice, st));
+        FB_CUDA_CHECK(c->d_out.ensure(hist + s->out_cap + 512));
+        if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, s->in.data(), n, cudaMemcpyHostToDevice, st));
         if (hist) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_out.p, s->hist.data(), hist, cudaMemcpyHostToDevice, st));
-        MemberDesc md{0, n, hist, cap, hist};
-        // the reference only checks `wp < distance` (CircularBuffer.zig:45): with more than 32 KiB of
-        // earlier output every distance is reachable
-        if (s->total_out > hist) md.hist = hist;
+        // the reference only checks `wp < distance` (CircularBuffer.zig:45): all of the history kept is reachable
+        MemberDesc md{0, n, hist, s->out_cap, hist, s->start_bit,
+                      kMemberNoFooter | (s->started ? kMemberResume : 0u) | (s->reader_eof ? 0u : kMemberPartial)};
         MemberResult res;
         int rc = run_members(c, s->container, c->d_in.p, &md, 1, c->d_out.p, &res, st);
         if (rc) return rc;
-        if (res.status == FB200_NO_SPACE_LEFT && cap < (n + 64) * 1100) {
-            cap *= 4;
+        if (res.status) return (int)res.status;  // the input is complete (or the error is real): the reference's error class
+        const bool moved = res.resume_bits > s->start_bit;
+        if (res.out_len) {
+            s->out.resize(res.out_len);
+            FB_CUDA_CHECK(cudaMemcpy(s->out.data(), c->d_out.p + hist, res.out_len, cudaMemcpyDeviceToHost));
+            s->member_out += res.out_len;
+            if (s->container == FB200_GZIP) s->sum = fb200_crc32_combine(s->sum, res.sum, res.out_len);
+            else if (s->container == FB200_ZLIB) s->sum = fb200_adler32_combine(s->sum, res.sum, res.out_len);
+            s->hist.insert(s->hist.end(), s->out.begin(), s->out.end());
+            if (s->hist.size() > kMaxDist) s->hist.erase(s->hist.begin(), s->hist.end() - kMaxDist);
+        }
+        if (moved) {
+            s->started = true;
+            const size_t whole = (size_t)(res.resume_bits >> 3);
+            s->in.erase(s->in.begin(), s->in.begin() + (whole < s->in.size() ? whole : s->in.size()));
+            s->start_bit = (uint32_t)(res.resume_bits & 7);
+        }
+        if (res.info & 1u) {  // the final block is done
+            rc = inflate_footer(s);
+            if (rc) return rc;
+            s->state = fb200_inflate::kEnd;
+            return FB200_OK;
+        }
+        if (!s->out.empty()) return FB200_OK;
+        const uint32_t why = (res.info >> 8) & 0xffu;
+        if (!moved && why == FB200_NO_SPACE_LEFT) {  // one block larger than a piece's room
+            if (s->out_cap >= ((size_t)1 << 34)) return FB200_NO_SPACE_LEFT;
+            s->out_cap *= 4;
             continue;
         }
-        if (res.status) return (int)res.status;
-        s->out.resize(res.out_len);
-        if (res.out_len) FB_CUDA_CHECK(cudaMemcpy(s->out.data(), c->d_out.p + hist, res.out_len, cudaMemcpyDeviceToHost));
-        s->out_pos = 0;
-        s->in_pos += res.consumed;
-        return FB200_OK;
+        // a block does not fit in what has been read (or nothing but headers went by): more input
+        const size_t before = s->in.size();
+        inflate_fill(s, before + s->read_chunk);
+        if (s->read_chunk < (8u << 20)) s->read_chunk *= 2;
+        if (s->in.size() == before) s->reader_eof = true;  // nothing more: the next pass decides what the truncated stream means
     }
 }
 int fb200_inflate_get(fb200_inflate* s, size_t limit, const uint8_t** data, size_t* len) {
@@ -1664,24 +1892,18 @@ int fb200_inflate_get(fb200_inflate* s, size_t limit, const uint8_t** data, size
     *data = nullptr;
     *len = 0;
     if (s->err) return s->err;
-    if (s->state == fb200_inflate::kHeader) {
-        int rc = inflate_decode_member(s);
+    while (s->out_pos == s->out.size()) {
+        if (s->state == fb200_inflate::kEnd) return FB200_OK;
+        int rc = inflate_decode_piece(s);
         if (rc) return s->err = rc;
-        s->state = fb200_inflate::kDecoded;
     }
-    if (s->state == fb200_inflate::kDecoded) {
-        size_t avail = s->out.size() - s->out_pos;
-        if (avail == 0) {
-            s->state = fb200_inflate::kEnd;
-            return FB200_OK;
-        }
-        // the reference hands out at most one 64 KiB ring's worth per call (inflate.zig:321-325)
-        size_t take = avail < 65536 ? avail : 65536;
-        if (limit && take > limit) take = limit;
-        *data = s->out.data() + s->out_pos;
-        *len = take;
-        s->out_pos += take;
-    }
+    // the reference hands out at most one 64 KiB ring's worth per call (inflate.zig:321-325)
+    size_t take = s->out.size() - s->out_pos;
+    if (take > 65536) take = 65536;
+    if (limit && take > limit) take = limit;
+    *data = s->out.data() + s->out_pos;
+    *len = take;
+    s->out_pos += take;
     return FB200_OK;
 }
 int fb200_inflate_next(fb200_inflate* s, const uint8_t** data, size_t* len) { return fb200_inflate_get(s, 0, data, len); }
@@ -1700,25 +1922,34 @@ int fb200_inflate_read(fb200_inflate* s, uint8_t* buf, size_t cap, size_t* n) {
 int fb200_inflate_reset(fb200_inflate* s) {
     if (!s) return FB200_INVALID_ARGUMENT;
     // inflate.zig:301-309: only legal once the current member has been fully delivered
-    if (s->err || !(s->state == fb200_inflate::kEnd ||
-                    (s->state == fb200_inflate::kDecoded && s->out_pos == s->out.size())))
-        return FB200_INVALID_STATE;
-    // keep the last 32 KiB as history for the next member
-    s->total_out += s->out.size();
-    s->hist.insert(s->hist.end(), s->out.begin(), s->out.end());
-    if (s->hist.size() > kMaxDist) s->hist.erase(s->hist.begin(), s->hist.end() - kMaxDist);
+    if (s->err || s->state != fb200_inflate::kEnd || s->out_pos != s->out.size()) return FB200_INVALID_STATE;
     s->out.clear();
     s->out_pos = 0;
-    s->in.erase(s->in.begin(), s->in.begin() + s->in_pos);
-    s->in_pos = 0;
-    s->state = fb200_inflate::kHeader;
+    s->member_out = 0;
+    s->sum = s->container == FB200_ZLIB ? 1u : 0u;
+    s->started = false;
+    s->state = fb200_inflate::kDecoding;
+    return FB200_OK;
+}
+int fb200_inflate_unused(fb200_inflate* s, const uint8_t** data, size_t* len) {
+    if (!s || !data || !len) return FB200_INVALID_ARGUMENT;
+    *data = s->in.empty() ? nullptr : s->in.data();
+    *len = s->in.size();
     return FB200_OK;
 }
 void fb200_inflate_set_reader(fb200_inflate* s, fb200_read_fn reader, void* user) {
     if (!s) return;
     s->reader = reader;
     s->user = user;
-    if (s->state == fb200_inflate::kEnd) s->state = fb200_inflate::kHeader;  // inflate.zig:283-288
+    s->reader_eof = false;
+    if (s->state == fb200_inflate::kEnd && s->out_pos == s->out.size()) {  // inflate.zig:283-288
+        s->out.clear();
+        s->out_pos = 0;
+        s->member_out = 0;
+        s->sum = s->container == FB200_ZLIB ? 1u : 0u;
+        s->started = false;
+        s->state = fb200_inflate::kDecoding;
+    }
 }
 void fb200_inflate_rebind(fb200_inflate* s, fb200_read_fn reader, void* user) {
     if (!s) return;

@@ -528,7 +528,7 @@ inflate_members_kernel(int container, const uint8_t* __restrict__ d_in, const Me
     }
     if (lane == 0) {
         if (status == FB200_OK) bc.align_to_byte();
-        MemberResult r;
+        MemberResult r{};
         r.out_len = pos;
         // bytes consumed: everything handed to the cursor minus whole bytes still buffered
         r.consumed = (uint64_t)((bc.next - (bc.cnt >> 3)) - (d_in + md.in_off));

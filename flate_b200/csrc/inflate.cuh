@@ -9,10 +9,22 @@ struct MemberDesc {
     uint64_t in_off, in_len;    // compressed member inside d_in
     uint64_t out_off, out_cap;  // where its plain bytes go inside d_out
     uint64_t hist;              // bytes of earlier output directly before out_off the member may reference
+    uint32_t start_bit;         // decoding starts at this bit of the first byte (a member resumed at a block boundary)
+    uint32_t flags;             // kMember*
 };
+// A streaming decompressor decodes a member piece by piece (inflate_par.cu only):
+//   kMemberResume    the container header was consumed by an earlier call: start with a block header
+//   kMemberPartial   more input may follow what is given: whatever stops the decode inside a block (input or output
+//                    running out, or an error that zero-padded look-ahead may have faked) ends the call at the start
+//                    of that block with status OK, so that it can be resumed there with more input
+//   kMemberNoFooter  leave the container footer to the caller and return the checksum of the bytes produced
+enum : uint32_t { kMemberResume = 1, kMemberPartial = 2, kMemberNoFooter = 4 };
 struct MemberResult {
     uint64_t out_len, consumed;
     uint32_t status, pad;
+    uint64_t resume_bits;       // bit offset from in_off of the block boundary the call stopped at
+    uint32_t sum;               // kMemberNoFooter: CRC-32 (gzip) / Adler-32 (zlib) of the out_len bytes produced
+    uint32_t info;              // bit 0: the final block was decoded; bits 8..15: the status that ended a partial call early
 };
 constexpr uint32_t kNeedsHistory = 100;  // internal: match reaches before the member; redo after predecessors
 

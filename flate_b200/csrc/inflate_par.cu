@@ -58,6 +58,7 @@ struct Ctrl {                 // written by one thread, read by all after a barr
     unsigned long long stored_src;
     uint32_t rounds, retries, exact_calls;
     uint32_t member;          // index of the member this CTA works on
+    unsigned long long blk_cur, blk_pos;  // cursor and output position at the start of the current block (resume point)
 };
 
 struct Shared {
@@ -715,10 +716,18 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
     bc.buf = 0;
     bc.cnt = 0;
 
+    const bool resume = (md.flags & kMemberResume) != 0, partial = (md.flags & kMemberPartial) != 0;
+    const bool nofooter = (md.flags & kMemberNoFooter) != 0;
     // ---- container header (container.zig:111-152), thread 0 ----
     if (tid == 0) {
         int status = FB200_OK;
-        if (container != FB200_RAW) {
+        S.c.blk_cur = (unsigned long long)(uintptr_t)in_begin * 8ull + md.start_bit;
+        S.c.blk_pos = 0;
+        if (md.start_bit) {
+            uint32_t skip;
+            status = bc.read(md.start_bit, skip);
+        }
+        if (container != FB200_RAW && !resume && !status) {
             uint32_t v;
             if (container == FB200_GZIP) {
                 uint32_t magic1 = 0, magic2 = 0, method = 0, flags = 0;
@@ -767,6 +776,10 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
     int status = S.c.status;
     while (status == FB200_OK) {  // inflate.zig:251-280 step: one deflate block per iteration
         __syncthreads();  // every warp has read the control block of the previous block before warp 0 rewrites it
+        if (tid == 0) {   // a block boundary: where a partial call can be resumed
+            S.c.blk_cur = S.c.cur;
+            S.c.blk_pos = S.c.pos;
+        }
         if (warp == 0) block_header(S, bc, md, fixed_ready);
         __syncthreads();
         status = S.c.status;
@@ -835,10 +848,37 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
         if (bfinal) break;
     }
     __syncthreads();
+    uint32_t info = status == FB200_OK ? 1u : 0u;  // the loop only ends without an error after the final block
+    if (status != FB200_OK && partial) {
+        // back to the start of the block that could not be completed: the caller resumes there with more input / room
+        info = ((uint32_t)status & 0xffu) << 8;
+        status = FB200_OK;
+        if (tid == 0) {
+            S.c.pos = S.c.blk_pos;
+            S.c.cur = S.c.blk_cur;
+        }
+        __syncthreads();
+    }
     const uint64_t pos = S.c.pos;
     drain_cta(W, S.c.flushed, pos);  // whatever was produced, also on error (the caller sees out_len and the status)
     __syncthreads();
 
+    uint32_t part_sum = 0;
+    if (nofooter) {
+        // the caller combines the checksums of the pieces and reads the footer itself
+        if (status == FB200_OK && container == FB200_GZIP) {
+            for (uint32_t i = tid; i < 256; i += kLanes) {
+                uint32_t c = i;
+                for (int b = 0; b < 8; b++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+                S.crc_tab[i] = c;
+            }
+            __syncthreads();
+            part_sum = cta_crc32(S, W.out, pos);
+        } else if (status == FB200_OK && container == FB200_ZLIB) {
+            part_sum = cta_adler32(S, W.out, pos);
+        }
+        if (tid == 0) bc.seek(S.c.cur);
+    } else
     // ---- protocol footer (inflate.zig:271-275, container.zig:154-166) ----
     if (status == FB200_OK && container != FB200_RAW) {
         uint32_t sum;
@@ -871,13 +911,16 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
         bc.seek(S.c.cur);
     }
     if (tid == 0) {
+        MemberResult res{};
+        res.resume_bits = S.c.cur - (unsigned long long)(uintptr_t)in_begin * 8ull;  // before the alignment below
         if (status == FB200_OK) bc.align_to_byte();
-        MemberResult res;
         res.out_len = pos;
         // bytes consumed: everything handed to the cursor minus whole bytes still buffered
         res.consumed = (uint64_t)((bc.next - (bc.cnt >> 3)) - in_begin);
         res.status = (uint32_t)status;
         res.pad = S.c.rounds | (S.c.retries << 12) | (S.c.exact_calls << 22);
+        res.sum = part_sum;
+        res.info = info;
         *result = res;
     }
 }

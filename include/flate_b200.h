@@ -188,6 +188,10 @@ int fb200_inflate_get(fb200_inflate* s, size_t limit, const uint8_t** data, size
 int fb200_inflate_read(fb200_inflate* s, uint8_t* buf, size_t cap, size_t* n);
 int fb200_inflate_reset(fb200_inflate* s);
 void fb200_inflate_set_reader(fb200_inflate* s, fb200_read_fn reader, void* user);
+/* The reader is pulled a chunk at a time, so bytes past the end of the member may have been read: they are kept for
+ * the next member (reset) and can be looked at here (valid until the next call on s).  The reference's bit reader
+ * holds at most 8 such bytes (bit_reader.zig:18-44). */
+int fb200_inflate_unused(fb200_inflate* s, const uint8_t** data, size_t* len);
 /* the caller's reader object moved (a by-value host struct, like the reference's Inflate): new callback context,
  * no change of state (fb200_inflate_set_reader restarts the header parse after an end of member, inflate.zig:283-288) */
 void fb200_inflate_rebind(fb200_inflate* s, fb200_read_fn reader, void* user);

@@ -231,3 +231,104 @@ def test_differential_corruptions_all_containers(ctx, o):
         else:
             n_err += 1
     assert n_err > 100 and n_ok > 5
+
+
+def _member_the_reference_accepts(ctx, plain, container, mode):
+    """The reference's inflate rejects a dynamic header whose code-length run crosses from the literal to the distance
+    lengths (inflate.zig:161-180) although its own block writer emits such runs; about 1 in 40 MiB of level-6 text has
+    one.  Shift the data until the one-shot path accepts the member."""
+    import flate_b200
+    for shift in range(0, 64 * 4099, 4099):
+        p = plain[shift:]
+        m = ctx.compress(p, container, mode)
+        try:
+            ctx.decompress(m, container, cap=len(p) + 64)
+            return p, m
+        except flate_b200.FlateError as e:
+            if type(e).__name__ != "InvalidDynamicBlockHeader":
+                raise
+    raise AssertionError("no acceptable member found")
+
+
+class _CountingReader:
+    """a reader that hands out at most `unit` bytes per call and counts what it was asked for"""
+
+    def __init__(self, data, unit=1 << 20):
+        self.data, self.pos, self.unit = data, 0, unit
+
+    def read(self, n):
+        n = min(n, self.unit, len(self.data) - self.pos)
+        b = self.data[self.pos:self.pos + n]
+        self.pos += n
+        return b
+
+
+def test_streaming_decompressor_pulls_on_demand_and_resumes(ctx, o):
+    """inflate.zig:313-336 next/get hand out data as it is decoded, from a reader pulled on demand (:283-309): a big
+    member is decoded piece by piece (resumed at block boundaries), the first bytes arrive long before the reader is
+    drained, reading stops near the member's end and what was read past it is kept."""
+    import flate_b200
+    from flate_b200 import synth
+    base = synth.enwik_like(24 << 20, seed=301).tobytes() + bytes(300000) + np.random.default_rng(9).integers(0, 256, 200000, dtype=np.uint8).tobytes()
+    for container, mode in ((1, 6), (2, 9), (0, 1), (1, 0)):
+        plain, member = _member_the_reference_accepts(ctx, base, container, mode)
+        trailer = b"TRAILING BYTES THAT ARE NOT PART OF THE MEMBER" * 3
+        rd = _CountingReader(member + trailer, unit=300000)
+        dec = flate_b200.Decompressor(container, rd, ctx=ctx)
+        first = dec.next()
+        assert first and plain.startswith(first)
+        assert rd.pos < len(member) // 4, "the reader was drained before the first byte was handed out"
+        got = bytearray(first)
+        while True:
+            b = dec.next()
+            if b is None:
+                break
+            assert len(b) <= 65536
+            got += b
+        assert bytes(got) == plain, (container, mode)
+        rest = dec.unread_bytes() + rd.data[rd.pos:]
+        assert rest == trailer
+        dec.close()
+
+
+def test_streaming_decompressor_members_and_errors(ctx, o):
+    """members one after the other through reset() with history kept, truncated input and a wrong checksum: same
+    error classes as the one-shot path (inflate.zig:72-78, container.zig:45-51)."""
+    import flate_b200
+    from flate_b200 import synth
+    a, ma = _member_the_reference_accepts(ctx, synth.enwik_like(3 << 20, seed=302).tobytes(), 1, 6)
+    b, mb = _member_the_reference_accepts(ctx, synth.mixed_small(400000, seed=303).tobytes(), 1, 4)
+    dec = flate_b200.Decompressor(1, _CountingReader(ma + mb, unit=70000), ctx=ctx)
+    out = io.BytesIO()
+    dec.decompress(out)
+    dec.reset()
+    dec.decompress(out)
+    assert out.getvalue() == a + b
+    # truncated inside the deflate stream, and inside the footer
+    for cut in (len(ma) // 2, len(ma) - 3):
+        dec = flate_b200.Decompressor(1, _CountingReader(ma[:cut], unit=50000), ctx=ctx)
+        with pytest.raises(flate_b200.FlateError) as ei:
+            dec.decompress(io.BytesIO())
+        assert type(ei.value).__name__ == "EndOfStream", cut
+    bad = bytearray(ma)
+    bad[-6] ^= 0x40
+    dec = flate_b200.Decompressor(1, _CountingReader(bytes(bad), unit=50000), ctx=ctx)
+    with pytest.raises(flate_b200.FlateError) as ei:
+        dec.decompress(io.BytesIO())
+    assert type(ei.value).__name__ == "WrongGzipChecksum"
+    # a corrupted block in the middle of a long member: the one-shot path's error class
+    bad = bytearray(ma)
+    for i in range(len(ma) // 2, len(ma) // 2 + 40):
+        bad[i] ^= 0xA5
+    try:
+        ctx.decompress(bytes(bad), 1)
+        want = None
+    except flate_b200.FlateError as e:
+        want = type(e).__name__
+    dec = flate_b200.Decompressor(1, _CountingReader(bytes(bad), unit=50000), ctx=ctx)
+    try:
+        dec.decompress(io.BytesIO())
+        got = None
+    except flate_b200.FlateError as e:
+        got = type(e).__name__
+    assert got == want and want is not None

@@ -66,6 +66,7 @@ pub extern "c" fn fb200_inflate_read(s: ?*InflateHandle, buf: [*]u8, cap: usize,
 pub extern "c" fn fb200_inflate_reset(s: ?*InflateHandle) c_int;
 pub extern "c" fn fb200_inflate_set_reader(s: ?*InflateHandle, r: ReadFn, user: ?*anyopaque) void;
 pub extern "c" fn fb200_inflate_rebind(s: ?*InflateHandle, r: ReadFn, user: ?*anyopaque) void;
+pub extern "c" fn fb200_inflate_unused(s: ?*InflateHandle, data: *?[*]const u8, len: *usize) c_int;
 pub extern "c" fn fb200_inflate_destroy(s: ?*InflateHandle) void;
 pub extern "c" fn fb200_debug_tokens(ctx: ?*Ctx, level: c_int, in: ?[*]const u8, n: usize, tokens: [*]u32, cap: usize, ntok: *usize) c_int;
 pub extern "c" fn fb200_debug_match_tables(ctx: ?*Ctx, level: c_int, in: [*]const u8, n: usize, r_full: [*]u32, r_quarter: [*]u32) c_int;
@@ -359,6 +360,16 @@ pub fn Inflate(comptime container: Container, comptime ReaderType: type) type {
         pub fn setReader(self: *Self, new_reader: ReaderType) void {
             self.rdr = new_reader;
             if (self.handle) |h| fb200_inflate_set_reader(h, onRead, self);
+        }
+        /// Bytes the library read from the inner reader past the end of the current member (it pulls the reader a
+        /// chunk at a time; the reference's bit reader holds at most 8 such bytes, bit_reader.zig:18-44).  They are
+        /// consumed by the next member after reset(); a caller that wants to go on reading the inner reader itself
+        /// takes them from here first.  Valid until the next call on this decompressor.
+        pub fn unreadBytes(self: *Self) []const u8 {
+            var p: ?[*]const u8 = null;
+            var n: usize = 0;
+            if (self.handle == null or fb200_inflate_unused(self.handle, &p, &n) != 0 or p == null) return &[_]u8{};
+            return p.?[0..n];
         }
         /// inflate.zig:292
         pub fn decompress(self: *Self, writer: anytype) !void {
