@@ -54,6 +54,11 @@ SIGNATURES = {
     "fb200_inflate_set_reader": (None, [_P, READ_FN, _P]),
     "fb200_inflate_rebind": (None, [_P, READ_FN, _P]),
     "fb200_inflate_unused": (_I, [_P, C.POINTER(_P), _SZP]),
+    "fb200_pool_create": (_I, [C.c_uint64, C.POINTER(_P)]),
+    "fb200_pool_devices": (_I, [_P]),
+    "fb200_pool_destroy": (None, [_P]),
+    "fb200_compress_batch": (_I, [_P, _I, _I, _SZ, _P, _P, _P, _P, _P, _P]),
+    "fb200_decompress_members_batch": (_I, [_P, _I, _P, _P, _P, _SZ, _P, _P, _P, _P, _P, _P]),
     "fb200_inflate_destroy": (None, [_P]),
     "fb200_debug_tokens": (_I, [_P, _I, _P, _SZ, _P, _SZ, _SZP]),
     "fb200_debug_match_tables": (_I, [_P, _I, _P, _SZ, _P, _P]),

@@ -269,6 +269,61 @@ def _read_all(reader):
     return b"".join(chunks)
 
 
+class Pool:
+    """Several GPUs of one node behind one call (fb200_pool_*): k independent streams, or the members of a multi-member
+    file, spread over the devices by the library (one context and one host thread per device)."""
+
+    def __init__(self, device_mask=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _check(self.lib.fb200_pool_create(device_mask, C.byref(h)))
+        self.h = h
+
+    @property
+    def devices(self):
+        return int(self.lib.fb200_pool_devices(self.h))
+
+    def compress_batch(self, items, container=RAW, mode=Level.default):
+        """items: list of bytes-like.  Returns the list of compressed streams (the reference's compress() per item)."""
+        arrs = [_as_u8(x) for x in items]
+        k = len(arrs)
+        caps = [int(self.lib.fb200_compress_bound(a.size, mode)) for a in arrs]
+        outs = [np.empty(c, dtype=np.uint8) for c in caps]
+        inp = (C.c_void_p * k)(*[_ptr(a) for a in arrs])
+        inl = (C.c_size_t * k)(*[a.size for a in arrs])
+        outp = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
+        outc = (C.c_size_t * k)(*caps)
+        outl = (C.c_size_t * k)()
+        st = (C.c_int * k)()
+        _check(self.lib.fb200_compress_batch(self.h, container, mode, k, inp, inl, outp, outc, outl, st))
+        return [outs[i][:outl[i]].tobytes() for i in range(k)]
+
+    def decompress_members(self, data, in_off, in_len, out_cap, container=GZIP):
+        """The members of one buffer, split over the devices by contiguous ranges.  Returns (plains, statuses)."""
+        a = _as_u8(data)
+        k = len(in_off)
+        io_ = np.asarray(in_off, dtype=np.uint64)
+        il = np.asarray(in_len, dtype=np.uint64)
+        oc = np.asarray(out_cap, dtype=np.uint64)
+        oo = np.zeros(k, dtype=np.uint64)
+        if k:
+            oo[1:] = np.cumsum(oc)[:-1]
+        out = np.empty(int(oc.sum()) + 1, dtype=np.uint8)
+        ol = np.zeros(k, dtype=np.uint64)
+        used = np.zeros(k, dtype=np.uint64)
+        st = np.zeros(k, dtype=np.int32)
+        self.lib.fb200_decompress_members_batch(self.h, container, _ptr(a), io_.ctypes.data, il.ctypes.data, k, out.ctypes.data,
+                                                oo.ctypes.data, oc.ctypes.data, ol.ctypes.data, used.ctypes.data, st.ctypes.data)
+        return [out[int(oo[i]):int(oo[i] + ol[i])].tobytes() for i in range(k)], [int(x) for x in st]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fb200_pool_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
 class Compressor:
     """deflate.zig:121-373 Deflate / :449-529 SimpleCompressor behind fb200_deflate_*."""
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <chrono>
 #include <mutex>
 #include <new>
@@ -18,7 +19,7 @@
 #include "pipeline.cuh"
 
 namespace fb {
-static thread_local char g_cuda_err[256] = "";
+static char g_cuda_err[256] = "";  // process-wide: worker threads (parts of a stream, devices of a pool) report through it too
 void set_last_cuda_error(cudaError_t e, const char* file, int line) {
     snprintf(g_cuda_err, sizeof g_cuda_err, "%s (%s:%d)", cudaGetErrorString(e), file, line);
 }
@@ -1951,6 +1952,121 @@ void fb200_inflate_set_reader(fb200_inflate* s, fb200_read_fn reader, void* user
         s->state = fb200_inflate::kDecoding;
     }
 }
+// =============================================================================================
+// several GPUs behind one call: one context and one host thread per device
+// =============================================================================================
+struct fb200_pool {
+    std::vector<fb200_ctx*> ctxs;
+};
+int fb200_pool_create(uint64_t device_mask, fb200_pool** out) {
+    if (!out) return FB200_INVALID_ARGUMENT;
+    *out = nullptr;
+    const int ndev = fb200_device_count();
+    if (ndev == 0) return FB200_NO_DEVICE;
+    fb200_pool* p = new (std::nothrow) fb200_pool();
+    if (!p) return FB200_INVALID_ARGUMENT;
+    for (int dev = 0; dev < ndev && dev < 64; dev++) {
+        if (device_mask && !((device_mask >> dev) & 1)) continue;
+        fb200_ctx* c = nullptr;
+        const int rc = fb200_ctx_create(dev, &c);
+        if (rc) {
+            fb200_pool_destroy(p);
+            return rc;
+        }
+        p->ctxs.push_back(c);
+    }
+    if (p->ctxs.empty()) {
+        fb200_pool_destroy(p);
+        return FB200_INVALID_ARGUMENT;
+    }
+    *out = p;
+    return FB200_OK;
+}
+int fb200_pool_devices(const fb200_pool* p) { return p ? (int)p->ctxs.size() : 0; }
+void fb200_pool_destroy(fb200_pool* p) {
+    if (!p) return;
+    for (fb200_ctx* c : p->ctxs) fb200_ctx_destroy(c);
+    delete p;
+}
+int fb200_compress_batch(fb200_pool* p, int container, int mode, size_t k, const uint8_t* const* in, const size_t* in_len,
+                         uint8_t* const* out, const size_t* out_cap, size_t* out_len, int* status) {
+    if (!p || (k && (!in || !in_len || !out || !out_cap || !out_len))) return FB200_INVALID_ARGUMENT;
+    const size_t ndev = p->ctxs.size();
+    // largest first onto the least loaded device (the time of a stream grows with its size)
+    std::vector<size_t> order(k);
+    for (size_t i = 0; i < k; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return in_len[a] != in_len[b] ? in_len[a] > in_len[b] : a < b; });
+    std::vector<std::vector<size_t>> share(ndev);
+    std::vector<uint64_t> load(ndev, 0);
+    for (size_t i : order) {
+        size_t best = 0;
+        for (size_t d = 1; d < ndev; d++)
+            if (load[d] < load[best]) best = d;
+        share[best].push_back(i);
+        load[best] += in_len[i] + 65536;
+    }
+    std::vector<int> st(k, FB200_OK);
+    std::vector<std::thread> workers;
+    for (size_t d = 0; d < ndev; d++) {
+        if (share[d].empty()) continue;
+        workers.emplace_back([&, d] {
+            for (size_t i : share[d]) {
+                out_len[i] = 0;
+                st[i] = fb200_compress(p->ctxs[d], container, mode, in[i], in_len[i], out[i], out_cap[i], &out_len[i]);
+            }
+        });
+    }
+    for (auto& w : workers) w.join();
+    int first = FB200_OK;
+    for (size_t i = 0; i < k; i++) {
+        if (status) status[i] = st[i];
+        if (first == FB200_OK && st[i]) first = st[i];
+    }
+    return first;
+}
+int fb200_decompress_members_batch(fb200_pool* p, int container, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len,
+                                   size_t k, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                                   uint64_t* consumed, int* status) {
+    if (!p || (k && (!in || !out || !in_off || !in_len || !out_off || !out_cap || !out_len))) return FB200_INVALID_ARGUMENT;
+    const size_t ndev = p->ctxs.size();
+    // contiguous ranges of members with about equal compressed bytes
+    uint64_t total = 0;
+    for (size_t i = 0; i < k; i++) total += in_len[i] + 4096;
+    std::vector<size_t> cut(ndev + 1, k);
+    cut[0] = 0;
+    uint64_t acc = 0;
+    size_t d = 1;
+    for (size_t i = 0; i < k && d < ndev; i++) {
+        acc += in_len[i] + 4096;
+        if (acc * ndev >= total * d) cut[d++] = i + 1;
+    }
+    std::vector<int> rcs(ndev, FB200_OK);
+    std::vector<std::thread> workers;
+    for (size_t dv = 0; dv < ndev; dv++) {
+        const size_t lo = cut[dv], hi = cut[dv + 1];
+        if (hi <= lo) continue;
+        workers.emplace_back([&, dv, lo, hi] {
+            // the members of a range are addressed inside the whole buffers: the device copies only what the range spans
+            uint64_t in_lo = ~0ull, out_lo = ~0ull;
+            for (size_t i = lo; i < hi; i++) {
+                in_lo = in_off[i] < in_lo ? in_off[i] : in_lo;
+                out_lo = out_off[i] < out_lo ? out_off[i] : out_lo;
+            }
+            std::vector<uint64_t> io(hi - lo), oo(hi - lo);
+            for (size_t i = lo; i < hi; i++) {
+                io[i - lo] = in_off[i] - in_lo;
+                oo[i - lo] = out_off[i] - out_lo;
+            }
+            rcs[dv] = fb200_decompress_members(p->ctxs[dv], container, in + in_lo, io.data(), in_len + lo, hi - lo, out + out_lo, oo.data(),
+                                               out_cap + lo, out_len + lo, consumed ? consumed + lo : nullptr, status ? status + lo : nullptr);
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (size_t dv = 0; dv < ndev; dv++)
+        if (rcs[dv]) return rcs[dv];
+    return FB200_OK;
+}
+
 void fb200_inflate_rebind(fb200_inflate* s, fb200_read_fn reader, void* user) {
     if (!s) return;
     s->reader = reader;  // same reader object at a new address: the read state is left alone (unlike set_reader)

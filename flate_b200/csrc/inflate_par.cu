@@ -796,7 +796,8 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
                 __syncthreads();
                 pos += piece;
                 done += piece;
-                const uint64_t upto = pos - ((pos + W.A) & 15);
+                const uint64_t tail = (pos + W.A) & 15;  // bytes of the last, incomplete 16-byte line stay in the window
+                const uint64_t upto = pos > tail ? pos - tail : 0;  // (a member that starts unaligned and has produced less than a line)
                 if (upto > flushed) {
                     drain_cta(W, flushed, upto);
                     flushed = upto;
@@ -832,7 +833,8 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
                 // drain what is complete
                 {
                     const uint64_t pos = S.c.pos, flushed = S.c.flushed;
-                    const uint64_t upto = pos - ((pos + W.A) & 15);
+                    const uint64_t tail = (pos + W.A) & 15;  // bytes of the last, incomplete 16-byte line stay in the window
+                const uint64_t upto = pos > tail ? pos - tail : 0;  // (a member that starts unaligned and has produced less than a line)
                     __syncthreads();
                     if (upto > flushed) {
                         drain_cta(W, flushed, upto);

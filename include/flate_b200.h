@@ -197,6 +197,23 @@ int fb200_inflate_unused(fb200_inflate* s, const uint8_t** data, size_t* len);
 void fb200_inflate_rebind(fb200_inflate* s, fb200_read_fn reader, void* user);
 void fb200_inflate_destroy(fb200_inflate* s);
 
+/* ---- several GPUs of one node behind one call (SURVEY.md section 8b "batch form", 8e-i) ----
+ * A pool owns one context and one host thread per device of the mask.  The k inputs of a batch are independent
+ * streams (the reference's compress() called k times, src/gzip.zig:12): they are dealt to the devices, largest first
+ * onto the least loaded one, and every device works through its share with fb200_compress (host buffers, copies
+ * overlapped inside).  Outputs land in the caller's host buffers, so there is nothing to gather afterwards.
+ * status[i] / out_len[i] per item; the call returns the first non-OK status.  The members form splits the member
+ * index of fb200_decompress_members into one contiguous range per device. */
+typedef struct fb200_pool fb200_pool;
+int fb200_pool_create(uint64_t device_mask, fb200_pool** pool); /* bit d = CUDA device d; 0 = every device present */
+int fb200_pool_devices(const fb200_pool* pool);
+void fb200_pool_destroy(fb200_pool* pool);
+int fb200_compress_batch(fb200_pool* pool, int container, int mode, size_t k, const uint8_t* const* in, const size_t* in_len,
+                         uint8_t* const* out, const size_t* out_cap, size_t* out_len, int* status);
+int fb200_decompress_members_batch(fb200_pool* pool, int container, const uint8_t* in, const uint64_t* in_off, const uint64_t* in_len,
+                                   size_t k, uint8_t* out, const uint64_t* out_off, const uint64_t* out_cap, uint64_t* out_len,
+                                   uint64_t* consumed, int* status);
+
 /* ---- test seams (all run on the GPU) ---- */
 int fb200_debug_tokens(fb200_ctx* ctx, int level, const uint8_t* in, size_t n, uint32_t* tokens, size_t cap,
                        size_t* ntok);

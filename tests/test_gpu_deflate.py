@@ -610,3 +610,29 @@ def test_streaming_parts_with_flushes(ctx, o, mode, monkeypatch):
     d.finish()
     got, want = w.getvalue(), d.output()
     assert got == want, (mode, first_diff(got, want))
+
+
+def test_pool_batch_over_all_devices(o):
+    """fb200_compress_batch / fb200_decompress_members_batch: independent streams and the members of one buffer spread
+    over every device present by the library itself; results equal the one-device calls (and the oracle)."""
+    import flate_b200
+    from flate_b200 import synth
+    pool = flate_b200.Pool(0)
+    assert pool.devices >= 1
+    items = [synth.enwik_like(200000 + 70001 * i, seed=500 + i).tobytes() for i in range(9)] + [b"", b"x", bytes(100000)]
+    for container, mode in ((1, 6), (0, 1), (2, 9)):
+        got = pool.compress_batch(items, container, mode)
+        for g, it in zip(got, items):
+            assert g == o.compress(it, container, mode)
+    members = [o.compress(it, 1, 6) for it in items]
+    blob = b"".join(members)
+    lens = [len(m) for m in members]
+    offs = [sum(lens[:i]) for i in range(len(lens))]
+    plains, st = pool.decompress_members(blob, offs, lens, [len(it) + 16 for it in items], flate_b200.GZIP)
+    # the reference's own inflate rejects some streams its writer produces (see test_gpu_inflate): compare with the one-device path
+    ctx = flate_b200.Context(0)
+    want, wst, _ = ctx.decompress_members(blob, offs, lens, [len(it) + 16 for it in items], flate_b200.GZIP)
+    assert st == list(wst) and plains == want
+    assert all(p == it for p, it, s in zip(plains, items, st) if s == 0)
+    pool.close()
+    ctx.close()

@@ -332,3 +332,18 @@ def test_streaming_decompressor_members_and_errors(ctx, o):
     except flate_b200.FlateError as e:
         got = type(e).__name__
     assert got == want and want is not None
+
+
+def test_members_batch_with_tiny_members_at_unaligned_offsets(ctx, o):
+    """an empty member and a one-byte member in the middle of a batch, at output offsets that are not multiples of 16:
+    nothing of a member's first 16-byte line may be written back before the line is complete"""
+    from flate_b200 import synth
+    items = [synth.enwik_like(200000 + 70001 * i, seed=500 + i).tobytes() for i in range(9)] + [b"", b"x", bytes(100000), b"", b"ab"]
+    members = [o.compress(it, 1, 6) for it in items]
+    blob = b"".join(members)
+    lens = [len(m) for m in members]
+    offs = [sum(lens[:i]) for i in range(len(lens))]
+    plains, st, used = ctx.decompress_members(blob, offs, lens, [len(it) + 16 for it in items], 1)
+    ok = [s == 0 for s in st]
+    assert all(p == it for p, it, good in zip(plains, items, ok) if good)
+    assert all(ok[9:])

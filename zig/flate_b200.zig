@@ -67,6 +67,12 @@ pub extern "c" fn fb200_inflate_reset(s: ?*InflateHandle) c_int;
 pub extern "c" fn fb200_inflate_set_reader(s: ?*InflateHandle, r: ReadFn, user: ?*anyopaque) void;
 pub extern "c" fn fb200_inflate_rebind(s: ?*InflateHandle, r: ReadFn, user: ?*anyopaque) void;
 pub extern "c" fn fb200_inflate_unused(s: ?*InflateHandle, data: *?[*]const u8, len: *usize) c_int;
+pub const PoolHandle = opaque {};
+pub extern "c" fn fb200_pool_create(device_mask: u64, pool: *?*PoolHandle) c_int;
+pub extern "c" fn fb200_pool_devices(pool: ?*const PoolHandle) c_int;
+pub extern "c" fn fb200_pool_destroy(pool: ?*PoolHandle) void;
+pub extern "c" fn fb200_compress_batch(pool: ?*PoolHandle, container: c_int, mode: c_int, k: usize, in: [*]const [*]const u8, in_len: [*]const usize, out: [*]const [*]u8, out_cap: [*]const usize, out_len: [*]usize, status: ?[*]c_int) c_int;
+pub extern "c" fn fb200_decompress_members_batch(pool: ?*PoolHandle, container: c_int, in: [*]const u8, in_off: [*]const u64, in_len: [*]const u64, k: usize, out: [*]u8, out_off: [*]const u64, out_cap: [*]const u64, out_len: [*]u64, consumed: ?[*]u64, status: ?[*]c_int) c_int;
 pub extern "c" fn fb200_inflate_destroy(s: ?*InflateHandle) void;
 pub extern "c" fn fb200_debug_tokens(ctx: ?*Ctx, level: c_int, in: ?[*]const u8, n: usize, tokens: [*]u32, cap: usize, ntok: *usize) c_int;
 pub extern "c" fn fb200_debug_match_tables(ctx: ?*Ctx, level: c_int, in: [*]const u8, n: usize, r_full: [*]u32, r_quarter: [*]u32) c_int;
