@@ -54,6 +54,7 @@ SIGNATURES = {
     "fb200_inflate_set_reader": (None, [_P, READ_FN, _P]),
     "fb200_inflate_rebind": (None, [_P, READ_FN, _P]),
     "fb200_inflate_unused": (_I, [_P, C.POINTER(_P), _SZP]),
+    "fb200_decompress_gzip_file": (_I, [_P, _P, _SZ, _P, _SZ, _SZP, _SZP, _SZP]),
     "fb200_pool_create": (_I, [C.c_uint64, C.POINTER(_P)]),
     "fb200_pool_devices": (_I, [_P]),
     "fb200_pool_destroy": (None, [_P]),

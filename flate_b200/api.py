@@ -128,6 +128,22 @@ class Context:
             _check(rc)
             return out[: n.value].tobytes(), used.value
 
+    def decompress_gzip_file(self, data, cap=None):
+        """A multi-member gzip file without a member index: members are found and inflated in parallel, the result is
+        the sequential loop's (decompress / reset per member).  Returns (plain, consumed, members)."""
+        a = _as_u8(data)
+        if cap is None:
+            cap = max(1 << 16, a.size * 8)
+        while True:
+            out = np.empty(cap, dtype=np.uint8)
+            n, used, mem = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+            rc = self.lib.fb200_decompress_gzip_file(self.h, _ptr(a), a.size, out.ctypes.data, cap, C.byref(n), C.byref(used), C.byref(mem))
+            if rc == 17 and cap < (a.size + 64) * 1100:  # NoSpaceLeft: our buffer; n.value is the size the file claims
+                cap = max(cap * 4, n.value + 64)
+                continue
+            _check(rc)
+            return out[:n.value].tobytes(), used.value, mem.value
+
     def decompress_members(self, data, in_off, in_len, out_cap, container=GZIP):
         """k independent members in one launch.  Returns (list of plain bytes, status list)."""
         a = _as_u8(data)

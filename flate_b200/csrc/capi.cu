@@ -1953,6 +1953,113 @@ void fb200_inflate_set_reader(fb200_inflate* s, fb200_read_fn reader, void* user
     }
 }
 // =============================================================================================
+// multi-member gzip file without an index: speculative cuts at header look-alikes, validated piece by piece
+// =============================================================================================
+int fb200_decompress_gzip_file(fb200_ctx* c, const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len, size_t* consumed,
+                               size_t* members) {
+    if (!c || (!in && n) || (!out && cap) || !out_len) return FB200_INVALID_ARGUMENT;
+    std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
+    *out_len = 0;
+    if (consumed) *consumed = 0;
+    if (members) *members = 0;
+    FB_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    FB_CUDA_CHECK(c->d_in.ensure(n + 512));
+    if (n) FB_CUDA_CHECK(cudaMemcpyAsync(c->d_in.p, in, n, cudaMemcpyHostToDevice, st));
+    // 1. candidates
+    uint32_t list_cap = (uint32_t)(n / 4096 + 1024);
+    std::vector<uint64_t> cuts;
+    for (;;) {
+        FB_CUDA_CHECK(c->m_desc.ensure(list_cap + 8));
+        uint32_t* d_count = c->d_scalars + 22;
+        FB_CUDA_CHECK(gzip_candidates_device(c->d_in.p, n, c->m_desc.p, list_cap, d_count, st));
+        uint32_t count = 0;
+        FB_CUDA_CHECK(cudaMemcpyAsync(&count, d_count, 4, cudaMemcpyDeviceToHost, st));
+        FB_CUDA_CHECK(cudaStreamSynchronize(st));
+        c->launches += 1;
+        if (count > list_cap) {  // a file made of header look-alikes: take them all
+            list_cap = count + 1024;
+            continue;
+        }
+        cuts.resize(count);
+        if (count) FB_CUDA_CHECK(cudaMemcpy(cuts.data(), c->m_desc.p, (size_t)count * 8, cudaMemcpyDeviceToHost));
+        break;
+    }
+    std::sort(cuts.begin(), cuts.end());
+    if (cuts.empty() || cuts[0] != 0) cuts.insert(cuts.begin(), 0);  // the file's first member starts at 0 whatever it looks like
+    // 2. decode the pieces; settle them in stream order
+    auto le32 = [&](uint64_t at) { return (uint64_t)in[at] | ((uint64_t)in[at + 1] << 8) | ((uint64_t)in[at + 2] << 16) | ((uint64_t)in[at + 3] << 24); };
+    size_t settled = 0;        // pieces [0, settled) are members
+    uint64_t settled_out = 0;  // their plain bytes
+    uint64_t end_of_members = 0;
+    while (settled < cuts.size()) {
+        const size_t k = cuts.size() - settled;
+        std::vector<uint64_t> io(k), il(k), oo(k), oc(k), ol(k), used(k);
+        std::vector<int> stv(k);
+        uint64_t total = settled_out, claimed = settled_out;
+        for (size_t i = 0; i < k; i++) {
+            const bool last = settled + i + 1 == cuts.size();
+            const uint64_t b = cuts[settled + i], e = last ? n : cuts[settled + i + 1];
+            io[i] = b;
+            il[i] = e - b;
+            const uint64_t isize = e - b >= 18 ? le32(e - 4) : 0;  // ISIZE of the member that ends where the next piece starts
+            claimed += isize;
+            // the last piece may be followed by bytes that belong to no member: its size is not known, it gets the room left
+            oc[i] = last ? (cap > total ? cap - total : 0) : isize;
+            oo[i] = total;
+            total += oc[i];
+        }
+        if (claimed > cap || total > cap) {
+            *out_len = (size_t)(claimed > total ? claimed : total);
+            return FB200_NO_SPACE_LEFT;
+        }
+        FB_CUDA_CHECK(c->d_out.ensure(total + 512));
+        int rc = fb200_decompress_members_device(c, FB200_GZIP, c->d_in.p, io.data(), il.data(), k, c->d_out.p, oo.data(), oc.data(), ol.data(),
+                                                 used.data(), stv.data(), nullptr);
+        if (rc == FB200_ERR_CUDA || rc == FB200_INVALID_ARGUMENT) return rc;
+        size_t good = 0;
+        while (good < k && stv[good] == FB200_OK && (used[good] == il[good] || settled + good + 1 == cuts.size())) good++;
+        // the good prefix is final: its bytes go home now (the pieces of a round are contiguous in the output)
+        if (good) {
+            const uint64_t lo = oo[0], hi = oo[good - 1] + ol[good - 1];
+            if (hi > lo) FB_CUDA_CHECK(cudaMemcpy(out + lo, c->d_out.p + lo, hi - lo, cudaMemcpyDeviceToHost));
+            settled_out = hi;
+            end_of_members = io[good - 1] + used[good - 1];
+        }
+        settled += good;
+        if (good == k) break;
+        // The first piece that is not a member.  What the sequential decoder does here is decode from this position with
+        // the rest of the file behind it: do exactly that.  If the member is sound, the cuts inside it were look-alikes;
+        // if it is not, this is the file's first error.
+        const uint64_t b = cuts[settled];
+        uint64_t solo_in = n - b, solo_out = settled_out, solo_cap = cap - settled_out, solo_len = 0, solo_used = 0;
+        int solo_st = 0;
+        FB_CUDA_CHECK(c->d_out.ensure(cap + 512));
+        rc = fb200_decompress_members_device(c, FB200_GZIP, c->d_in.p, &b, &solo_in, 1, c->d_out.p, &solo_out, &solo_cap, &solo_len, &solo_used,
+                                             &solo_st, nullptr);
+        if (rc == FB200_ERR_CUDA || rc == FB200_INVALID_ARGUMENT) return rc;
+        if (solo_st != FB200_OK) {
+            *out_len = (size_t)settled_out;
+            if (consumed) *consumed = (size_t)end_of_members;
+            if (members) *members = settled;
+            return solo_st;
+        }
+        if (solo_len) FB_CUDA_CHECK(cudaMemcpy(out + solo_out, c->d_out.p + solo_out, solo_len, cudaMemcpyDeviceToHost));
+        settled_out += solo_len;
+        end_of_members = b + solo_used;
+        settled += 1;
+        size_t drop = settled;
+        while (drop < cuts.size() && cuts[drop] < end_of_members) drop++;
+        cuts.erase(cuts.begin() + settled, cuts.begin() + drop);
+        if (settled < cuts.size() && cuts[settled] != end_of_members) cuts.resize(settled);  // what follows the member is not a member
+    }
+    *out_len = (size_t)settled_out;
+    if (consumed) *consumed = (size_t)end_of_members;
+    if (members) *members = settled;
+    return FB200_OK;
+}
+
+// =============================================================================================
 // several GPUs behind one call: one context and one host thread per device
 // =============================================================================================
 struct fb200_pool {

@@ -605,6 +605,35 @@ cudaError_t inflate_members(int container, const uint8_t* d_in, const MemberDesc
     inflate_members_kernel<<<k, 32, smem, st>>>(container, d_in, d_desc, k, d_out, d_res);
     return cudaGetLastError();
 }
+// ---- member discovery: every position that could start a gzip member ----
+__global__ void __launch_bounds__(256)
+gzip_candidates_kernel(const uint8_t* __restrict__ data, uint64_t n, uint64_t* __restrict__ list, uint32_t cap, uint32_t* __restrict__ count) {
+    // a thread looks at four positions through two aligned words (the buffer is readable a few bytes past n)
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t mis = (uint32_t)((uintptr_t)data & 3);
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(data - mis);
+    const uint64_t nwords = (n + mis + 3) / 4;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride) {
+        const uint32_t w0 = words[w], w1 = w + 1 < nwords ? words[w + 1] : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t v = __funnelshift_r(w0, w1, 8 * k);
+            if ((v & 0x00ffffffu) == 0x00088b1fu && (v & 0xe0000000u) == 0) {
+                const uint64_t at = w * 4 + k;
+                if (at >= mis && at - mis + 18 <= n) {  // a member is at least header + empty block + footer
+                    const uint32_t slot = atomicAdd(count, 1u);
+                    if (slot < cap) list[slot] = at - mis;
+                }
+            }
+        }
+    }
+}
+cudaError_t gzip_candidates_device(const uint8_t* d_data, uint64_t n, uint64_t* d_list, uint32_t cap, uint32_t* d_count, cudaStream_t st) {
+    cudaMemsetAsync(d_count, 0, 4, st);
+    if (n >= 18) gzip_candidates_kernel<<<148 * 8, 256, 0, st>>>(d_data, n, d_list, cap, d_count);
+    return cudaGetLastError();
+}
+
 cudaError_t crc32_device(const uint8_t* d_data, uint64_t n, uint32_t* d_result, cudaStream_t st) {
     cudaMemsetAsync(d_result, 0, 4, st);
     const uint64_t chunks = (n + kSumChunk - 1) / kSumChunk;

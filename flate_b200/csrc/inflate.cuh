@@ -37,6 +37,10 @@ cudaError_t inflate_members_par(int container, const uint8_t* d_in, const Member
 cudaError_t inflate_members(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
                             MemberResult* d_res, cudaStream_t st);
 
+// Positions of d_data[0..n) that look like the start of a gzip member (ID1 ID2 CM = 1f 8b 08, reserved flag bits zero,
+// container.zig:119-126): up to `cap` of them, unordered, into d_list; *d_count receives how many there are.
+cudaError_t gzip_candidates_device(const uint8_t* d_data, uint64_t n, uint64_t* d_list, uint32_t cap, uint32_t* d_count, cudaStream_t st);
+
 // CRC-32 (IEEE, reflected) / Adler-32 of d_data[0..n) into *d_result (device u32)
 cudaError_t crc32_device(const uint8_t* d_data, uint64_t n, uint32_t* d_result, cudaStream_t st);
 cudaError_t adler32_device(const uint8_t* d_data, uint64_t n, uint32_t* d_result, uint64_t* d_scratch2, cudaStream_t st);

@@ -197,6 +197,21 @@ int fb200_inflate_unused(fb200_inflate* s, const uint8_t** data, size_t* len);
 void fb200_inflate_rebind(fb200_inflate* s, fb200_read_fn reader, void* user);
 void fb200_inflate_destroy(fb200_inflate* s);
 
+/* ---- a multi-member gzip file without a member index ----
+ * The reference decodes concatenated members one after the other (reset() per member, inflate.zig:301-309): where a
+ * member ends is only known once it has been decoded.  Here every position that looks like a member header is found on
+ * the device (1f 8b 08, reserved flag bits zero), the file is cut there, every piece is inflated as a member in one
+ * launch (its size is the ISIZE field in front of the next cut), and a piece only counts if it decodes without error,
+ * its footer checks out and it ends exactly where the next piece starts.  The first piece that does not is the victim
+ * of a header look-alike inside compressed data: the cut after it is dropped and the pieces from there on are decoded
+ * again.  By induction the accepted pieces are exactly the members the sequential loop finds, so the output (and the
+ * first error, if the file is corrupt) is the sequential one.  Bytes after the last member are left alone: *consumed
+ * tells where the members end.  out must hold the sum of the members' sizes; when it does not, FB200_NO_SPACE_LEFT is
+ * returned and *out_len is the size the file claims (the sum of the ISIZE fields seen).  zlib and raw streams carry no
+ * marker to look for and have to go through the sequential Decompressor. */
+int fb200_decompress_gzip_file(fb200_ctx* ctx, const uint8_t* in, size_t n, uint8_t* out, size_t cap, size_t* out_len,
+                               size_t* consumed, size_t* members);
+
 /* ---- several GPUs of one node behind one call (SURVEY.md section 8b "batch form", 8e-i) ----
  * A pool owns one context and one host thread per device of the mask.  The k inputs of a batch are independent
  * streams (the reference's compress() called k times, src/gzip.zig:12): they are dealt to the devices, largest first

@@ -347,3 +347,55 @@ def test_members_batch_with_tiny_members_at_unaligned_offsets(ctx, o):
     ok = [s == 0 for s in st]
     assert all(p == it for p, it, good in zip(plains, items, ok) if good)
     assert all(ok[9:])
+
+
+def _sequential_members(ctx, blob):
+    """what the reference does with a multi-member file: decompress, reset, decompress ... (inflate.zig:301-309)"""
+    import flate_b200
+    out, pos, members = bytearray(), 0, 0
+    while pos < len(blob):
+        plain, used = ctx.decompress(blob[pos:], 1, cap=1 << 24)
+        out += plain
+        pos += used
+        members += 1
+    return bytes(out), pos, members
+
+
+def test_gzip_file_members_found_without_an_index(ctx, o):
+    """the members of a concatenated gzip file are found (header look-alikes, validated by
+    decoding) and inflated in one launch; same bytes, same member count, same end as the sequential loop, also when the
+    compressed data itself contains the magic bytes and when other bytes follow the last member."""
+    import flate_b200
+    from flate_b200 import synth
+    rng = np.random.default_rng(77)
+    plains, members = [], []
+    for i in range(40):
+        p, m = _member_the_reference_accepts(ctx, synth.enwik_like(30000 + 9973 * i, seed=700 + i).tobytes(), 1, 6)
+        plains.append(p)
+        members.append(m)
+    # members whose stored blocks carry header look-alikes, an empty member, a member of random bytes
+    decoy = (b"\x1f\x8b\x08\x00" + bytes(20)) * 500
+    for p, mode in ((decoy, 0), (b"", 6), (decoy + b"tail", 1), (rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(), 6)):
+        plains.insert(7, p)
+        members.insert(7, o.compress(p, 1, mode))
+    blob = b"".join(members)
+    want = b"".join(plains)
+    got, used, cnt = ctx.decompress_gzip_file(blob)
+    assert got == want and used == len(blob) and cnt == len(members)
+    # other bytes after the last member: the members end where the sequential loop would stop
+    got, used, cnt = ctx.decompress_gzip_file(blob + b"\x00" * 1000)
+    assert got == want and used == len(blob) and cnt == len(members)
+    # a corrupt member in the middle: the sequential loop's first error, after the members before it
+    bad = bytearray(blob)
+    at = sum(len(m) for m in members[:20]) + len(members[20]) // 2
+    for i in range(at, at + 30):
+        bad[i] ^= 0x5A
+    try:
+        _sequential_members(ctx, bytes(bad))
+        want_err = None
+    except flate_b200.FlateError as e:
+        want_err = type(e).__name__
+    assert want_err is not None
+    with pytest.raises(flate_b200.FlateError) as ei:
+        ctx.decompress_gzip_file(bytes(bad))
+    assert type(ei.value).__name__ == want_err

@@ -67,6 +67,7 @@ pub extern "c" fn fb200_inflate_reset(s: ?*InflateHandle) c_int;
 pub extern "c" fn fb200_inflate_set_reader(s: ?*InflateHandle, r: ReadFn, user: ?*anyopaque) void;
 pub extern "c" fn fb200_inflate_rebind(s: ?*InflateHandle, r: ReadFn, user: ?*anyopaque) void;
 pub extern "c" fn fb200_inflate_unused(s: ?*InflateHandle, data: *?[*]const u8, len: *usize) c_int;
+pub extern "c" fn fb200_decompress_gzip_file(ctx: ?*Ctx, in: [*]const u8, n: usize, out: [*]u8, cap: usize, out_len: *usize, consumed: ?*usize, members: ?*usize) c_int;
 pub const PoolHandle = opaque {};
 pub extern "c" fn fb200_pool_create(device_mask: u64, pool: *?*PoolHandle) c_int;
 pub extern "c" fn fb200_pool_devices(pool: ?*const PoolHandle) c_int;
