@@ -212,7 +212,21 @@ __device__ uint32_t bit_counts_warp(HuffScratch& s, uint32_t n, uint32_t max_bit
 
 // huffman_encoder.zig:62-95 generate + :251-278 assignEncodingAndSize.  Whole warp.
 // out[i] = code | len << 16 (code bit-reversed, ready for LSB-first packing); len 0 for unused.
-__device__ void huff_generate_warp(HuffScratch& s, const uint16_t* freq, uint32_t n, uint32_t max_bits, uint32_t* out) {
+// Split form (huffman-only streams: tens of thousands of blocks with full alphabets): the serial bitCounts of 32 blocks
+// runs on the 32 lanes of a warp in a kernel of its own (bit_counts_lanes_kernel), between a pass that sorts
+// (kSortOnly: sorted list to global memory) and a pass that takes up again from the per-length counts (kFromCounts).
+enum HuffPhase : int { kHuffFull = 0, kHuffSortOnly = 1, kHuffFromCounts = 2 };
+struct HuffSplit {         // per-block slots in global memory
+    uint16_t* slit;        // [288] symbols sorted by (freq, literal)
+    uint16_t* sfreq;       // [288] their frequencies
+    uint32_t* count;       // number of used symbols; kHuffDone: the block was finished by the sort pass (stored)
+    uint16_t* bit_count;   // [16] codes per length
+};
+constexpr uint32_t kHuffDone = 0xffffffffu;
+
+template <int kPhase>
+__device__ void huff_generate_warp(HuffScratch& s, const uint16_t* freq, uint32_t n, uint32_t max_bits, uint32_t* out,
+                                   const HuffSplit* split = nullptr) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t count = 0;
     for (uint32_t base = 0; base < n; base += 32) {  // compact non-zero symbols, literal order
@@ -229,21 +243,37 @@ __device__ void huff_generate_warp(HuffScratch& s, const uint16_t* freq, uint32_
         count += __popc(bal);
     }
     __syncwarp();
+    if (kPhase == kHuffSortOnly && lane == 0) *split->count = count;
     if (count <= 2) {  // :79-87
         if (lane < count) out[s.t_lit[lane]] = lane | (1u << 16);
         __syncwarp();
         return;
     }
-    // rank sort by (freq, literal): a total order, so any sort agrees with std.mem.sort (:89, :355-361)
-    for (uint32_t i = lane; i < count; i += 32) {
-        const uint32_t key = ((uint32_t)s.t_freq[i] << 16) | s.t_lit[i];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < count; j++) rank += ((((uint32_t)s.t_freq[j] << 16) | s.t_lit[j]) < key);
-        s.s_lit[rank] = s.t_lit[i];
-        s.s_freq[rank] = s.t_freq[i];
+    uint32_t mb;
+    if (kPhase != kHuffFromCounts) {
+        // rank sort by (freq, literal): a total order, so any sort agrees with std.mem.sort (:89, :355-361)
+        for (uint32_t i = lane; i < count; i += 32) {
+            const uint32_t key = ((uint32_t)s.t_freq[i] << 16) | s.t_lit[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < count; j++) rank += ((((uint32_t)s.t_freq[j] << 16) | s.t_lit[j]) < key);
+            s.s_lit[rank] = s.t_lit[i];
+            s.s_freq[rank] = s.t_freq[i];
+        }
+        __syncwarp();
+        if (kPhase == kHuffSortOnly) {
+            for (uint32_t i = lane; i < count; i += 32) {
+                split->slit[i] = s.s_lit[i];
+                split->sfreq[i] = s.s_freq[i];
+            }
+            return;
+        }
+        mb = bit_counts_warp(s, count, max_bits);
+    } else {
+        for (uint32_t i = lane; i < count; i += 32) s.s_lit[i] = split->slit[i];
+        if (lane < 16) s.bit_count[lane] = split->bit_count[lane];
+        mb = max_bits > count - 1 ? count - 1 : max_bits;  // :131
+        __syncwarp();
     }
-    __syncwarp();
-    const uint32_t mb = bit_counts_warp(s, count, max_bits);
     if (lane == 0) {
         // lengths: the last bit_count[1] symbols of the sorted list get 1 bit, the next bit_count[2] get 2, ...
         uint32_t remaining = count, code = 0;
@@ -303,14 +333,22 @@ struct HdrWriter {
 
 constexpr uint32_t kBuildWarps = 2;  // deflate blocks per CTA
 
+constexpr uint32_t kSplitSlots = 288;
+template <int kPhase>
 __global__ void __launch_bounds__(kBuildWarps * 32)
 build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restrict__ nblocks_dev,
                     const uint32_t* __restrict__ lit_freq_g, const uint32_t* __restrict__ dist_freq_g,
-                    BlockDesc* __restrict__ descs) {
+                    BlockDesc* __restrict__ descs, uint16_t* __restrict__ g_slit, uint16_t* __restrict__ g_sfreq,
+                    uint32_t* __restrict__ g_count, uint16_t* __restrict__ g_bit_count) {
     __shared__ BuildShared sh_all[kBuildWarps];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * kBuildWarps + (threadIdx.x >> 5);
     if (b >= *nblocks_dev) return;
+    HuffSplit split{nullptr, nullptr, nullptr, nullptr};
+    if (kPhase != kHuffFull) {
+        split = HuffSplit{g_slit + (size_t)b * kSplitSlots, g_sfreq + (size_t)b * kSplitSlots, g_count + b, g_bit_count + (size_t)b * 16};
+        if (kPhase == kHuffFromCounts && *split.count == kHuffDone) return;  // finished by the sort pass
+    }
     BuildShared& sh = sh_all[threadIdx.x >> 5];
     const BlockPlan pl = plans[b];
     BlockDesc& d = descs[b];
@@ -325,6 +363,7 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
     }
     if (pl.kind == 3) {  // verbatim stored block (store mode, sync marker): block_writer.zig:385-388
         if (lane == 0) { d.type = kStored; d.hdr_bits = 3; d.body_bits = 0; d.hdr[0] = pl.eof ? 1 : 0; }
+        if (kPhase == kHuffSortOnly && lane == 0) *split.count = kHuffDone;
         return;
     }
     for (uint32_t i = lane; i < kHdrWords; i += 32) sh.hdr[i] = 0;
@@ -386,16 +425,18 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
                 d.body_bits = 0;
             }
             for (uint32_t i = lane; i < kHdrWords; i += 32) d.hdr[i] = i == 0 ? (pl.eof ? 1u : 0u) : 0u;
+            if (kPhase == kHuffSortOnly && lane == 0) *split.count = kHuffDone;
             return;
         }
     }
 
     // ---- code construction ----
-    huff_generate_warp(sh.hs, sh.lit_freq, kNumLit, 15, sh.lit_code);
+    huff_generate_warp<kPhase>(sh.hs, sh.lit_freq, kNumLit, 15, sh.lit_code, &split);
+    if (kPhase == kHuffSortOnly) return;  // bit_counts_lanes_kernel and the kHuffFromCounts pass go on from here
     if (pl.kind == kHuffmanBlock) {  // huffmanDistanceEncoder, huffman_encoder.zig:340-348: one 1-bit code
         for (uint32_t i = lane; i < kNumDist; i += 32) sh.dist_code[i] = i == 0 ? (1u << 16) : 0;
     } else {
-        huff_generate_warp(sh.hs, sh.dist_freq, kNumDist, 15, sh.dist_code);
+        huff_generate_warp<kHuffFull>(sh.hs, sh.dist_freq, kNumDist, 15, sh.dist_code);
     }
     __syncwarp();
 
@@ -449,7 +490,7 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
         cg[out_index] = 255;
     }
     __syncwarp();
-    huff_generate_warp(sh.hs, sh.codegen_freq, kNumCodegen, 7, sh.codegen_code);
+    huff_generate_warp<kHuffFull>(sh.hs, sh.codegen_freq, kNumCodegen, 7, sh.codegen_code);
     __syncwarp();
 
     if (lane == 0) {
@@ -532,6 +573,107 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------
+// K5 split, middle pass: huffman_encoder.zig:122-247 bitCounts, one block per lane.  The algorithm is a serial walk
+// over about 2 n (levels) list items; a warp that runs it for ONE block spends 32 lanes on one instruction stream
+// (bit_counts_warp), here the 32 lanes carry 32 blocks.  The per-block state (level records and the leaf-count
+// triangle) lives in shared memory, element e of lane l at e * 32 + l, so the lanes never collide on a bank.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kLaneWarps = 7;
+constexpr uint32_t kLaneList = 258;                      // sorted frequencies of a block (at most 257 symbols in a huffman-only block)
+constexpr uint32_t kLaneTri = 135;                       // leaf counts (level, j <= level) of levels 1..15
+constexpr uint32_t kLaneSmemPerWarp = (17 * 2 * 4 + 17 * 2 * 2 + kLaneTri * 2 + kLaneList * 2) * 32;  // per block: 990 bytes
+__global__ void __launch_bounds__(kLaneWarps * 32, 1)
+bit_counts_lanes_kernel(const uint32_t* __restrict__ nblocks_dev, const uint16_t* __restrict__ g_sfreq, const uint32_t* __restrict__ g_count,
+                        uint16_t* __restrict__ g_bit_count) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t* lv32 = reinterpret_cast<uint32_t*>(smem_raw + (size_t)w * kLaneSmemPerWarp);  // [level][last | next_pair][lane]
+    uint16_t* lv16 = reinterpret_cast<uint16_t*>(lv32 + 17 * 2 * 32);                       // [level][next_char | needed][lane]
+    uint16_t* lc = lv16 + 17 * 2 * 32;                                                      // triangle [(level, j)][lane]
+    uint16_t* sl = lc + kLaneTri * 32;                                                      // sorted list [i][lane]
+#define LAST(level) lv32[((level) * 2 + 0) * 32 + lane]
+#define PAIR(level) lv32[((level) * 2 + 1) * 32 + lane]
+#define CHAR(level) lv16[((level) * 2 + 0) * 32 + lane]
+#define NEED(level) lv16[((level) * 2 + 1) * 32 + lane]
+#define LC(level, j) lc[((level) * ((level) + 1) / 2 - 1 + (j)) * 32 + lane]   /* level 1..15, j <= level */
+    const uint32_t kMaxI32 = 0x7fffffffu;
+    const uint32_t nb = *nblocks_dev;
+    const uint32_t ntasks = (nb + 31) / 32;  // a task: 32 consecutive blocks, one per lane
+    for (uint32_t task = blockIdx.x * kLaneWarps + w; task < ntasks; task += gridDim.x * kLaneWarps) {
+        const uint32_t b = task * 32 + lane;
+        uint32_t n = b < nb ? g_count[b] : 0;
+        if (n == kHuffDone || n <= 2 || n >= kLaneList) n = 0;  // nothing to do for this lane (n >= 258 cannot happen here)
+        if (n) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(g_sfreq + (size_t)b * kSplitSlots);
+            for (uint32_t i = 0; i < (n + 1) / 2; i++) {
+                const uint32_t v = src[i];
+                sl[(2 * i) * 32 + lane] = (uint16_t)v;
+                sl[(2 * i + 1) * 32 + lane] = (uint16_t)(v >> 16);
+            }
+            uint32_t max_bits = 15;
+            if (max_bits > n - 1) max_bits = n - 1;  // :131
+            for (uint32_t i = 0; i < kLaneTri; i++) lc[i * 32 + lane] = 0;
+            for (uint32_t i = 0; i < 17 * 2; i++) { lv32[i * 32 + lane] = 0; lv16[i * 32 + lane] = 0; }
+            const uint32_t f0 = sl[lane], f1 = sl[32 + lane], f2 = sl[64 + lane];
+            for (uint32_t level = 1; level <= max_bits; level++) {  // :144-161
+                LAST(level) = f1;
+                CHAR(level) = (uint16_t)f2;
+                PAIR(level) = level == 1 ? kMaxI32 : f0 + f1;
+                NEED(level) = 0;
+                LC(level, level) = 2;
+            }
+            NEED(max_bits) = (uint16_t)(2 * n - 4);  // :164
+            uint32_t level = max_bits;
+            while (true) {  // :168-224
+                const uint32_t last = LAST(level), next_char = CHAR(level), next_pair = PAIR(level);
+                uint32_t needed = NEED(level);
+                // :170 `next_pair == maxInt and next_char == maxInt` cannot hold: the leaf sentinel is 65535 (maxNode, :282)
+                uint32_t new_last;
+                if (next_char < next_pair) {  // :182 next item is a leaf
+                    const uint32_t next = (uint32_t)LC(level, level) + 1;
+                    new_last = next_char;
+                    LC(level, level) = (uint16_t)next;
+                    CHAR(level) = next >= n ? (uint16_t)65535u : sl[next * 32 + lane];  // :188-192
+                } else {  // :193 next item is a pair from the level below
+                    new_last = next_pair;
+                    if (level > 1)
+                        for (uint32_t j = 0; j < level; j++) LC(level, j) = LC(level - 1, j);  // :199 (the row of level 0 is all zero)
+                    else
+                        LC(1, 0) = 0;
+                    NEED(level - 1) = 2;
+                }
+                needed -= 1;
+                LAST(level) = new_last;
+                NEED(level) = (uint16_t)needed;
+                if (needed == 0) {  // :204
+                    if (level == max_bits) break;
+                    PAIR(level + 1) = last + new_last;
+                    level += 1;
+                } else {
+                    while (NEED(level - 1) > 0) {  // :217
+                        level -= 1;
+                        if (level == 0) break;
+                    }
+                }
+            }
+            uint16_t* out = g_bit_count + (size_t)b * 16;
+            for (uint32_t i = 0; i < 16; i++) out[i] = 0;
+            uint32_t bits = 1;
+            for (uint32_t l = max_bits; l > 0; l--) {  // :235-245
+                out[bits] = (uint16_t)(LC(max_bits, l) - LC(max_bits, l - 1));
+                bits++;
+            }
+        }
+        __syncwarp();
+    }
+#undef LAST
+#undef PAIR
+#undef CHAR
+#undef NEED
+#undef LC
+}
+
+// ------------------------------------------------------------------------------------------
 // K5b: block bit offsets.  Huffman blocks are not byte aligned; a stored block pads after its
 // 3 header bits (block_writer.zig:283-291), so the offset recurrence is sequential.
 // ------------------------------------------------------------------------------------------
@@ -561,7 +703,7 @@ __global__ void __launch_bounds__(kScanThreads)
 scan_block_offsets_kernel(BlockDesc* __restrict__ descs, const uint32_t* __restrict__ nblocks_dev,
                                           uint64_t start_bits, uint64_t* __restrict__ total_bits) {
     // total_bits[0] = end of the stream in bits, [1] = number of blocks, [2 + i] = start bit of block
-    // nb * (i + 1) / kPackParts (lets the host overlap the device-to-host copy of finished parts with the packing of
+    // pack_part_begin(nb, i + 1) (lets the host overlap the device-to-host copy of finished parts with the packing of
     // later ones), [16..18] = (pre, has, post) of the whole run (block-range sharded streams)
     __shared__ RunBits runs[kScanThreads];
     __shared__ uint64_t starts[kScanThreads];
@@ -592,7 +734,7 @@ scan_block_offsets_kernel(BlockDesc* __restrict__ descs, const uint32_t* __restr
     __syncthreads();
     uint32_t mark[kPackParts - 1];
 #pragma unroll
-    for (uint32_t i = 0; i + 1 < kPackParts; i++) mark[i] = (uint32_t)(((uint64_t)nb * (i + 1)) / kPackParts);
+    for (uint32_t i = 0; i + 1 < kPackParts; i++) mark[i] = pack_part_begin(nb, i + 1);
     uint64_t off = starts[threadIdx.x];
     for (uint32_t b = b0; b < b1; b++) {
         descs[b].bit_offset = off;
@@ -830,10 +972,35 @@ cudaError_t histogram_bytes(const uint8_t* in, const BlockPlan* plans, uint32_t 
     histogram_bytes_kernel<<<nblocks, kHistThreads, 0, st>>>(in, plans, nblocks, lit_freq);
     return cudaGetLastError();
 }
+size_t build_blocks_split_bytes(uint32_t max_blocks) { return (size_t)max_blocks * (kSplitSlots * 2 * 2 + 4 + 16 * 2) + 64; }
 cudaError_t build_blocks(const BlockPlan* plans, const uint32_t* nblocks_dev, uint32_t max_blocks,
-                         const uint32_t* lit_freq, const uint32_t* dist_freq, BlockDesc* descs, cudaStream_t st) {
-    build_blocks_kernel<<<(max_blocks + kBuildWarps - 1) / kBuildWarps, kBuildWarps * 32, 0, st>>>(plans, nblocks_dev, lit_freq,
-                                                                                                  dist_freq, descs);
+                         const uint32_t* lit_freq, const uint32_t* dist_freq, BlockDesc* descs, cudaStream_t st, void* split_scratch) {
+    const uint32_t grid = (max_blocks + kBuildWarps - 1) / kBuildWarps;
+    if (!split_scratch) {
+        build_blocks_kernel<kHuffFull><<<grid, kBuildWarps * 32, 0, st>>>(plans, nblocks_dev, lit_freq, dist_freq, descs, nullptr, nullptr,
+                                                                        nullptr, nullptr);
+        return cudaGetLastError();
+    }
+    // split form: sort -> bitCounts of 32 blocks per warp -> the rest (split_scratch holds build_blocks_split_bytes(max_blocks))
+    uint8_t* base = reinterpret_cast<uint8_t*>(split_scratch);
+    uint16_t* slit = reinterpret_cast<uint16_t*>(base);
+    uint16_t* sfreq = slit + (size_t)max_blocks * kSplitSlots;
+    uint16_t* bitc = sfreq + (size_t)max_blocks * kSplitSlots;
+    uint32_t* count = reinterpret_cast<uint32_t*>(bitc + (size_t)max_blocks * 16);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaFuncSetAttribute(bit_counts_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLaneWarps * kLaneSmemPerWarp));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    build_blocks_kernel<kHuffSortOnly><<<grid, kBuildWarps * 32, 0, st>>>(plans, nblocks_dev, lit_freq, dist_freq, descs, slit, sfreq, count, bitc);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t ntasks = (max_blocks + 31) / 32;  // persistent: one CTA of kLaneWarps warps per SM, tasks dealt round robin
+    const uint32_t lgrid = min((uint32_t)sms, (ntasks + kLaneWarps - 1) / kLaneWarps);
+    bit_counts_lanes_kernel<<<lgrid, kLaneWarps * 32, kLaneWarps * kLaneSmemPerWarp, st>>>(nblocks_dev, sfreq, count, bitc);
+    build_blocks_kernel<kHuffFromCounts><<<grid, kBuildWarps * 32, 0, st>>>(plans, nblocks_dev, lit_freq, dist_freq, descs, slit, sfreq, count, bitc);
     return cudaGetLastError();
 }
 cudaError_t scan_block_offsets(BlockDesc* descs, const uint32_t* nblocks_dev, uint64_t start_bits, uint64_t* total_bits,

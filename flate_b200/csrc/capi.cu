@@ -171,6 +171,7 @@ struct fb200_ctx {
     DevBuf<BlockPlan> plans;
     DevBuf<BlockDesc> descs;
     DevBuf<uint32_t> lit_freq, dist_freq;
+    DevBuf<uint8_t> huff_split;  // sorted lists and per-length counts between the passes of the split code construction
     // staging
     DevBuf<uint8_t> d_in, d_out;
     // device scalars: u32[0] total_tokens, u32[1] nblocks; u64 at byte 8: total_bits, nblocks, kPackParts-1 part
@@ -271,7 +272,7 @@ void fb200_ctx_destroy(fb200_ctx* c) {
     c->r_full.release(); c->r_quarter.release(); c->nx.release(); c->bitmap.release(); c->chunk_tokens.release();
     c->tok_offset.release(); c->tokens.release(); c->cut_rp.release(); c->plans.release(); c->descs.release();
     c->lit_freq.release(); c->dist_freq.release(); c->d_in.release(); c->d_out.release(); c->m_desc.release();
-    c->jumps.release(); c->chunk_fail.release(); c->chunk_list.release(); c->m_scratch.release();
+    c->jumps.release(); c->chunk_fail.release(); c->chunk_list.release(); c->m_scratch.release(); c->huff_split.release();
     c->timer.destroy();
     if (c->d_scalars) cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
@@ -619,7 +620,13 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
     } else {
         return FB200_INVALID_ARGUMENT;
     }
-    FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, c->descs.p, st));
+    void* split = nullptr;
+    if (mode == FB200_MODE_HUFFMAN && max_blocks >= 64) {
+        FB_CUDA_CHECK(c->huff_split.ensure(build_blocks_split_bytes(max_blocks)));
+        split = c->huff_split.p;
+    }
+    FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, max_blocks, c->lit_freq.p, c->dist_freq.p, c->descs.p, st, split));
+    c->launches += split ? 2 : 0;
     c->timer.mark(st, kPhBuild);
     FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, hdr * 8 + (carry ? carry->bit_phase : 0), total_bits_dev, st));
     zero_output_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<uint32_t*>(d_out), total_bits_dev, cap / 4);
@@ -643,7 +650,7 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
         if (!speculation_failed && out_bytes + footer_size(container) > h_cap) return FB200_NO_SPACE_LEFT;
         size_t byte_lo = 0;
         for (uint32_t i = 0; i < kPackParts && !speculation_failed; i++) {
-            const uint32_t b_lo = (uint32_t)(((uint64_t)nb * i) / kPackParts), b_hi = (uint32_t)(((uint64_t)nb * (i + 1)) / kPackParts);
+            const uint32_t b_lo = pack_part_begin(nb, i), b_hi = pack_part_begin(nb, i + 1);
             FB_CUDA_CHECK(pack_blocks_range(d_in, tokens, c->descs.p, nblocks_dev, b_lo, b_hi - b_lo, reinterpret_cast<uint32_t*>(d_out), st));
             // bytes below the next part's first bit are final once this part is packed (a shared byte goes with the next part)
             const size_t byte_hi = i + 1 == kPackParts ? out_bytes : (size_t)(c->h_scalars[2 + i] >> 3);
@@ -881,7 +888,12 @@ int fb200_simple_shard_plan(fb200_ctx* c, int container, int mode, const void* d
         c->launches += 1;
         c->timer.mark(st, kPhHist);
     }
-    FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, nslices, c->lit_freq.p, c->dist_freq.p, c->descs.p, st));
+    void* split = nullptr;
+    if (mode == FB200_MODE_HUFFMAN && nslices >= 64) {
+        FB_CUDA_CHECK(c->huff_split.ensure(build_blocks_split_bytes(nslices)));
+        split = c->huff_split.p;
+    }
+    FB_CUDA_CHECK(build_blocks(c->plans.p, nblocks_dev, nslices, c->lit_freq.p, c->dist_freq.p, c->descs.p, st, split));
     c->timer.mark(st, kPhBuild);
     FB_CUDA_CHECK(scan_block_offsets(c->descs.p, nblocks_dev, 0, total_bits_dev, st));
     c->launches += 2;

@@ -135,14 +135,25 @@ cudaError_t histogram_tokens(const uint32_t* tokens, const BlockPlan* plans, con
                              uint32_t max_blocks, uint32_t* lit_freq, uint32_t* dist_freq, cudaStream_t st);
 cudaError_t histogram_bytes(const uint8_t* in, const BlockPlan* plans, uint32_t nblocks, uint32_t* lit_freq,
                             cudaStream_t st);
+// split_scratch (may be null): build_blocks_split_bytes(max_blocks) bytes of device memory; with it the code construction
+// runs in its split form (sort / bitCounts of 32 blocks per warp / the rest), which pays off for many blocks with large
+// alphabets (huffman-only streams)
+size_t build_blocks_split_bytes(uint32_t max_blocks);
 cudaError_t build_blocks(const BlockPlan* plans, const uint32_t* nblocks_dev, uint32_t max_blocks,
-                         const uint32_t* lit_freq, const uint32_t* dist_freq, BlockDesc* descs, cudaStream_t st);
+                         const uint32_t* lit_freq, const uint32_t* dist_freq, BlockDesc* descs, cudaStream_t st,
+                         void* split_scratch = nullptr);
 // sequential offset scan; start_bits = container header bits. Writes total bits to *total_bits.
 cudaError_t scan_block_offsets(BlockDesc* descs, const uint32_t* nblocks_dev, uint64_t start_bits, uint64_t* total_bits,
                                cudaStream_t st);
 cudaError_t pack_blocks(const uint8_t* in, const uint32_t* tokens, const BlockDesc* descs, const uint32_t* nblocks_dev,
                         uint32_t max_blocks, uint32_t* out_words, cudaStream_t st);
 constexpr uint32_t kPackParts = 4;  // scan_block_offsets reports kPackParts-1 interior part boundaries after total_bits
+// first block of part i out of nb blocks: parts shrink towards the end (40, 30, 20, 10 %), because the copy back of the
+// last part is the one that nothing overlaps
+__host__ __device__ inline uint32_t pack_part_begin(uint32_t nb, uint32_t i) {
+    const uint32_t tenths = i == 0 ? 0u : i == 1 ? 4u : i == 2 ? 7u : i == 3 ? 9u : 10u;
+    return (uint32_t)(((uint64_t)nb * tenths) / 10);
+}
 cudaError_t pack_blocks_range(const uint8_t* in, const uint32_t* tokens, const BlockDesc* descs, const uint32_t* nblocks_dev,
                               uint32_t first_block, uint32_t count, uint32_t* out_words, cudaStream_t st);
 
