@@ -1120,7 +1120,9 @@ static int run_members(fb200_ctx* c, int container, const uint8_t* d_in, const M
     if (warp_kernel) FB_CUDA_CHECK(inflate_members(container, d_in, d_desc, (uint32_t)k, d_out, d_res, st));
     else {
         FB_CUDA_CHECK(c->m_scratch.ensure(inflate_par_scratch_bytes((uint32_t)k, c->sm_count)));
-        FB_CUDA_CHECK(inflate_members_par(container, d_in, d_desc, (uint32_t)k, d_out, d_res, c->m_scratch.p, c->sm_count, st));
+        bool pieces = false;  // a streaming decompressor's piece of a member: the kernel variant that can stop and resume
+        for (size_t i = 0; i < k; i++) pieces = pieces || h_desc[i].flags != 0 || h_desc[i].start_bit != 0;
+        FB_CUDA_CHECK(inflate_members_par(container, d_in, d_desc, (uint32_t)k, d_out, d_res, c->m_scratch.p, c->sm_count, st, pieces));
     }
     c->timer.mark(st, kPhInflate);
     c->launches += 1;

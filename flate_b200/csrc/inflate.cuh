@@ -32,7 +32,7 @@ constexpr uint32_t kNeedsHistory = 100;  // internal: match reaches before the m
 // d_scratch: inflate_par_scratch_bytes(k, sm_count) bytes of device memory (work counter + one match queue per CTA)
 size_t inflate_par_scratch_bytes(uint32_t k, int sm_count);
 cudaError_t inflate_members_par(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
-                                MemberResult* d_res, void* d_scratch, int sm_count, cudaStream_t st);
+                                MemberResult* d_res, void* d_scratch, int sm_count, cudaStream_t st, bool pieces = false);
 // one warp per member (inflate.cu): kept for comparison, FB200_INFLATE=warp
 cudaError_t inflate_members(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
                             MemberResult* d_res, cudaStream_t st);

@@ -699,6 +699,9 @@ __device__ void fast_round(Shared& S, const Window& W, const MemberDesc& md, uin
 using namespace par;
 
 // one member, all threads of the CTA
+// kPieces: the member may be one piece of a member that a streaming decompressor decodes bit by bit (MemberDesc::flags,
+// start_bit); the batch path is compiled without any of that
+template <bool kPieces>
 static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue, int container, const uint8_t* __restrict__ d_in,
                                           const MemberDesc md, uint8_t* d_out, MemberResult* __restrict__ result) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
@@ -716,14 +719,14 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
     bc.buf = 0;
     bc.cnt = 0;
 
-    const bool resume = (md.flags & kMemberResume) != 0, partial = (md.flags & kMemberPartial) != 0;
-    const bool nofooter = (md.flags & kMemberNoFooter) != 0;
+    const bool resume = kPieces && (md.flags & kMemberResume) != 0, partial = kPieces && (md.flags & kMemberPartial) != 0;
+    const bool nofooter = kPieces && (md.flags & kMemberNoFooter) != 0;
     // ---- container header (container.zig:111-152), thread 0 ----
     if (tid == 0) {
         int status = FB200_OK;
-        S.c.blk_cur = (unsigned long long)(uintptr_t)in_begin * 8ull + md.start_bit;
+        S.c.blk_cur = (unsigned long long)(uintptr_t)in_begin * 8ull + (kPieces ? md.start_bit : 0u);
         S.c.blk_pos = 0;
-        if (md.start_bit) {
+        if (kPieces && md.start_bit) {
             uint32_t skip;
             status = bc.read(md.start_bit, skip);
         }
@@ -776,7 +779,7 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
     int status = S.c.status;
     while (status == FB200_OK) {  // inflate.zig:251-280 step: one deflate block per iteration
         __syncthreads();  // every warp has read the control block of the previous block before warp 0 rewrites it
-        if (tid == 0) {   // a block boundary: where a partial call can be resumed
+        if (kPieces && tid == 0) {   // a block boundary: where a partial call can be resumed
             S.c.blk_cur = S.c.cur;
             S.c.blk_pos = S.c.pos;
         }
@@ -834,7 +837,7 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
                 {
                     const uint64_t pos = S.c.pos, flushed = S.c.flushed;
                     const uint64_t tail = (pos + W.A) & 15;  // bytes of the last, incomplete 16-byte line stay in the window
-                const uint64_t upto = pos > tail ? pos - tail : 0;  // (a member that starts unaligned and has produced less than a line)
+                    const uint64_t upto = pos > tail ? pos - tail : 0;  // (nothing complete yet when pos + A < 16)
                     __syncthreads();
                     if (upto > flushed) {
                         drain_cta(W, flushed, upto);
@@ -865,25 +868,9 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
     drain_cta(W, S.c.flushed, pos);  // whatever was produced, also on error (the caller sees out_len and the status)
     __syncthreads();
 
-    uint32_t part_sum = 0;
-    if (nofooter) {
-        // the caller combines the checksums of the pieces and reads the footer itself
-        if (status == FB200_OK && container == FB200_GZIP) {
-            for (uint32_t i = tid; i < 256; i += kLanes) {
-                uint32_t c = i;
-                for (int b = 0; b < 8; b++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
-                S.crc_tab[i] = c;
-            }
-            __syncthreads();
-            part_sum = cta_crc32(S, W.out, pos);
-        } else if (status == FB200_OK && container == FB200_ZLIB) {
-            part_sum = cta_adler32(S, W.out, pos);
-        }
-        if (tid == 0) bc.seek(S.c.cur);
-    } else
-    // ---- protocol footer (inflate.zig:271-275, container.zig:154-166) ----
+    // ---- checksum of what was produced, then the protocol footer (inflate.zig:271-275, container.zig:154-166) ----
+    uint32_t sum = 0;
     if (status == FB200_OK && container != FB200_RAW) {
-        uint32_t sum;
         if (container == FB200_GZIP) {
             for (uint32_t i = tid; i < 256; i += kLanes) {
                 uint32_t c = i;
@@ -895,8 +882,11 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
         } else {
             sum = cta_adler32(S, W.out, pos);
         }
-        if (tid == 0) {
-            bc.seek(S.c.cur);
+    }
+    const uint32_t part_sum = nofooter ? sum : 0;  // kMemberNoFooter: the caller combines the pieces' sums and reads the footer itself
+    if (tid == 0) {
+        bc.seek(S.c.cur);
+        if (status == FB200_OK && container != FB200_RAW && !nofooter) {
             bc.align_to_byte();
             uint32_t v = 0;
             status = bc.read(32, v);
@@ -909,8 +899,6 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
                 if (!status && v != be) status = FB200_WRONG_ZLIB_CHECKSUM;
             }
         }
-    } else if (tid == 0) {
-        bc.seek(S.c.cur);
     }
     if (tid == 0) {
         MemberResult res{};
@@ -929,6 +917,7 @@ static __device__ void inflate_one_member(Shared& S, uint8_t* ring, uint2* queue
 
 // Persistent CTAs: each takes the next member from a work counter until none is left, so that members of very
 // different sizes balance and the match queues (one per CTA) stay L2-resident.
+template <bool kPieces>
 __global__ void __launch_bounds__(par::kLanes, 1)
 inflate_members_par_kernel(int container, const uint8_t* __restrict__ d_in, const MemberDesc* __restrict__ descs, uint32_t k,
                            uint8_t* d_out, MemberResult* __restrict__ results, uint2* __restrict__ queues, uint32_t* work_counter) {
@@ -941,7 +930,7 @@ inflate_members_par_kernel(int container, const uint8_t* __restrict__ d_in, cons
         __syncthreads();
         const uint32_t m = S.c.member;
         if (m >= k) break;
-        inflate_one_member(S, smem_raw, queue, container, d_in, descs[m], d_out, results + m);
+        inflate_one_member<kPieces>(S, smem_raw, queue, container, d_in, descs[m], d_out, results + m);
     }
 }
 
@@ -951,14 +940,15 @@ size_t inflate_par_scratch_bytes(uint32_t k, int sm_count) {
 }
 
 cudaError_t inflate_members_par(int container, const uint8_t* d_in, const MemberDesc* d_desc, uint32_t k, uint8_t* d_out,
-                                MemberResult* d_res, void* d_scratch, int sm_count, cudaStream_t st) {
+                                MemberResult* d_res, void* d_scratch, int sm_count, cudaStream_t st, bool pieces) {
     if (k == 0) return cudaSuccess;
     static bool attr_set[64] = {};  // per device
     const size_t smem = par::kRing + sizeof(par::Shared);
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaFuncSetAttribute(inflate_members_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(inflate_members_par_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(inflate_members_par_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     // scratch: a work counter (first 256 bytes), then one match queue per CTA
@@ -967,7 +957,8 @@ cudaError_t inflate_members_par(int container, const uint8_t* d_in, const Member
     uint2* queues = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(d_scratch) + 256);
     cudaError_t e = cudaMemsetAsync(counter, 0, 4, st);
     if (e != cudaSuccess) return e;
-    inflate_members_par_kernel<<<grid, par::kLanes, smem, st>>>(container, d_in, d_desc, k, d_out, d_res, queues, counter);
+    if (pieces) inflate_members_par_kernel<true><<<grid, par::kLanes, smem, st>>>(container, d_in, d_desc, k, d_out, d_res, queues, counter);
+    else inflate_members_par_kernel<false><<<grid, par::kLanes, smem, st>>>(container, d_in, d_desc, k, d_out, d_res, queues, counter);
     return cudaGetLastError();
 }
 

@@ -1,4 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 300 python tools/phase_times.py 4096 1 2>&1 | tail -1
-timeout 900 python -m pytest tests/test_gpu_deflate.py tests/test_gpu_fullsize.py -x -q -m gpu -k "huffman or simple or block_range or fullsize or compress_bit_exact or streaming" > gpurun_out/r2_pytest_c.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest_c.log
+timeout 300 python tools/inflate_times.py 1 1024 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_inflate.py -x -q -m gpu 2>&1 | tail -2

@@ -1,5 +1,7 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest_final.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_final.log 2>&1
-python bench.py > gpurun_out/bench_v4.json 2> gpurun_out/bench_v4.err
-python bench.py --impl reference > gpurun_out/bench_ref_v4.json 2> gpurun_out/bench_ref_v4.err
-cat gpurun_out/pytest_final.log; tail -2 gpurun_out/smoke_final.log; cat gpurun_out/bench_v4.json; cat gpurun_out/bench_ref_v4.json
+#!/bin/bash
+# round-2 final pass on one GPU: all parity tests, the bench line, the reference arm, the ncu launch list of the bench command
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_final.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2_pytest_final.log
+python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; echo "bench rc=$?"; tail -2 gpurun_out/r2_bench_final.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_ref.json 2> gpurun_out/r2_bench_ref.err; echo "ref rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --skip-cpu --skip-c5 --skip-stream > gpurun_out/r2_ncu_bench.log 2>&1; echo "ncu rc=$?"
