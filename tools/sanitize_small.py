@@ -35,4 +35,47 @@ w = io.BytesIO()
 comp = flate_b200.Compressor(1, w, 6, ctx=ctx)
 comp.write(text[:70001]); comp.flush(); comp.write(text[70001:70004]); comp.flush(); comp.write(text[70004:]); comp.finish()
 assert zlib.decompress(w.getvalue(), 31) == text
+# round 2: streaming compressor in parts (tiny parts: slides, carried open blocks and partial bytes), huffman-only in
+# its split code construction (>= 64 blocks), streaming decompressor piece by piece, member discovery, tiny members
+os.environ["FB200_STREAM_PART"] = "128"
+big = (synth.enwik_like(700000, seed=5).tobytes() + bytes(90000) + text)
+for mode in (6, 1):
+    w = io.BytesIO()
+    comp = flate_b200.Compressor(1, w, mode, ctx=ctx)
+    for p in range(0, len(big), 50000):
+        comp.write(big[p:p + 50000])
+    comp.finish()
+    assert zlib.decompress(w.getvalue(), 31) == big
+    comp.close()
+hb = np.random.default_rng(1).integers(0, 64, 65535 * 70, dtype=np.uint8).tobytes()
+c = ctx.compress(hb, 0, 1)
+assert zlib.decompress(c, -15) == hb
+
+
+class Rd:
+    def __init__(self, d):
+        self.d, self.p = d, 0
+
+    def read(self, n):
+        n = min(n, 30000)
+        b = self.d[self.p:self.p + n]
+        self.p += len(b)
+        return b
+
+
+members = [ctx.compress(x, 1, 6) for x in (text[:60000], b"", b"x", bytes(50000), text[60000:150000])]
+out = io.BytesIO()
+dec = flate_b200.Decompressor(1, Rd(b"".join(members)), ctx=ctx)
+for i in range(len(members)):
+    try:
+        dec.decompress(out)
+    except flate_b200.FlateError as e:
+        assert type(e).__name__ == "InvalidDynamicBlockHeader"
+        break
+    if i + 1 < len(members):
+        dec.reset()
+try:
+    ctx.decompress_gzip_file(b"".join(members))
+except flate_b200.FlateError as e:
+    assert type(e).__name__ == "InvalidDynamicBlockHeader"
 print("sanitize run ok")
