@@ -94,3 +94,25 @@ def test_zig_binding_declares_every_symbol():
                  "pub const flate = ", "pub const gzip = ", "pub const zlib = "):
         assert name in src, name
     assert "..." not in re.sub(r"//.*", "", src)   # no elided bodies
+
+
+def test_checksum_combiners_are_pure_host_arithmetic():
+    """fb200_crc32_combine / fb200_adler32_combine (used for block-range shards, streaming parts and piecewise inflate):
+    the checksum of a concatenation from the checksums of its pieces, against zlib on random splits; and the pool and
+    streaming entry points refuse to work without a device instead of falling back."""
+    import zlib
+    import numpy as np
+    from flate_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    data = rng.integers(0, 256, 300000, dtype=np.uint8).tobytes()
+    for _ in range(50):
+        a, b = sorted(int(x) for x in rng.integers(0, len(data) + 1, 2))
+        left, mid = data[:a], data[a:b]
+        assert lib.fb200_crc32_combine(zlib.crc32(left), zlib.crc32(mid), len(mid)) == zlib.crc32(data[:b])
+        assert lib.fb200_adler32_combine(zlib.adler32(left), zlib.adler32(mid), len(mid)) == zlib.adler32(data[:b])
+    assert lib.fb200_crc32_combine(zlib.crc32(b"abc"), 0, 0) == zlib.crc32(b"abc")
+    if lib.fb200_device_count() == 0:
+        h = C.c_void_p()
+        assert lib.fb200_pool_create(0, C.byref(h)) == 20          # FB200_NO_DEVICE
+        assert lib.fb200_pool_devices(None) == 0
