@@ -1374,6 +1374,7 @@ int stream_sum(fb200_deflate* d, size_t upto, cudaStream_t st) {
     }
     fb200_ctx* c = d->ctx;
     std::lock_guard<std::recursive_mutex> ctx_lock(c->mu);
+    FB_CUDA_CHECK(cudaStreamSynchronize(d->copy_stream));  // the bytes being summed have landed (a write() may be in the middle of its copies)
     const size_t len = upto - d->sum_done;
     uint32_t* sum_dev = c->d_scalars + 16;
     uint32_t got = 0;

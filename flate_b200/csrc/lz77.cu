@@ -42,6 +42,7 @@ constexpr uint16_t kNoLink = 0xFFFF;
 constexpr uint32_t kLinkTile = 8192;
 constexpr uint32_t kLinkWarm = kHist / kLinkTile;  // warm-up tiles
 constexpr uint32_t kLinkWarps = 16;
+constexpr uint32_t kLinkGroup = 3;  // tiles between two rebases of the head table
 constexpr uint32_t kLinkThreads = kLinkWarps * 32;
 constexpr uint32_t kLinkPerWarp = kLinkTile / kLinkWarps;  // positions each warp splits
 constexpr uint32_t kLinkSmem = 32768 * 2 /*head*/ + kLinkTile * 2 /*partition lists*/ + kLinkTile * 2 /*hash, then link*/ +
@@ -87,6 +88,9 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
     for (uint32_t i = tid; i < 32768 / 2; i += kLinkThreads) reinterpret_cast<uint32_t*>(head)[i] = 0;
     const uint32_t t0 = first > kLinkWarm ? first - kLinkWarm : 0;
     const bool aligned = ((uintptr_t)in & 3) == 0;
+    // head entries are codes relative to a base that moves every kLinkGroup tiles (one pass over the 64 KiB table per
+    // group instead of per tile): code = position - group_base + 32768 + 1, at most 32768 + 3 * 8192 = 57344
+    uint32_t grp = 0;
     for (uint32_t t = t0; t < last; t++) {
         const bool emit = t >= first;
         const uint32_t base = t * kLinkTile;
@@ -193,7 +197,7 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
                 // optimistic step: most groups hold 32 different hashes.  Everybody reads its old head,
                 // publishes itself and reads back; a lane that does not find its own code lost to a peer
                 // with the same hash, and only then is the group ordered with MATCH.ANY.
-                const uint32_t code = off + kHist + 1;
+                const uint32_t code = off + grp * kLinkTile + kHist + 1;
                 uint32_t e = 0;
                 if (have) e = head[h];
                 __syncwarp();  // every lane has the old head before anybody publishes
@@ -241,12 +245,14 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
                     if (base + i >= begin) dst[i] = hl[i] == 0 ? kNoLink : hl[i];
             }
         }
-        if (t + 1 < last) {
+        if (++grp == kLinkGroup && t + 1 < last) {
+            constexpr uint32_t kShift = kLinkGroup * kLinkTile;  // entries at or below it are more than 32768 behind the new base
             for (uint32_t i = tid; i < 32768 / 2; i += kLinkThreads) {
                 const uint32_t v = reinterpret_cast<uint32_t*>(head)[i];
                 const uint32_t lo = v & 0xffffu, hi = v >> 16;
-                reinterpret_cast<uint32_t*>(head)[i] = (lo > kLinkTile ? lo - kLinkTile : 0u) | ((hi > kLinkTile ? hi - kLinkTile : 0u) << 16);
+                reinterpret_cast<uint32_t*>(head)[i] = (lo > kShift ? lo - kShift : 0u) | ((hi > kShift ? hi - kShift : 0u) << 16);
             }
+            grp = 0;
         }
         __syncthreads();
     }
@@ -1607,45 +1613,43 @@ __global__ void lazy_step_range_kernel(const uint32_t* __restrict__ r_full, cons
     nx[i] = out;
 }
 
-// K3b alone: exit tables from nx.  Pointer jumping is restricted to 256-position sub-chunks (jump[i] =
-// first arrival at or past the end of i's sub-chunk: 8-9 rounds instead of 12 for the whole chunk); the 516
-// possible entries then hop from sub-chunk to sub-chunk (at most 16 hops).  The jump table is kept in HBM
+// K3b alone: exit tables from nx.  jump[i] = first arrival at or past the end of i's 256-position sub-chunk.  Because
+// every step goes forward, that is a right-to-left recurrence inside a sub-chunk: jump[i] = i + step(i) if that leaves
+// the sub-chunk, else jump[i + step(i)], which is already final.  One lane per sub-chunk runs it (16 lanes per chunk,
+// 256 dependent steps): O(n) work where pointer jumping over the chunk does O(n log n), and no racing accesses.  The
+// 516 possible entries then hop from sub-chunk to sub-chunk (at most 16 hops).  The jump table is kept in HBM
 // (2 B per position): orbit_mark needs exactly this table and would otherwise rebuild it.
 constexpr uint32_t kSub = 256;                    // sub-chunk walked by one lane of orbit_mark
 constexpr uint32_t kSubs = kChunk / kSub;         // 16 walkers per chunk
+// the sub-chunks are 258 entries apart in shared memory, so that the 16 lanes that walk them in step hit 16 banks
+__device__ __forceinline__ uint32_t exit_slot(uint32_t i) { return i + 2 * (i >> 8); }
 __global__ void __launch_bounds__(1024)
 chunk_exit_kernel(const uint32_t* __restrict__ nx, uint32_t n, uint16_t* __restrict__ exits, uint16_t* __restrict__ jumps) {
-    __shared__ __align__(16) uint16_t jump[kChunk];
+    __shared__ __align__(16) uint16_t jump[kChunk + 2 * kSubs];
     const uint32_t c = blockIdx.x;
     const uint32_t cs = c * kChunk;
     for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
         const uint32_t p = cs + i;
-        jump[i] = (uint16_t)(p < n ? i + nx_step(nx_clean(nx[p])) : kChunk);  // <= 4095 + 515
+        jump[exit_slot(i)] = (uint16_t)(p < n ? i + nx_step(nx_clean(nx[p])) : kChunk);  // <= 4095 + 515
     }
     __syncthreads();
-    // Pointer jumping in place.  A thread may read jump[t] while its owner replaces it: 16-bit shared-memory accesses
-    // are single transactions, and both the old and the new value are "first arrival at or past some point of t's
-    // sub-chunk reached from t", so whichever is seen the invariant holds and the rounds only end when nothing moved
-    // (racecheck reports the read/write pair; a barrier-separated variant costs 0.2 - 1.2 ms per 256 MiB, measured).
-    volatile uint16_t* vj = jump;
-    while (true) {
-        bool pending = false;
-        for (uint32_t i = threadIdx.x; i < kChunk; i += blockDim.x) {
-            const uint32_t t = vj[i];
-            if (t < (i | (kSub - 1)) + 1) {  // still inside i's sub-chunk
-                vj[i] = vj[t];
-                pending = true;
-            }
+    if (threadIdx.x < kSubs) {
+        const uint32_t lo = threadIdx.x * kSub, end = lo + kSub;
+        for (uint32_t i = end; i-- > lo;) {
+            const uint32_t t = jump[exit_slot(i)];
+            if (t < end) jump[exit_slot(i)] = jump[exit_slot(t)];  // t > i: final already
         }
-        if (!__syncthreads_or(pending)) break;
     }
+    __syncthreads();
     for (uint32_t e = threadIdx.x; e < kEntries; e += blockDim.x) {
         uint32_t cur = e;
-        while (cur < kChunk) cur = jump[cur];
+        while (cur < kChunk) cur = jump[exit_slot(cur)];
         exits[(size_t)c * kEntries + e] = (uint16_t)(cur - kChunk);
     }
-    uint4* dst = reinterpret_cast<uint4*>(jumps + (size_t)c * kChunk);
-    for (uint32_t i = threadIdx.x; i < kChunk / 8; i += blockDim.x) dst[i] = reinterpret_cast<const uint4*>(jump)[i];
+    // back to the linear layout, two entries per word (a sub-chunk is 128 words, its slot 129)
+    uint32_t* dst = reinterpret_cast<uint32_t*>(jumps + (size_t)c * kChunk);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(jump);
+    for (uint32_t w = threadIdx.x; w < kChunk / 2; w += blockDim.x) dst[w] = src[w + (w >> 7)];
 }
 
 // K3c: resolve the true entry offset of every chunk.  Two-level: groups of kGroup chunks.
@@ -1888,6 +1892,7 @@ static SparseTune g_sparse_tune{1, 1, 1};
 static int g_sparse_roll = 0;      // FB200_SPARSE_ROLL: 0 = chunk kernel only (default: faster), 16 / 32 = rolling kernel with a seed every 16 / 32 positions
 static uint32_t g_sparse_roll_k = 1;  // runs per SM (dynamic hand-out when > 1)
 static uint32_t g_sparse_roll_prio = 0;  // see sparse_roll_kernel
+static int g_sparse_long = 1;      // FB200_SPARSE_LONG=0: levels 8 and 9 use the 8-step kernel too
 static void lz77_init_once() {
     // function attributes are per device: a process may hold contexts on several GPUs
     static bool done[64] = {};
@@ -1908,6 +1913,7 @@ static void lz77_init_once() {
     FB_SPARSE_ATTR(32, 4, false);
     FB_SPARSE_ATTR(16, 8, false);
     FB_SPARSE_ATTR(32, 8, true);
+    FB_SPARSE_ATTR(32, 16, false);
 #undef FB_SPARSE_ATTR
     cudaFuncSetAttribute(sparse_roll_kernel<kSparseW, 16, kSparseThreads, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSrSmem);
     cudaFuncSetAttribute(sparse_roll_kernel<kSparseW, 32, kSparseThreads, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSrSmem);
@@ -1935,6 +1941,7 @@ static void lz77_init_once() {
         if (got >= 1) g_sparse_roll = (g == 0 || g == 16 || g == 32) ? g : 16;
         if (got >= 2 && k >= 1 && k <= 16) g_sparse_roll_k = (uint32_t)k;
     }
+    if (const char* sl = getenv("FB200_SPARSE_LONG")) g_sparse_long = atoi(sl) != 0;
     if (const char* sp = getenv("FB200_SPARSE")) {
         int v = 0, p = 0, d = 0, r = 0;
         const int got = sscanf(sp, "%d,%d,%d,%d", &v, &p, &d, &r);
@@ -2038,9 +2045,13 @@ cudaError_t lz77_sparse_range(const Lz77Buffers& b, const uint8_t* d_in, uint32_
     const uint32_t grid = end_chunk - first_chunk;
 #define FB_SPARSE(G, ST) sparse_parse_kernel<kSparseT, kSparseW, G, kSparseThreads, 1, ST, false><<<grid, kSparseThreads, SparseCfg<kSparseT, kSparseW>::kSmem, st>>>(d_in, begin, first_chunk, nullptr, n, b.link, lv, g_sparse_tune, b.nx - begin, chunk_fail, flags)
     // the seeds of a run's overlap must be seeds of whatever evaluates the next chunk: same spacing as the rolling kernel
-    switch (g_sparse_variant == 0 && g_sparse_roll == 16 && run_counter ? 2 : g_sparse_variant) {
+    // long chains (levels 8 and 9: 1024 / 4096 candidates): 16 chain steps per round, the phases around the walk matter less
+    const int variant = g_sparse_variant == 0 && g_sparse_roll == 16 && run_counter ? 2
+                        : g_sparse_variant == 0 && lv.chain >= 1024 && g_sparse_long ? 3 : g_sparse_variant;
+    switch (variant) {
         case 1: FB_SPARSE(32, 4); break;
         case 2: FB_SPARSE(16, 8); break;
+        case 3: FB_SPARSE(32, 16); break;
         default: FB_SPARSE(32, 8); break;
     }
 #undef FB_SPARSE
