@@ -138,12 +138,11 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
         __syncthreads();
         // ---- 2. stable split of the tile's positions by owner warp (hash >> 11) ----
         // 2a. every warp counts, per owner, the positions of its own 512-position slice
+        // (counting needs no order: one shared-memory atomic per position; the ordered ranks are only needed in 2c)
         for (uint32_t it = 0; it < kLinkPerWarp / 32; it++) {
             const uint32_t off = w * kLinkPerWarp + it * 32 + lane;
             const uint32_t part = hl[off] >> 11;  // 0..15, or 31 for not insertable
-            const uint32_t peers = part_peers(part);
-            if ((peers & ltmask) == 0 && part < kLinkWarps) cnt[w * 17 + part] += __popc(peers);
-            __syncwarp();
+            if (part < kLinkWarps) atomicAdd(&cnt[w * 17 + part], 1u);
         }
         __syncthreads();
         // 2b. exclusive prefix down each owner's column, then over the owners
@@ -1874,8 +1873,9 @@ emit_tokens_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
     const uint32_t i0 = threadIdx.x * kPer;
     const uint32_t word = bitmap[(size_t)c * (kChunk / 32) + (i0 >> 5)];
     const uint32_t mask = kPer >= 32 ? word : (word >> (i0 & 31)) & ((1u << (kPer & 31)) - 1);
-    // tokens of my arrivals (scalar loads: the arrivals are a quarter of the positions, and fetching all 16 entries of a
-    // thread as vectors reads the whole table: measured 0.84 ms against 0.59 ms)
+    // tokens of my arrivals (scalar loads, twice: the arrivals are a quarter of the positions; fetching all 16 entries of a
+    // thread as vectors reads the whole table (0.84 ms against 0.59 ms), keeping the first pass's values in registers for
+    // the second costs more than the reloads from L1/L2 (0.64 ms))
     uint32_t mine = 0;
     for (uint32_t m = mask; m; m &= m - 1) {
         const uint32_t v = nx_clean(nx[cs + i0 + (__ffs(m) - 1)]);
