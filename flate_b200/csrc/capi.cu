@@ -348,8 +348,11 @@ static int sparse_begin(fb200_ctx* c, const Lz77Buffers& b, size_t count, cudaSt
 }
 // segment [begin, n) of a stream that is already on the device (begin > 0: earlier bytes are history, their links
 // are in place; d_skip/nskip: history positions the reference never inserted into its chains)
+static int sparse_verdict(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in, size_t begin, size_t n, const LevelArgs& lv,
+                          cudaStream_t st, bool* dense);
 static int sparse_tokenize(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in, size_t begin, size_t n, const uint32_t* d_skip,
-                           uint32_t nskip, const LevelArgs& lv, cudaStream_t st) {
+                           uint32_t nskip, const LevelArgs& lv, cudaStream_t st, bool* dense) {
+    *dense = false;
     if (n == begin) {
         FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, 0, lv, st, &c->timer));
         return FB200_OK;
@@ -360,8 +363,10 @@ static int sparse_tokenize(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_
     FB_CUDA_CHECK(lz77_link_range(b, d_in, (uint32_t)begin, (uint32_t)n, (uint32_t)n, st, &c->timer, d_skip, nskip));
     FB_CUDA_CHECK(lz77_sparse_range(b, d_in, (uint32_t)(begin / T), (uint32_t)((n + T - 1) / T), (uint32_t)n, lv, c->chunk_fail.p,
                                     c->d_scalars + kSparseFlagIdx, st, &c->timer, (uint32_t)begin, c->d_scalars + kRunCounterIdx));
+    c->launches += 2;
+    if ((rc = sparse_verdict(c, b, d_in, begin, n, lv, st, dense)) || *dense) return rc;
     FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in + begin, (uint32_t)(n - begin), lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
-    c->launches += 9;
+    c->launches += 7;
     return FB200_OK;
 }
 
@@ -397,6 +402,30 @@ static int sparse_repair(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in
         list.swap(next);
     }
     *ok = list.empty();
+    return FB200_OK;
+}
+
+// The verdict of the coverage check is known as soon as the sparse parse has run (flag bit 0): repair at once, so that
+// the parse and the block writer only ever run over a table that is closed under the lazy step.  *dense = true: the
+// repair gave up (mostly periodic data), the caller goes to the dense match tables.  Costs the happy path one
+// synchronisation (the kernels before and after it are long).
+static int sparse_verdict(fb200_ctx* c, const Lz77Buffers& b, const uint8_t* d_in, size_t begin, size_t n, const LevelArgs& lv,
+                          cudaStream_t st, bool* dense) {
+    *dense = false;
+    c->h_scalars[12] = 0;
+    FB_CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 12, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
+    FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (((uint32_t)c->h_scalars[12] & 1u) == 0) return FB200_OK;
+    bool ok = false;
+    int rc = sparse_repair(c, b, d_in, begin, n, lv, st, &ok);
+    if (rc) return rc;
+    if (ok) {
+        c->sparse_repairs++;
+        FB_CUDA_CHECK(cudaMemsetAsync(c->d_scalars + kSparseFlagIdx, 0, sizeof(uint32_t), st));
+    } else {
+        c->sparse_fallbacks++;
+        *dense = true;
+    }
     return FB200_OK;
 }
 
@@ -530,7 +559,11 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
             c->launches += n ? 7 : 0;
         } else if ((sparse = (n > begin && redo == 0 && c->parse_mode == 0)) && !(h_src && begin == 0 && n > kSlab + kLag)) {
             if (h_src) FB_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(d_in) + begin, h_src, n - begin, cudaMemcpyHostToDevice, st));
-            if ((rc = sparse_tokenize(c, b, d_in, begin, n, d_skip, nskip, lv, st))) return rc;
+            bool dense = false;
+            if ((rc = sparse_tokenize(c, b, d_in, begin, n, d_skip, nskip, lv, st, &dense))) return rc;
+            if (dense)  // mostly periodic data: the dense tables are the better tool (nothing was parsed or packed yet)
+                return deflate_body_device(c, container, mode, d_in, begin, n, d_skip, nskip, d_out, cap, end_bytes, final_flush, with_header,
+                                           st, nullptr, h_dst, h_cap, nullptr, 2);
         } else if (sparse) {
             // slab-overlapped copy: links follow the copy front one hash tile behind, the sparse parse follows the
             // links by its look-ahead
@@ -561,6 +594,11 @@ static int deflate_body_device(fb200_ctx* c, int container, int mode, const uint
                 copied = slab_end;
                 k++;
             }
+            bool dense = false;
+            if ((rc = sparse_verdict(c, b, d_in, 0, n, lv, st, &dense))) return rc;
+            if (dense)
+                return deflate_body_device(c, container, mode, d_in, begin, n, d_skip, nskip, d_out, cap, end_bytes, final_flush, with_header,
+                                           st, nullptr, h_dst, h_cap, nullptr, 2);
             FB_CUDA_CHECK(lz77_parse_from_nx(b, d_in, (uint32_t)n, lv, st, &c->timer, c->d_scalars + kSparseFlagIdx));
             c->launches += 7;
         } else if (h_src && n - begin > kSlab + kLag) {
@@ -1009,10 +1047,12 @@ int fb200_debug_tokens(fb200_ctx* c, int level, const uint8_t* in, size_t n, uin
     Lz77Buffers b = lz77_view(c);
     uint32_t total = 0, bad = 0;
     if (c->parse_mode == 0 && n) {
-        if ((rc = sparse_tokenize(c, b, c->d_in.p, 0, n, nullptr, 0, lv, st))) return rc;
-        FB_CUDA_CHECK(cudaMemcpyAsync(&bad, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
+        bool dense = false;  // the repair inside already gave up
+        if ((rc = sparse_tokenize(c, b, c->d_in.p, 0, n, nullptr, 0, lv, st, &dense))) return rc;
+        if (!dense) FB_CUDA_CHECK(cudaMemcpyAsync(&bad, c->d_scalars + kSparseFlagIdx, 4, cudaMemcpyDeviceToHost, st));
         FB_CUDA_CHECK(cudaStreamSynchronize(st));
-        if (bad) {
+        if (dense) bad = 1;
+        else if (bad) {
             bool ok = false;
             if ((rc = sparse_repair(c, b, c->d_in.p, 0, n, lv, st, &ok))) return rc;
             if (ok) {

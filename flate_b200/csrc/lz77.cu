@@ -43,10 +43,12 @@ constexpr uint32_t kLinkTile = 8192;
 constexpr uint32_t kLinkWarm = kHist / kLinkTile;  // warm-up tiles
 constexpr uint32_t kLinkWarps = 16;
 constexpr uint32_t kLinkGroup = 3;  // tiles between two rebases of the head table
+constexpr uint32_t kRunFlag = 0x8000u;   // on a hash: the position continues a run of one byte (its link is 1)
+constexpr uint32_t kRunLink = 0xFFFEu;   // in the link slot of such a position until the tile is flushed (real links are <= 0x8000)
 constexpr uint32_t kLinkThreads = kLinkWarps * 32;
 constexpr uint32_t kLinkPerWarp = kLinkTile / kLinkWarps;  // positions each warp splits
 constexpr uint32_t kLinkSmem = 32768 * 2 /*head*/ + kLinkTile * 2 /*partition lists*/ + kLinkTile * 2 /*hash, then link*/ +
-                               (kLinkWarps * 17 + 32) * 4;
+                               (kLinkWarps * 17 + 32 + kLinkTile / 32) * 4;
 
 __device__ __forceinline__ uint32_t hash_be(uint32_t le32) {
     // Lookup.zig:75-84: big-endian read of 4 bytes, times 0x9E3779B1, top 15 bits
@@ -74,6 +76,7 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
     uint16_t* hl = reinterpret_cast<uint16_t*>(smem_raw + 65536 + kLinkTile * 2);  // hash per position, later its link
     uint32_t* cnt = reinterpret_cast<uint32_t*>(hl + kLinkTile);              // [warp][17] counts -> running bases
     uint32_t* pstart = cnt + kLinkWarps * 17;                                 // [17] partition starts
+    uint32_t* lastbits = pstart + 32;                                         // [kLinkTile / 32] last position of a run of one byte
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t ltmask = (1u << lane) - 1;
     // [begin, n) is the segment being compressed (begin > 0 after a sync flush); earlier positions are
@@ -96,6 +99,7 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
         const uint32_t base = t * kLinkTile;
         const uint32_t cnt_pos = min(kLinkTile, n - base);
         // ---- 1. hashes of the tile (0xFFFF = not insertable) ----
+        bool any_run = false;
         if (aligned) {
             const uint32_t* words = reinterpret_cast<const uint32_t*>(in + base);
             const uint32_t nwords_total = (n - base + 3) / 4, nwords_full = (n - base) / 4;
@@ -115,6 +119,7 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
                     const bool valid = off < cnt_pos && (uint64_t)base + off + 4 <= n;  // Lookup.zig:24 needs 4 bytes
                     hh[k] = valid ? hash_be(__funnelshift_r(w0, w1, 8 * k)) : 0xFFFFu;
                 }
+                any_run |= w0 == __byte_perm(w0, 0, 0x0321) && i < nwords_full;  // four equal bytes: a run of one byte may pass here
                 reinterpret_cast<uint2*>(hl)[i] = make_uint2(hh[0] | (hh[1] << 16), hh[2] | (hh[3] << 16));
             }
         } else {
@@ -123,6 +128,7 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
                 if (off < cnt_pos && (uint64_t)base + off + 4 <= n) {
                     const uint8_t* b = in + base + off;
                     h = hash_be((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
+                    any_run |= b[0] == b[1] && b[1] == b[2] && b[2] == b[3];
                 }
                 hl[off] = (uint16_t)h;
             }
@@ -135,14 +141,42 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
                 if (q >= base && q < base + cnt_pos) hl[q - base] = 0xFFFFu;
             }
         }
-        __syncthreads();
+        // Runs of one byte.  A position whose four bytes equal the four bytes one position earlier has its predecessor's
+        // hash, so its link is 1 whatever the table says.  In a tile with long runs (zero padding, holes) such positions
+        // are flagged (kRunFlag), stay out of the ordered resolve, and only the last one of a run takes part, to leave the
+        // right head behind: without this a run of zeros puts a whole tile on one warp's list, 32 conflicts per step.
+        // Tiles without four equal bytes in a row at 16 places or more (text) skip all of it.
+        const bool has_runs = __syncthreads_count(any_run) >= 16;
+        if (has_runs) {
+            for (uint32_t off = tid; off < cnt_pos; off += kLinkThreads) {
+                const uint32_t h = hl[off];
+                if (h == 0xFFFFu || h == 0x7FFFu || (base | off) == 0) continue;
+                // the position before must have been inserted (the three before a flush point never are, Lookup.zig:24)
+                bool pred_in = off ? hl[off - 1] != 0xFFFFu : true;  // (a racing flag write never makes or unmakes 0xFFFF)
+                if (off == 0)
+                    for (uint32_t j = 0; j < nskip; j++) pred_in = pred_in && skip[j] != base - 1;
+                const uint8_t* b = in + base + off;
+                if (pred_in && b[-1] == b[0] && b[0] == b[1] && b[1] == b[2] && b[2] == b[3]) hl[off] = (uint16_t)(h | kRunFlag);
+            }
+            __syncthreads();
+        }
         // ---- 2. stable split of the tile's positions by owner warp (hash >> 11) ----
         // 2a. every warp counts, per owner, the positions of its own 512-position slice
         // (counting needs no order: one shared-memory atomic per position; the ordered ranks are only needed in 2c)
         for (uint32_t it = 0; it < kLinkPerWarp / 32; it++) {
             const uint32_t off = w * kLinkPerWarp + it * 32 + lane;
-            const uint32_t part = hl[off] >> 11;  // 0..15, or 31 for not insertable
-            if (part < kLinkWarps) atomicAdd(&cnt[w * 17 + part], 1u);
+            const uint32_t h = hl[off];
+            if (!has_runs) {
+                if ((h >> 11) < kLinkWarps) atomicAdd(&cnt[w * 17 + (h >> 11)], 1u);  // 0..15, or 31 for not insertable
+                continue;
+            }
+            const uint32_t hn = off + 1 < cnt_pos ? (uint32_t)hl[off + 1] : 0u;  // (the neighbour may belong to the next warp: read only)
+            const bool in_run = (h & kRunFlag) && h != 0xFFFFu, next_in_run = (hn & kRunFlag) && hn != 0xFFFFu;
+            const bool run_last = in_run && !next_in_run;
+            const uint32_t lb = __ballot_sync(0xffffffffu, run_last);
+            if (lane == 0) lastbits[off >> 5] = lb;
+            const uint32_t part = (in_run && !run_last) ? 31u : (h & 0x7FFFu) >> 11;  // 0..15; run interior and not insertable: none
+            if (h != 0xFFFFu && part < kLinkWarps) atomicAdd(&cnt[w * 17 + part], 1u);
         }
         __syncthreads();
         // 2b. exclusive prefix down each owner's column, then over the owners
@@ -169,7 +203,12 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
         for (uint32_t it = 0; it < kLinkPerWarp / 32; it++) {
             const uint32_t off = w * kLinkPerWarp + it * 32 + lane;
             const uint32_t h = hl[off];
-            const uint32_t part = h >> 11;
+            uint32_t part = h >> 11;
+            if (has_runs) {
+                const bool in_run = (h & kRunFlag) && h != 0xFFFFu, run_last = in_run && ((lastbits[off >> 5] >> lane) & 1u);
+                part = h == 0xFFFFu || (in_run && !run_last) ? 31u : (h & 0x7FFFu) >> 11;
+                if (in_run && !run_last) hl[off] = kRunLink;  // its link is 1: nothing else to find out (only this lane reads hl[off] here)
+            }
             uint32_t peers = part_peers(part);
             if (part >= kLinkWarps) peers = 1u << lane;  // not insertable: alone
             const uint32_t leader = __ffs(peers) - 1;
@@ -189,9 +228,12 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
             for (uint32_t sidx = lo; sidx < hi; sidx += 32) {
                 uint32_t h = 0x10000u | lane, off = 0;  // unique key for idle lanes
                 const bool have = sidx + lane < hi;
+                bool run_last = false;
                 if (have) {
                     off = lists[sidx + lane];
                     h = hl[off];
+                    run_last = (h & kRunFlag) != 0;  // a listed position with the flag is the last one of a run
+                    h &= 0x7FFFu;
                 }
                 // optimistic step: most groups hold 32 different hashes.  Everybody reads its old head,
                 // publishes itself and reads back; a lane that does not find its own code lost to a peer
@@ -218,7 +260,7 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
                         if ((peers >> lane) == 1u) head[h] = (uint16_t)code;  // the group's last lane wins
                     }
                 }
-                if (have) hl[off] = (uint16_t)d;  // only this lane ever needed the hash of this position
+                if (have) hl[off] = (uint16_t)(run_last ? 1u : d);  // only this lane ever needed the hash of this position
                 __syncwarp();
             }
         }
@@ -235,13 +277,17 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
                     for (int k = 0; k < 4; k++) {  // no predecessor (0) and never inserted (0xFFFF) both become kNoLink
                         if ((x[k] & 0xffffu) == 0) x[k] |= 0x0000ffffu;
                         if ((x[k] >> 16) == 0) x[k] |= 0xffff0000u;
+                        if (has_runs) {  // inside a run of one byte
+                            if ((x[k] & 0xffffu) == kRunLink) x[k] = (x[k] & 0xffff0000u) | 1u;
+                            if ((x[k] >> 16) == kRunLink) x[k] = (x[k] & 0x0000ffffu) | 0x00010000u;
+                        }
                     }
                     reinterpret_cast<uint4*>(dst)[i] = v;
                 }
-                for (uint32_t i = nv * 8 + tid; i < cnt_pos; i += kLinkThreads) dst[i] = hl[i] == 0 ? kNoLink : hl[i];
+                for (uint32_t i = nv * 8 + tid; i < cnt_pos; i += kLinkThreads) dst[i] = hl[i] == 0 ? kNoLink : hl[i] == kRunLink ? (uint16_t)1 : hl[i];
             } else {  // the tile straddles the segment start: keep the links of earlier segments
                 for (uint32_t i = tid; i < cnt_pos; i += kLinkThreads)
-                    if (base + i >= begin) dst[i] = hl[i] == 0 ? kNoLink : hl[i];
+                    if (base + i >= begin) dst[i] = hl[i] == 0 ? kNoLink : hl[i] == kRunLink ? (uint16_t)1 : hl[i];
             }
         }
         if (++grp == kLinkGroup && t + 1 < last) {
