@@ -144,3 +144,49 @@ def test_c3_inflate_1GiB_of_members_on_device(ctx, text256):
     want = torch.from_numpy(np.concatenate(plains)).cuda()
     got = d_plain[: nmem * MIB].view(nmem // uniq, uniq * MIB)
     assert bool((got == want.unsqueeze(0)).all())
+
+
+def test_streaming_compressor_equals_oracle_and_one_shot_at_size(ctx, text256, monkeypatch):
+    """SURVEY.md section 8f rank 2 at size: 40 MiB of text + a tar-like tail through Compressor.write in 1 MiB pieces with
+    4 MiB parts (ten parts, window slides, a flush in the middle) equals the CPU oracle's streaming Deflate byte for byte;
+    and 200 MiB with the default part size (64 MiB: three parts) equals the one-shot stream of the same bytes."""
+    import io
+    import sys
+    import flate_b200
+    sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+    import bench
+    from oracle import oracle as o
+    data = np.concatenate([text256[:40 * MIB], bench.make_tar_like(8 * MIB)]).tobytes()
+    monkeypatch.setenv("FB200_STREAM_PART", "4096")
+    w = io.BytesIO()
+    c = flate_b200.Compressor(1, w, 6, ctx=ctx)
+    d = o.Deflate(1, 6)
+    cut = 29 * MIB + 17
+    for a, b in ((0, cut), (cut, len(data))):
+        for p in range(a, b, MIB):
+            c.write(data[p:min(p + MIB, b)])
+        d.write(data[a:b])
+        if b != len(data):
+            c.flush()
+            d.flush()
+    c.finish()
+    d.finish()
+    assert w.getvalue() == d.output()
+    c.close()
+    monkeypatch.delenv("FB200_STREAM_PART")
+    big = text256[:200 * MIB]
+    w = io.BytesIO()
+    c = flate_b200.Compressor(0, w, 6, ctx=ctx)
+    for p in range(0, big.size, 4 * MIB):
+        c.write(big[p:p + 4 * MIB])
+    c.finish()
+    want = _device_compress(ctx, big, 6)
+    assert w.getvalue() == want
+    c.close()
+    # the same bytes in ONE write() call (larger than the window: the call itself has to run parts and slide)
+    w = io.BytesIO()
+    c = flate_b200.Compressor(0, w, 6, ctx=ctx)
+    c.write(big)
+    c.finish()
+    assert w.getvalue() == want
+    c.close()
