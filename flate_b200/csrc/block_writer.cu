@@ -6,6 +6,8 @@
 // :206, storedSizeFits :221, write :307, dynamicBlock :395, huffmanBlock :524, dynamicHeader :237,
 // writeTokens :492, storedBlock :385), huffman_encoder.zig (generate :62, bitCounts :122,
 // assignEncodingAndSize :251) and bit_writer.zig (only the byte stream is observable).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "pipeline.cuh"
 
@@ -674,6 +676,111 @@ bit_counts_lanes_kernel(const uint32_t* __restrict__ nblocks_dev, const uint16_t
 }
 
 // ------------------------------------------------------------------------------------------
+// K5 split, middle pass, data-parallel form: the same per-length counts as bitCounts (huffman_encoder.zig:122-247) from
+// the EAGER package-merge, one warp per block.  bitCounts is the lazy ("boundary") evaluation of this construction:
+// level 1 is the sorted leaves; level l is the merge of the leaves with the pairs (sums of consecutive items) of level
+// l - 1, a pair going first when it ties with a leaf (`next_char_freq < next_pair_freq` takes the leaf, :182); the top
+// level takes 2n - 2 items, a level that contributes p pairs makes the level below contribute 2p items, and the number
+// of leaves a_l among the items a level contributes gives the counts: bit_count[L - l + 1] = a_l - a_(l-1).  A merge is
+// two binary searches per item (rank of a leaf among the pairs, of a pair among the leaves), so a level is 17 parallel
+// steps of a warp instead of ~500 dependent ones.  Equality with the lazy form was checked on the CPU against the oracle
+// (tools/eager_package_merge_check.py: 12000 frequency sets with ties, binding length limits, 15- and 7-bit limits) and
+// is checked on the GPU by the bit-exact huffman-only tests.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kEagerWarps = 8;
+constexpr uint32_t kEagerItems = 576;  // 2 * 288
+struct EagerShared {
+    uint32_t leaf[kSplitSlots];      // sorted leaf frequencies
+    uint32_t pair[kSplitSlots];      // pair sums of the level below
+    uint32_t item[2][kEagerItems];   // items of the level below / of this level
+    uint32_t mask[16][kEagerItems / 32];  // level l: bit i set = item i is a leaf
+    uint32_t len[16];
+};
+__global__ void __launch_bounds__(kEagerWarps * 32)
+bit_counts_eager_kernel(const uint32_t* __restrict__ nblocks_dev, const uint16_t* __restrict__ g_sfreq, const uint32_t* __restrict__ g_count,
+                        uint16_t* __restrict__ g_bit_count) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    EagerShared& S = reinterpret_cast<EagerShared*>(smem_raw)[w];
+    const uint32_t b = blockIdx.x * kEagerWarps + w;
+    if (b >= *nblocks_dev) return;
+    const uint32_t n = g_count[b];
+    if (n == kHuffDone || n <= 2 || n > kSplitSlots) return;
+    const uint32_t L = min(15u, n - 1);  // :131
+    const uint32_t T = 2 * n - 2;        // items the top level takes; no level contributes more
+    const uint16_t* list = g_sfreq + (size_t)b * kSplitSlots;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t f = list[i];
+        S.leaf[i] = f;
+        S.item[0][i] = f;
+    }
+    for (uint32_t i = lane; i < 16 * (kEagerItems / 32); i += 32) (&S.mask[0][0])[i] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < (n + 31) / 32; i += 32) S.mask[1][i] = (i + 1) * 32 <= n ? 0xffffffffu : (1u << (n & 31)) - 1;
+    if (lane == 0) S.len[1] = n;
+    __syncwarp();
+    uint32_t cur = 0, len_prev = n;
+    for (uint32_t l = 2; l <= L; l++) {
+        const uint32_t* below = S.item[cur];
+        uint32_t* here = S.item[cur ^ 1];
+        const uint32_t m = len_prev / 2;
+        for (uint32_t j = lane; j < m; j += 32) S.pair[j] = below[2 * j] + below[2 * j + 1];
+        __syncwarp();
+        // leaves: position = i + number of pairs <= leaf (a pair that ties goes first)
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t v = S.leaf[i];
+            uint32_t lo = 0, hi = m;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (S.pair[mid] <= v) lo = mid + 1;
+                else hi = mid;
+            }
+            const uint32_t pos = i + lo;
+            if (pos < T) {
+                here[pos] = v;
+                atomicOr(&S.mask[l][pos >> 5], 1u << (pos & 31));
+            }
+        }
+        // pairs: position = j + number of leaves < pair
+        for (uint32_t j = lane; j < m; j += 32) {
+            const uint32_t v = S.pair[j];
+            uint32_t lo = 0, hi = n;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (S.leaf[mid] < v) lo = mid + 1;
+                else hi = mid;
+            }
+            const uint32_t pos = j + lo;
+            if (pos < T) here[pos] = v;
+        }
+        len_prev = min(n + m, T);
+        if (lane == 0) S.len[l] = len_prev;
+        cur ^= 1;
+        __syncwarp();
+    }
+    // top-down: how many leaves each level contributes
+    uint32_t take = T, a_above = 0;
+    uint16_t* out = g_bit_count + (size_t)b * 16;
+    if (lane < 16) out[lane] = 0;
+    __syncwarp();
+    for (uint32_t l = L; l >= 1; l--) {
+        take = min(take, S.len[l]);
+        uint32_t a = 0;
+        for (uint32_t wd = lane; wd * 32 < take; wd += 32) {
+            uint32_t bits = S.mask[l][wd];
+            if ((wd + 1) * 32 > take) bits &= (1u << (take & 31)) - 1;
+            a += __popc(bits);
+        }
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        // bit_count[L - l + 1] = a_l - a_(l-1): written when the level below is known
+        if (l < L && lane == 0) out[L - l] = (uint16_t)(a_above - a);
+        a_above = a;
+        take = 2 * (take - a);
+    }
+    if (lane == 0) out[L] = (uint16_t)a_above;  // level 1: a_1 - a_0
+}
+
+// ------------------------------------------------------------------------------------------
 // K5b: block bit offsets.  Huffman blocks are not byte aligned; a stored block pads after its
 // 3 header bits (block_writer.zig:283-291), so the offset recurrence is sequential.
 // ------------------------------------------------------------------------------------------
@@ -999,7 +1106,18 @@ cudaError_t build_blocks(const BlockPlan* plans, const uint32_t* nblocks_dev, ui
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t ntasks = (max_blocks + 31) / 32;  // persistent: one CTA of kLaneWarps warps per SM, tasks dealt round robin
     const uint32_t lgrid = min((uint32_t)sms, (ntasks + kLaneWarps - 1) / kLaneWarps);
-    bit_counts_lanes_kernel<<<lgrid, kLaneWarps * 32, kLaneWarps * kLaneSmemPerWarp, st>>>(nblocks_dev, sfreq, count, bitc);
+    static const bool lazy_lanes = [] { const char* e = getenv("FB200_BITCOUNTS"); return e && e[0] == 'l'; }();  // FB200_BITCOUNTS=lanes: the lazy form
+    if (lazy_lanes) {
+        bit_counts_lanes_kernel<<<lgrid, kLaneWarps * 32, kLaneWarps * kLaneSmemPerWarp, st>>>(nblocks_dev, sfreq, count, bitc);
+    } else {
+        static bool eager_attr[64] = {};
+        if (dev < 0 || dev >= 64 || !eager_attr[dev]) {
+            cudaFuncSetAttribute(bit_counts_eager_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEagerWarps * sizeof(EagerShared)));
+            if (dev >= 0 && dev < 64) eager_attr[dev] = true;
+        }
+        bit_counts_eager_kernel<<<(max_blocks + kEagerWarps - 1) / kEagerWarps, kEagerWarps * 32, kEagerWarps * sizeof(EagerShared), st>>>(
+            nblocks_dev, sfreq, count, bitc);
+    }
     build_blocks_kernel<kHuffFromCounts><<<grid, kBuildWarps * 32, 0, st>>>(plans, nblocks_dev, lit_freq, dist_freq, descs, slit, sfreq, count, bitc);
     return cudaGetLastError();
 }

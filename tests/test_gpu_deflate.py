@@ -636,3 +636,27 @@ def test_pool_batch_over_all_devices(o):
     assert all(p == it for p, it, s in zip(plains, items, st) if s == 0)
     pool.close()
     ctx.close()
+
+
+def test_huffman_only_many_blocks_split_construction(ctx, o):
+    """huffman-only streams of 64 blocks and more build their codes in three passes, the middle one from the eager
+    package-merge (block_writer.cu): bytes equal to the oracle's for blocks of every kind of frequency shape -- text,
+    uniform random, few symbols, skewed (binding length limit), runs, and blocks that end up stored."""
+    from flate_b200 import synth
+    rng = np.random.default_rng(2024)
+    parts = [synth.enwik_like(3 << 20, seed=81),
+             rng.integers(0, 256, 1 << 20, dtype=np.uint8),
+             rng.integers(0, 3, 1 << 20, dtype=np.uint8),
+             (rng.zipf(1.2, 1 << 20) % 256).astype(np.uint8),
+             np.minimum(255, rng.geometric(0.02, 1 << 20)).astype(np.uint8),
+             np.repeat(rng.integers(0, 256, 4096, dtype=np.uint8), 256),
+             synth.random_zero_mix(2 << 20)]
+    # a block whose frequencies double from symbol to symbol: the 15-bit limit binds
+    skew = np.concatenate([np.full(1 << min(i, 14), i, dtype=np.uint8) for i in range(24)])
+    parts.append(np.tile(skew, 20))
+    data = np.concatenate(parts).tobytes()
+    assert len(data) // 65535 >= 64
+    for container in (0, 1):
+        got = ctx.compress(data, container, 1)
+        want = o.compress(data, container, 1)
+        assert got == want, first_diff(got, want)
