@@ -212,6 +212,91 @@ __device__ uint32_t bit_counts_warp(HuffScratch& s, uint32_t n, uint32_t max_bit
     return max_bits;
 }
 
+constexpr uint32_t kEagerItems = 576;  // 2 * 288
+constexpr uint32_t kEagerSlots = 288;
+struct EagerShared {
+    uint32_t leaf[kEagerSlots];      // sorted leaf frequencies
+    uint32_t pair[kEagerSlots];      // pair sums of the level below
+    uint32_t item[2][kEagerItems];   // items of the level below / of this level
+    uint32_t mask[16][kEagerItems / 32];  // level l: bit i set = item i is a leaf
+    uint32_t len[16];
+};
+// Per-length counts of the length-limited code of n >= 3 sorted frequencies (S.leaf[0..n) filled by the caller, warp
+// converged): out[1..L] with L = min(max_bits, n - 1), the same numbers bitCounts (huffman_encoder.zig:122-247) computes.
+// See bit_counts_eager_kernel for the construction.  Returns L.
+template <typename OutT>
+__device__ uint32_t bit_counts_eager_warp(EagerShared& S, uint32_t n, uint32_t max_bits, OutT* out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t L = min(max_bits, n - 1);  // :131
+    const uint32_t T = 2 * n - 2;             // items the top level takes; no level contributes more
+    for (uint32_t i = lane; i < n; i += 32) S.item[0][i] = S.leaf[i];
+    for (uint32_t i = lane; i < 16 * (kEagerItems / 32); i += 32) (&S.mask[0][0])[i] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < (n + 31) / 32; i += 32) S.mask[1][i] = (i + 1) * 32 <= n ? 0xffffffffu : (1u << (n & 31)) - 1;
+    if (lane == 0) S.len[1] = n;
+    __syncwarp();
+    uint32_t cur = 0, len_prev = n;
+    for (uint32_t l = 2; l <= L; l++) {
+        const uint32_t* below = S.item[cur];
+        uint32_t* here = S.item[cur ^ 1];
+        const uint32_t m = len_prev / 2;
+        for (uint32_t j = lane; j < m; j += 32) S.pair[j] = below[2 * j] + below[2 * j + 1];
+        __syncwarp();
+        // leaves: position = i + number of pairs <= leaf (a pair that ties goes first)
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t v = S.leaf[i];
+            uint32_t lo = 0, hi = m;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (S.pair[mid] <= v) lo = mid + 1;
+                else hi = mid;
+            }
+            const uint32_t pos = i + lo;
+            if (pos < T) {
+                here[pos] = v;
+                atomicOr(&S.mask[l][pos >> 5], 1u << (pos & 31));
+            }
+        }
+        // pairs: position = j + number of leaves < pair
+        for (uint32_t j = lane; j < m; j += 32) {
+            const uint32_t v = S.pair[j];
+            uint32_t lo = 0, hi = n;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (S.leaf[mid] < v) lo = mid + 1;
+                else hi = mid;
+            }
+            const uint32_t pos = j + lo;
+            if (pos < T) here[pos] = v;
+        }
+        len_prev = min(n + m, T);
+        if (lane == 0) S.len[l] = len_prev;
+        cur ^= 1;
+        __syncwarp();
+    }
+    // top-down: how many leaves each level contributes
+    uint32_t take = T, a_above = 0;
+    if (lane < 16) out[lane] = 0;
+    __syncwarp();
+    for (uint32_t l = L; l >= 1; l--) {
+        take = min(take, S.len[l]);
+        uint32_t a = 0;
+        for (uint32_t wd = lane; wd * 32 < take; wd += 32) {
+            uint32_t bits = S.mask[l][wd];
+            if ((wd + 1) * 32 > take) bits &= (1u << (take & 31)) - 1;
+            a += __popc(bits);
+        }
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        // bit_count[L - l + 1] = a_l - a_(l-1): written when the level below is known
+        if (l < L && lane == 0) out[L - l] = (OutT)(a_above - a);
+        a_above = a;
+        take = 2 * (take - a);
+    }
+    if (lane == 0) out[L] = (OutT)a_above;  // level 1: a_1 - a_0
+    __syncwarp();
+    return L;
+}
+
 // huffman_encoder.zig:62-95 generate + :251-278 assignEncodingAndSize.  Whole warp.
 // out[i] = code | len << 16 (code bit-reversed, ready for LSB-first packing); len 0 for unused.
 // Split form (huffman-only streams: tens of thousands of blocks with full alphabets): the serial bitCounts of 32 blocks
@@ -228,7 +313,7 @@ constexpr uint32_t kHuffDone = 0xffffffffu;
 
 template <int kPhase>
 __device__ void huff_generate_warp(HuffScratch& s, const uint16_t* freq, uint32_t n, uint32_t max_bits, uint32_t* out,
-                                   const HuffSplit* split = nullptr) {
+                                   const HuffSplit* split = nullptr, EagerShared* eager = nullptr) {
     const uint32_t lane = threadIdx.x & 31;
     uint32_t count = 0;
     for (uint32_t base = 0; base < n; base += 32) {  // compact non-zero symbols, literal order
@@ -269,7 +354,13 @@ __device__ void huff_generate_warp(HuffScratch& s, const uint16_t* freq, uint32_
             }
             return;
         }
-        mb = bit_counts_warp(s, count, max_bits);
+        if (eager && count >= 16) {  // large alphabets: the data-parallel form of the same construction
+            for (uint32_t i = lane; i < count; i += 32) eager->leaf[i] = s.s_freq[i];
+            __syncwarp();
+            mb = bit_counts_eager_warp(*eager, count, max_bits, s.bit_count);
+        } else {
+            mb = bit_counts_warp(s, count, max_bits);
+        }
     } else {
         for (uint32_t i = lane; i < count; i += 32) s.s_lit[i] = split->slit[i];
         if (lane < 16) s.bit_count[lane] = split->bit_count[lane];
@@ -297,7 +388,18 @@ __device__ void huff_generate_warp(HuffScratch& s, const uint16_t* freq, uint32_
     __syncwarp();
 }
 
-struct BuildShared {
+// (the split passes leave the counts to bit_counts_eager_kernel: they carry no scratch for them)
+template <bool kWithEager>
+struct EagerHolder {
+    EagerShared eager;
+    __device__ EagerShared* eager_ptr() { return &eager; }
+};
+template <>
+struct EagerHolder<false> {
+    __device__ EagerShared* eager_ptr() { return nullptr; }
+};
+template <bool kWithEager>
+struct BuildSharedT : EagerHolder<kWithEager> {
     HuffScratch hs;
     uint16_t lit_freq[kNumLit];
     uint16_t dist_freq[kNumDist];
@@ -342,7 +444,7 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
                     const uint32_t* __restrict__ lit_freq_g, const uint32_t* __restrict__ dist_freq_g,
                     BlockDesc* __restrict__ descs, uint16_t* __restrict__ g_slit, uint16_t* __restrict__ g_sfreq,
                     uint32_t* __restrict__ g_count, uint16_t* __restrict__ g_bit_count) {
-    __shared__ BuildShared sh_all[kBuildWarps];
+    __shared__ BuildSharedT<kPhase == kHuffFull> sh_all[kBuildWarps];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * kBuildWarps + (threadIdx.x >> 5);
     if (b >= *nblocks_dev) return;
@@ -351,7 +453,7 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
         split = HuffSplit{g_slit + (size_t)b * kSplitSlots, g_sfreq + (size_t)b * kSplitSlots, g_count + b, g_bit_count + (size_t)b * 16};
         if (kPhase == kHuffFromCounts && *split.count == kHuffDone) return;  // finished by the sort pass
     }
-    BuildShared& sh = sh_all[threadIdx.x >> 5];
+    auto& sh = sh_all[threadIdx.x >> 5];
     const BlockPlan pl = plans[b];
     BlockDesc& d = descs[b];
 
@@ -433,12 +535,12 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
     }
 
     // ---- code construction ----
-    huff_generate_warp<kPhase>(sh.hs, sh.lit_freq, kNumLit, 15, sh.lit_code, &split);
+    huff_generate_warp<kPhase>(sh.hs, sh.lit_freq, kNumLit, 15, sh.lit_code, &split, sh.eager_ptr());
     if (kPhase == kHuffSortOnly) return;  // bit_counts_lanes_kernel and the kHuffFromCounts pass go on from here
     if (pl.kind == kHuffmanBlock) {  // huffmanDistanceEncoder, huffman_encoder.zig:340-348: one 1-bit code
         for (uint32_t i = lane; i < kNumDist; i += 32) sh.dist_code[i] = i == 0 ? (1u << 16) : 0;
     } else {
-        huff_generate_warp<kHuffFull>(sh.hs, sh.dist_freq, kNumDist, 15, sh.dist_code);
+        huff_generate_warp<kHuffFull>(sh.hs, sh.dist_freq, kNumDist, 15, sh.dist_code, nullptr, sh.eager_ptr());
     }
     __syncwarp();
 
@@ -688,14 +790,6 @@ bit_counts_lanes_kernel(const uint32_t* __restrict__ nblocks_dev, const uint16_t
 // is checked on the GPU by the bit-exact huffman-only tests.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kEagerWarps = 8;
-constexpr uint32_t kEagerItems = 576;  // 2 * 288
-struct EagerShared {
-    uint32_t leaf[kSplitSlots];      // sorted leaf frequencies
-    uint32_t pair[kSplitSlots];      // pair sums of the level below
-    uint32_t item[2][kEagerItems];   // items of the level below / of this level
-    uint32_t mask[16][kEagerItems / 32];  // level l: bit i set = item i is a leaf
-    uint32_t len[16];
-};
 __global__ void __launch_bounds__(kEagerWarps * 32)
 bit_counts_eager_kernel(const uint32_t* __restrict__ nblocks_dev, const uint16_t* __restrict__ g_sfreq, const uint32_t* __restrict__ g_count,
                         uint16_t* __restrict__ g_bit_count) {
@@ -706,78 +800,10 @@ bit_counts_eager_kernel(const uint32_t* __restrict__ nblocks_dev, const uint16_t
     if (b >= *nblocks_dev) return;
     const uint32_t n = g_count[b];
     if (n == kHuffDone || n <= 2 || n > kSplitSlots) return;
-    const uint32_t L = min(15u, n - 1);  // :131
-    const uint32_t T = 2 * n - 2;        // items the top level takes; no level contributes more
     const uint16_t* list = g_sfreq + (size_t)b * kSplitSlots;
-    for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t f = list[i];
-        S.leaf[i] = f;
-        S.item[0][i] = f;
-    }
-    for (uint32_t i = lane; i < 16 * (kEagerItems / 32); i += 32) (&S.mask[0][0])[i] = 0;
+    for (uint32_t i = lane; i < n; i += 32) S.leaf[i] = list[i];
     __syncwarp();
-    for (uint32_t i = lane; i < (n + 31) / 32; i += 32) S.mask[1][i] = (i + 1) * 32 <= n ? 0xffffffffu : (1u << (n & 31)) - 1;
-    if (lane == 0) S.len[1] = n;
-    __syncwarp();
-    uint32_t cur = 0, len_prev = n;
-    for (uint32_t l = 2; l <= L; l++) {
-        const uint32_t* below = S.item[cur];
-        uint32_t* here = S.item[cur ^ 1];
-        const uint32_t m = len_prev / 2;
-        for (uint32_t j = lane; j < m; j += 32) S.pair[j] = below[2 * j] + below[2 * j + 1];
-        __syncwarp();
-        // leaves: position = i + number of pairs <= leaf (a pair that ties goes first)
-        for (uint32_t i = lane; i < n; i += 32) {
-            const uint32_t v = S.leaf[i];
-            uint32_t lo = 0, hi = m;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (S.pair[mid] <= v) lo = mid + 1;
-                else hi = mid;
-            }
-            const uint32_t pos = i + lo;
-            if (pos < T) {
-                here[pos] = v;
-                atomicOr(&S.mask[l][pos >> 5], 1u << (pos & 31));
-            }
-        }
-        // pairs: position = j + number of leaves < pair
-        for (uint32_t j = lane; j < m; j += 32) {
-            const uint32_t v = S.pair[j];
-            uint32_t lo = 0, hi = n;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (S.leaf[mid] < v) lo = mid + 1;
-                else hi = mid;
-            }
-            const uint32_t pos = j + lo;
-            if (pos < T) here[pos] = v;
-        }
-        len_prev = min(n + m, T);
-        if (lane == 0) S.len[l] = len_prev;
-        cur ^= 1;
-        __syncwarp();
-    }
-    // top-down: how many leaves each level contributes
-    uint32_t take = T, a_above = 0;
-    uint16_t* out = g_bit_count + (size_t)b * 16;
-    if (lane < 16) out[lane] = 0;
-    __syncwarp();
-    for (uint32_t l = L; l >= 1; l--) {
-        take = min(take, S.len[l]);
-        uint32_t a = 0;
-        for (uint32_t wd = lane; wd * 32 < take; wd += 32) {
-            uint32_t bits = S.mask[l][wd];
-            if ((wd + 1) * 32 > take) bits &= (1u << (take & 31)) - 1;
-            a += __popc(bits);
-        }
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        // bit_count[L - l + 1] = a_l - a_(l-1): written when the level below is known
-        if (l < L && lane == 0) out[L - l] = (uint16_t)(a_above - a);
-        a_above = a;
-        take = 2 * (take - a);
-    }
-    if (lane == 0) out[L] = (uint16_t)a_above;  // level 1: a_1 - a_0
+    bit_counts_eager_warp(S, n, 15, g_bit_count + (size_t)b * 16);
 }
 
 // ------------------------------------------------------------------------------------------
