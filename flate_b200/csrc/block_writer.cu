@@ -942,7 +942,7 @@ pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
         const uint32_t total = len + 4;
         const uint8_t* src = in + d.in_begin;
         const uint64_t w0 = a >> 2, w1 = (a + total + 3) >> 2;
-        for (uint64_t w = w0 + threadIdx.x; w < w1; w += kPackThreads) {
+        auto emit_word = [&](uint64_t w) {
             const int64_t s0 = (int64_t)(w * 4) - (int64_t)a;  // stream index of the word's first byte
             if (s0 >= 4 && s0 + 4 <= (int64_t)total) {
                 // interior word: four payload bytes from an arbitrarily aligned source (two aligned loads + funnel shift)
@@ -952,7 +952,7 @@ pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
                 const uint32_t lo = pw[0];
                 const uint32_t hi = sh ? pw[1] : 0;  // when aligned the second word may lie past the buffer
                 out[w] = __funnelshift_r(lo, hi, sh);
-                continue;
+                return;
             }
             uint32_t v = 0;
             bool full = true;
@@ -969,7 +969,25 @@ pack_blocks_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ 
             }
             if (full) out[w] = v;
             else if (v) atomicOr(out + w, v);
+        };
+        // the bulk in 16-byte stores (the output buffer is 16-byte aligned): five aligned source words give four output words
+        const uint64_t g0 = (w0 + 3) >> 2, g1 = w1 >> 2;
+        for (uint64_t g = g0 + threadIdx.x; g < g1; g += kPackThreads) {
+            const int64_t s0 = (int64_t)(g * 16) - (int64_t)a;
+            if (s0 >= 4 && s0 + 16 <= (int64_t)total) {
+                const uint8_t* p = src + (s0 - 4);
+                const uint32_t* pw = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+                const uint32_t sh = (uint32_t)((uintptr_t)p & 3) * 8;
+                const uint32_t x0 = pw[0], x1 = pw[1], x2 = pw[2], x3 = pw[3], x4 = sh ? pw[4] : 0;
+                reinterpret_cast<uint4*>(out)[g] = make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh),
+                                                              __funnelshift_r(x2, x3, sh), __funnelshift_r(x3, x4, sh));
+            } else {
+                for (uint32_t k = 0; k < 4; k++) emit_word(g * 4 + k);
+            }
         }
+        const uint64_t head_end = g0 * 4 < w1 ? g0 * 4 : w1, tail_begin = g1 > g0 ? g1 * 4 : head_end;
+        for (uint64_t w = w0 + threadIdx.x; w < head_end; w += kPackThreads) emit_word(w);
+        for (uint64_t w = tail_begin + threadIdx.x; w < w1; w += kPackThreads) emit_word(w);
         return;
     }
 

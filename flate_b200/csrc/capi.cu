@@ -1519,10 +1519,12 @@ int stream_run(fb200_deflate* d, size_t n, size_t parse_end, size_t chunk_end, s
     if (ncopy) FB_CUDA_CHECK(cudaMemcpyAsync(d->h_out, d->d_outs[hb].p, ncopy, cudaMemcpyDeviceToHost, d->out_stream));
     FB_CUDA_CHECK(cudaEventRecord(d->out_ev[hb], d->out_stream));
     if (d->level_mode && carry.leftover) FB_CUDA_CHECK(cudaMemcpyAsync(d->tokbuf.p, c->tokens.p, (size_t)carry.leftover * 4, cudaMemcpyDeviceToDevice, st));
-    uint8_t last = 0;  // the byte the next part's bits share
     const uint32_t phase = parse_end ? (uint32_t)(carry.total_bits & 7) : 0;
-    if (phase) FB_CUDA_CHECK(cudaMemcpyAsync(&last, d->d_outs[hb].p + nfull, 1, cudaMemcpyDeviceToHost, st));
+    uint8_t* last_pinned = reinterpret_cast<uint8_t*>(c->h_scalars + 13);  // the byte the next part's bits share
+    *last_pinned = 0;
+    if (phase) FB_CUDA_CHECK(cudaMemcpyAsync(last_pinned, d->d_outs[hb].p + nfull, 1, cudaMemcpyDeviceToHost, st));
     FB_CUDA_CHECK(cudaStreamSynchronize(st));
+    const uint8_t last = *last_pinned;
     if (!parse_end) FB_CUDA_CHECK(cudaEventSynchronize(d->out_ev[hb]));  // flush / finish hand their bytes out at once
     if (trace) {
         const auto t2 = std::chrono::steady_clock::now();
