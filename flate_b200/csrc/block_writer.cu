@@ -785,9 +785,9 @@ bit_counts_lanes_kernel(const uint32_t* __restrict__ nblocks_dev, const uint16_t
 // level takes 2n - 2 items, a level that contributes p pairs makes the level below contribute 2p items, and the number
 // of leaves a_l among the items a level contributes gives the counts: bit_count[L - l + 1] = a_l - a_(l-1).  A merge is
 // two binary searches per item (rank of a leaf among the pairs, of a pair among the leaves), so a level is 17 parallel
-// steps of a warp instead of ~500 dependent ones.  Equality with the lazy form was checked on the CPU against the oracle
-// (tools/eager_package_merge_check.py: 12000 frequency sets with ties, binding length limits, 15- and 7-bit limits) and
-// is checked on the GPU by the bit-exact huffman-only tests.
+// steps of a warp instead of ~500 dependent ones.  Equality with the lazy form is a CPU test of its own
+// (tests/test_eager_package_merge_cpu.py: frequency sets with ties, binding length limits, 15- and 7-bit limits, against the
+// sequential restatement of bitCounts) and is checked on the GPU by the bit-exact huffman-only tests.
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kEagerWarps = 8;
 __global__ void __launch_bounds__(kEagerWarps * 32)
