@@ -568,6 +568,37 @@ def main():
             c4["cpu_baseline"] = {"value": round(n / 1e6 / dt, 2), "unit": "MB/s", "cores": 1, "kind": "port",
                                   "sample": "the whole %d MiB chunk, one pass; output compared byte for byte: identical" % (n // MIB)}
 
+        # worst case of SURVEY.md section 8(d): a low-entropy 4-gram alphabet, so that almost every 4-byte hash has been
+        # seen hundreds of times inside the window and the chain walk goes to its full depth (rank 0, N = 1 only)
+        if world == 1:
+            wn = min(n, 32 * MIB)
+            rng = np.random.default_rng(0x5EED0009)
+            low = rng.integers(0, 4, wn, dtype=np.uint8) + ord("a")
+            d_low = torch.from_numpy(low).cuda()
+            lw = [0]
+
+            def worst_step():
+                lw[0] = ctx.compress_device(d_low.data_ptr(), wn, d_out.data_ptr(), cap, mode=9, stream=sp)
+
+            msw = timed(worst_step, 2, warmup=1)
+            c4["worst_case"] = {"metric": "deflate L9 MB/s in (low-entropy input, full-depth chain walks)", "value": round(wn / 1e6 / (msw / 1e3), 1),
+                                "unit": "MB/s", "ms_per_step": round(msw, 3), "ratio": round(wn / lw[0], 3),
+                                "workload": "%d MiB of uniformly random bytes over a 4-letter alphabet, level 9" % (wn // MIB)}
+            if not args.skip_cpu:
+                import zlib
+                comp_w = d_out[:lw[0]].cpu().numpy().tobytes()
+                assert zlib.decompress(comp_w, -15) == low.tobytes(), "worst case: the stream does not inflate back"
+                o, olib = oracle_lib()
+                samp = 2 * MIB
+                t0 = time.perf_counter()
+                want_w = o.compress(low[:samp], o.RAW, 9, _lib_override=olib)
+                dt = time.perf_counter() - t0
+                got_w = ctx.compress(low[:samp], flate_b200.RAW, 9)
+                assert got_w == want_w, "worst case: GPU output differs from the CPU oracle on the sample"
+                c4["worst_case"]["cpu_baseline"] = {"value": round(samp / 1e6 / dt, 2), "unit": "MB/s", "cores": 1, "kind": "port",
+                                                    "sample": "first %d MiB as a stream of its own: output identical; the whole stream inflates back (zlib)" % (samp // MIB)}
+            del d_low
+
     # =====================================================================================================
     # mixed: tar-like input, the sparse parse off its happy path (level 6)
     # =====================================================================================================
