@@ -143,12 +143,9 @@ struct HuffScratch {
 __device__ __forceinline__ uint32_t bit_reverse(uint32_t v, uint32_t nbits) { return __brev(v) >> (32 - nbits); }
 
 // huffman_encoder.zig:122-247.  list = s.s_freq[0..n) ascending; n >= 3.
-// The algorithm is inherently sequential (and must stay a literal restatement to be bit-exact), so
-// the whole warp executes it redundantly on broadcast shared-memory reads; the one O(level) step --
-// copying a row of leaf counts when a pair is taken (:199) -- is spread over the lanes.  Element
-// (l, j < l) of leaf_counts is only ever written and read by lane j, the diagonal and the level
-// records are written identically by every lane; one __syncwarp per step separates the reads of a step
-// from the (identical) writes of the lanes that are ahead.
+// The lazy boundary package-merge as the reference runs it, step for step, by lane 0 alone (it is inherently
+// sequential).  Only short lists come here (fewer than 16 symbols: small distance and code-length alphabets); longer
+// ones take the eager form below, which gives the same length histogram with all lanes at work.
 __device__ uint32_t bit_counts_warp(HuffScratch& s, uint32_t n, uint32_t max_bits) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t kMaxI32 = 0x7fffffffu;
@@ -156,52 +153,46 @@ __device__ uint32_t bit_counts_warp(HuffScratch& s, uint32_t n, uint32_t max_bit
     for (uint32_t i = lane; i < 17 * 16; i += 32) (&s.leaf_counts[0][0])[i] = 0;
     for (uint32_t l = lane; l < 17; l += 32) s.levels[l] = LevelInfo{0, 0, 0, 0};
     __syncwarp();
-    const uint32_t f0 = s.s_freq[0], f1 = s.s_freq[1], f2 = s.s_freq[2];
-    for (uint32_t level = 1; level <= max_bits; level++) {  // :144-161
-        s.levels[level] = LevelInfo{f1, f2, level == 1 ? kMaxI32 : f0 + f1, 0};
-        s.leaf_counts[level][level] = 2;
-    }
-    s.levels[max_bits].needed = 2 * n - 4;  // :164
-    uint32_t level = max_bits;
-    while (true) {  // :168-224
-        LevelInfo l = s.levels[level];
-        const uint32_t diag = s.leaf_counts[level][level];
-        // Every lane has read this step's state before any lane overwrites it.  All lanes then write the same
-        // values, and no lane can reach the writes of the next step before all have passed this point, so a
-        // lane never reads a value "from the future" even if the warp's lanes drift apart.
-        __syncwarp();
-        if (l.next_pair_freq == kMaxI32 && l.next_char_freq == kMaxI32) {  // :170 (leaf sentinel is 65535: not taken)
-            s.levels[level].needed = 0;
-            s.levels[level + 1].next_pair_freq = kMaxI32;
-            level += 1;
-            continue;
+    if (lane == 0) {
+        const uint32_t f0 = s.s_freq[0], f1 = s.s_freq[1], f2 = s.s_freq[2];
+        for (uint32_t level = 1; level <= max_bits; level++) {  // :144-161
+            s.levels[level] = LevelInfo{f1, f2, level == 1 ? kMaxI32 : f0 + f1, 0};
+            s.leaf_counts[level][level] = 2;
         }
-        const uint32_t prev_freq = l.last_freq;
-        if (l.next_char_freq < l.next_pair_freq) {  // :182 next item is a leaf
-            const uint32_t next = diag + 1;
-            l.last_freq = l.next_char_freq;
-            s.leaf_counts[level][level] = next;
-            l.next_char_freq = (next >= n) ? 65535u : (uint32_t)s.s_freq[next];  // :188-192, maxNode :282
-        } else {  // :193 next item is a pair from the level below
-            l.last_freq = l.next_pair_freq;
-            if (lane < level) s.leaf_counts[level][lane] = s.leaf_counts[level - 1][lane];  // :199
-            s.levels[level - 1].needed = 2;
-        }
-        l.needed -= 1;
-        s.levels[level] = l;
-        if (l.needed == 0) {  // :204
-            if (level == max_bits) break;
-            s.levels[level + 1].next_pair_freq = prev_freq + l.last_freq;
-            level += 1;
-        } else {
-            while (s.levels[level - 1].needed > 0) {  // :217
-                level -= 1;
-                if (level == 0) break;
+        s.levels[max_bits].needed = 2 * n - 4;  // :164
+        uint32_t level = max_bits;
+        while (true) {  // :168-224
+            LevelInfo l = s.levels[level];
+            if (l.next_pair_freq == kMaxI32 && l.next_char_freq == kMaxI32) {  // :170 (leaf sentinel is 65535: not taken)
+                s.levels[level].needed = 0;
+                s.levels[level + 1].next_pair_freq = kMaxI32;
+                level += 1;
+                continue;
+            }
+            const uint32_t prev_freq = l.last_freq;
+            if (l.next_char_freq < l.next_pair_freq) {  // :182 next item is a leaf
+                const uint32_t next = s.leaf_counts[level][level] + 1;
+                l.last_freq = l.next_char_freq;
+                s.leaf_counts[level][level] = next;
+                l.next_char_freq = (next >= n) ? 65535u : (uint32_t)s.s_freq[next];  // :188-192, maxNode :282
+            } else {  // :193 next item is a pair from the level below
+                l.last_freq = l.next_pair_freq;
+                for (uint32_t j = 0; j < level; j++) s.leaf_counts[level][j] = s.leaf_counts[level - 1][j];  // :199
+                s.levels[level - 1].needed = 2;
+            }
+            l.needed -= 1;
+            s.levels[level] = l;
+            if (l.needed == 0) {  // :204
+                if (level == max_bits) break;
+                s.levels[level + 1].next_pair_freq = prev_freq + l.last_freq;
+                level += 1;
+            } else {
+                while (s.levels[level - 1].needed > 0) {  // :217
+                    level -= 1;
+                    if (level == 0) break;
+                }
             }
         }
-    }
-    __syncwarp();
-    if (lane == 0) {
         uint32_t bits = 1;
         for (uint32_t lv = max_bits; lv > 0; lv--) {  // :235-245
             s.bit_count[bits] = s.leaf_counts[max_bits][lv] - s.leaf_counts[max_bits][lv - 1];
@@ -492,6 +483,7 @@ build_blocks_kernel(const BlockPlan* __restrict__ plans, const uint32_t* __restr
         while (sh.lit_freq[num_literals - 1] == 0) num_literals--;
         num_distances = kNumDist;
         while (num_distances > 0 && sh.dist_freq[num_distances - 1] == 0) num_distances--;
+        __syncwarp();  // every lane has finished reading dist_freq before lane 0 writes the phantom symbol
         if (num_distances == 0) {
             if (lane == 0) sh.dist_freq[0] = 1;
             num_distances = 1;

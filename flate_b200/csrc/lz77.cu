@@ -148,16 +148,21 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
         // Tiles without four equal bytes in a row at 16 places or more (text) skip all of it.
         const bool has_runs = __syncthreads_count(any_run) >= 16;
         if (has_runs) {
-            for (uint32_t off = tid; off < cnt_pos; off += kLinkThreads) {
+            static_assert(kLinkTile / kLinkThreads <= 32, "one decision bit per round of the loop");
+            uint32_t flagged = 0;  // decided for all positions first, written after the barrier: the test reads the neighbour's hash
+            for (uint32_t off = tid, r = 0; off < cnt_pos; off += kLinkThreads, r++) {
                 const uint32_t h = hl[off];
                 if (h == 0xFFFFu || h == 0x7FFFu || (base | off) == 0) continue;
                 // the position before must have been inserted (the three before a flush point never are, Lookup.zig:24)
-                bool pred_in = off ? hl[off - 1] != 0xFFFFu : true;  // (a racing flag write never makes or unmakes 0xFFFF)
+                bool pred_in = off ? hl[off - 1] != 0xFFFFu : true;
                 if (off == 0)
                     for (uint32_t j = 0; j < nskip; j++) pred_in = pred_in && skip[j] != base - 1;
                 const uint8_t* b = in + base + off;
-                if (pred_in && b[-1] == b[0] && b[0] == b[1] && b[1] == b[2] && b[2] == b[3]) hl[off] = (uint16_t)(h | kRunFlag);
+                if (pred_in && b[-1] == b[0] && b[0] == b[1] && b[1] == b[2] && b[2] == b[3]) flagged |= 1u << r;
             }
+            __syncthreads();
+            for (uint32_t off = tid, r = 0; off < cnt_pos; off += kLinkThreads, r++)
+                if ((flagged >> r) & 1u) hl[off] = (uint16_t)(hl[off] | kRunFlag);
             __syncthreads();
         }
         // ---- 2. stable split of the tile's positions by owner warp (hash >> 11) ----
@@ -235,31 +240,28 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
                     run_last = (h & kRunFlag) != 0;  // a listed position with the flag is the last one of a run
                     h &= 0x7FFFu;
                 }
-                // optimistic step: most groups hold 32 different hashes.  Everybody reads its old head,
-                // publishes itself and reads back; a lane that does not find its own code lost to a peer
-                // with the same hash, and only then is the group ordered with MATCH.ANY.
+                // Lanes with the same hash are ordered with MATCH.ANY: a lane's predecessor is the next lower lane of
+                // its group, or, for the group's first lane, the head entry; the group's last lane leaves the new head.
+                // One writer per entry and step, and every lane has read the old head before anybody publishes.  (An
+                // optimistic variant -- everybody publishes, reads back, and only a group that saw a loser is ordered --
+                // saved the MATCH on data without repeats but took the ordered path on nearly every step of text, and
+                // its same-address stores were a race by the letter.)
                 const uint32_t code = off + grp * kLinkTile + kHist + 1;
                 uint32_t e = 0;
                 if (have) e = head[h];
-                __syncwarp();  // every lane has the old head before anybody publishes
-                if (have) head[h] = (uint16_t)code;  // same-hash lanes race on purpose: any winner exposes the conflict
-                __syncwarp();
-                const bool lost = have && head[h] != code;
+                const uint32_t peers = __match_any_sync(0xffffffffu, h);
+                const uint32_t lower = peers & ltmask;
+                const uint32_t src = lower ? 31 - __clz(lower) : lane;
+                const uint32_t off_prev = __shfl_sync(0xffffffffu, off, src);
                 uint32_t d = 0;
-                if (e) {
+                if (lower) {
+                    d = off - off_prev;  // predecessor inside the group, same tile
+                } else if (e) {
                     d = code - e;
                     if (d > kMaxDist) d = 0;
                 }
-                if (__any_sync(0xffffffffu, lost)) {
-                    const uint32_t peers = __match_any_sync(0xffffffffu, h);
-                    const uint32_t lower = peers & ltmask;
-                    const uint32_t src = lower ? 31 - __clz(lower) : lane;
-                    const uint32_t off_prev = __shfl_sync(0xffffffffu, off, src);
-                    if (have) {
-                        if (lower) d = off - off_prev;  // predecessor inside the group, same tile
-                        if ((peers >> lane) == 1u) head[h] = (uint16_t)code;  // the group's last lane wins
-                    }
-                }
+                __syncwarp();
+                if (have && (peers >> lane) == 1u) head[h] = (uint16_t)code;
                 if (have) hl[off] = (uint16_t)(run_last ? 1u : d);  // only this lane ever needed the hash of this position
                 __syncwarp();
             }
