@@ -25,10 +25,10 @@ namespace fb {
 // of 8192-position tiles; inside a tile the 15-bit hash space is split over the block's 16 warps
 // (warp w owns hashes with top 4 bits == w), so 16 sequential chains advance in parallel:
 //   1. all threads hash the tile into shared memory (u16 per position, 0xFFFF = not insertable)
-//   2. every warp scans the tile's hashes in order (128 positions per step), compacts the positions
-//      it owns into a staging buffer, and resolves them 32 at a time: predecessor inside the group
-//      via __match_any_sync, otherwise from its slice of the head table; the last lane of each hash
-//      group publishes the new head
+//   2. the tile's positions are split by owner, stably (per-owner counts, then an ordered scatter: one ballot per
+//      bit of the owner number -- MATCH.ANY's latency grows with the number of distinct values, 16 here), and every
+//      warp resolves its own list 32 entries at a time: predecessor inside the group via __match_any_sync,
+//      otherwise from its slice of the head table; the last lane of each hash group publishes the new head
 //   3. links are collected in shared memory and flushed coalesced; the head table is rebased by one
 //      tile (the reference's Lookup.slide, Lookup.zig:43-51, is the same saturating subtract)
 // Head entries are u16 codes c = p - (tile_base - 32768) + 1 in [1, 40960], 0 = none.
@@ -53,18 +53,6 @@ constexpr uint32_t kLinkSmem = 32768 * 2 /*head*/ + kLinkTile * 2 /*partition li
 __device__ __forceinline__ uint32_t hash_be(uint32_t le32) {
     // Lookup.zig:75-84: big-endian read of 4 bytes, times 0x9E3779B1, top 15 bits
     return (__byte_perm(le32, 0, 0x0123) * 0x9E3779B1u) >> 17;
-}
-
-// lanes of the warp whose `part` (0..15) equals mine, from one ballot per bit of `part` (MATCH.ANY's
-// latency grows with the number of distinct values; 16 per-value ballots cost 3x the instructions)
-__device__ __forceinline__ uint32_t part_peers(uint32_t part) {
-    uint32_t peers = __ballot_sync(0xffffffffu, part < kLinkWarps);
-#pragma unroll
-    for (uint32_t b = 0; b < 4; b++) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, (part >> b) & 1u);
-        peers &= ((part >> b) & 1u) ? bal : ~bal;
-    }
-    return peers;
 }
 
 __global__ void __launch_bounds__(kLinkThreads, 2)
@@ -204,27 +192,36 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
             }
         }
         __syncthreads();
-        // 2c. scatter (off, hash) into the owner's list, keeping position order
-        for (uint32_t it = 0; it < kLinkPerWarp / 32; it++) {
-            const uint32_t off = w * kLinkPerWarp + it * 32 + lane;
-            const uint32_t h = hl[off];
-            uint32_t part = h >> 11;
-            if (has_runs) {
-                const bool in_run = (h & kRunFlag) && h != 0xFFFFu, run_last = in_run && ((lastbits[off >> 5] >> lane) & 1u);
-                part = h == 0xFFFFu || (in_run && !run_last) ? 31u : (h & 0x7FFFu) >> 11;
-                if (in_run && !run_last) hl[off] = kRunLink;  // its link is 1: nothing else to find out (only this lane reads hl[off] here)
+        // 2c. scatter (off, hash) into the owner's list, keeping position order.  Lane l < 16 carries, in a register,
+        // where the next entry of owner l from this warp's slice goes; a step needs one ballot per bit of the owner
+        // number, from which every lane derives the lanes with ITS position's owner (its rank among them is its place)
+        // and lane l the lanes with owner l (their number moves its cursor): no shared-memory counter on the way.
+        {
+            uint32_t cursor = lane < kLinkWarps ? pstart[lane] + cnt[w * 17 + lane] : 0u;
+            uint32_t own_x[4];  // all-ones where this lane's number has a 0 bit
+#pragma unroll
+            for (uint32_t b = 0; b < 4; b++) own_x[b] = ((lane >> b) & 1u) - 1u;
+            for (uint32_t it = 0; it < kLinkPerWarp / 32; it++) {
+                const uint32_t off = w * kLinkPerWarp + it * 32 + lane;
+                const uint32_t h = hl[off];
+                uint32_t part = h >> 11;
+                if (has_runs) {
+                    const bool in_run = (h & kRunFlag) && h != 0xFFFFu, run_last = in_run && ((lastbits[off >> 5] >> lane) & 1u);
+                    part = h == 0xFFFFu || (in_run && !run_last) ? 31u : (h & 0x7FFFu) >> 11;
+                    if (in_run && !run_last) hl[off] = kRunLink;  // its link is 1: nothing else to find out (only this lane reads hl[off] here)
+                }
+                const uint32_t listed = __ballot_sync(0xffffffffu, part < kLinkWarps);
+                uint32_t peers = listed, mine = listed;
+#pragma unroll
+                for (uint32_t b = 0; b < 4; b++) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, (part >> b) & 1u);
+                    peers &= bal ^ (((part >> b) & 1u) - 1u);
+                    mine &= bal ^ own_x[b];
+                }
+                const uint32_t at = __shfl_sync(0xffffffffu, cursor, part & (kLinkWarps - 1));
+                if (part < kLinkWarps) lists[at + __popc(peers & ltmask)] = (uint16_t)off;
+                cursor += __popc(mine);  // (lanes 16..31 count owners that do not exist: unused)
             }
-            uint32_t peers = part_peers(part);
-            if (part >= kLinkWarps) peers = 1u << lane;  // not insertable: alone
-            const uint32_t leader = __ffs(peers) - 1;
-            uint32_t at = 0;
-            if (lane == leader && part < kLinkWarps) {
-                at = cnt[w * 17 + part];
-                cnt[w * 17 + part] = at + __popc(peers);
-            }
-            at = __shfl_sync(0xffffffffu, at, leader);
-            if (part < kLinkWarps) lists[pstart[part] + at + __popc(peers & ltmask)] = (uint16_t)off;
-            __syncwarp();
         }
         __syncthreads();
         // ---- 3. every warp resolves its own list in order, 32 entries per step ----
