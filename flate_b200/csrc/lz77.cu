@@ -90,7 +90,7 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
         bool any_run = false;
         if (aligned) {
             const uint32_t* words = reinterpret_cast<const uint32_t*>(in + base);
-            const uint32_t nwords_total = (n - base + 3) / 4, nwords_full = (n - base) / 4;
+            const uint32_t nwords_total = (n - base + 3) / 4, nwords_full = (n - base) / 4, room = n - base;
             for (uint32_t i = tid; i < kLinkTile / 4; i += kLinkThreads) {
                 // whole words inside the stream; the last, partial word is assembled from its valid bytes
                 uint32_t w0 = 0, w1 = 0;
@@ -104,7 +104,7 @@ hash_link_kernel(const uint8_t* __restrict__ in, uint32_t begin, uint32_t range_
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++) {
                     const uint32_t off = i * 4 + k;
-                    const bool valid = off < cnt_pos && (uint64_t)base + off + 4 <= n;  // Lookup.zig:24 needs 4 bytes
+                    const bool valid = off + 4 <= room;  // Lookup.zig:24 needs 4 bytes (room = bytes from the tile's start to the stream's end)
                     hh[k] = valid ? hash_be(__funnelshift_r(w0, w1, 8 * k)) : 0xFFFFu;
                 }
                 any_run |= w0 == __byte_perm(w0, 0, 0x0321) && i < nwords_full;  // four equal bytes: a run of one byte may pass here
