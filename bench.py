@@ -717,10 +717,14 @@ def main():
                 out5[1] = ctx.compress_device(d5.data_ptr(), n5, d5_out.data_ptr(), cap5, mode=1, stream=sp)
                 out5[0] = d5_out
         else:
-            local5 = torch.empty((sh_bytes + sh_bytes // 8 + 4096 + 255) // 256 * 256, dtype=torch.uint8, device="cuda")
+            # every rank builds its own copy of the whole stream: its shard packed in place, the others' by broadcast
+            full5 = torch.empty((lib.fb200_compress_bound(n5, 1) + 64 + 255) // 256 * 256, dtype=torch.uint8, device="cuda")
 
             def c5_step():
-                out5[0], out5[1] = sharding.compress_simple_sharded(ctx, d5, lo5, hi5, n5, mode=1, container=0, local=local5)
+                out5[0], out5[1] = sharding.compress_simple_sharded(ctx, d5, lo5, hi5, n5, mode=1, container=0, out=full5)
+
+            def c5_step_in_place():
+                sharding.compress_simple_sharded(ctx, d5, lo5, hi5, n5, mode=1, container=0, out=full5, gather=False)
 
         c5_step()
         ctx.profile(True)
@@ -728,6 +732,11 @@ def main():
         ph5 = ctx.profile_read()
         ctx.profile(False)
         total5 = out5[1]
+        ms5_in_place = None
+        if world > 1:
+            c5_step_in_place()
+            ms5_in_place = timed(c5_step_in_place, max(2, args.steps // 2), warmup=1)
+            c5_step()   # (the parity check below reads the gathered stream)
         # e2e: N = 1 through fb200_compress with pinned host buffers; N > 1: host shard -> device, sharded compress
         # (all-gather included), this rank's share of the stream back to the host
         if world == 1:
@@ -746,7 +755,7 @@ def main():
 
             def c5_host():
                 d5.copy_(h5, non_blocking=True)
-                fin, tot = sharding.compress_simple_sharded(ctx, d5, lo5, hi5, n5, mode=1, container=0, local=local5)
+                fin, tot = sharding.compress_simple_sharded(ctx, d5, lo5, hi5, n5, mode=1, container=0, out=full5)
                 a = min(tot, rank * share)
                 b = min(tot, a + share)
                 h5_part[: b - a].copy_(fin[a:b], non_blocking=True)
@@ -757,11 +766,16 @@ def main():
         c5 = {"metric": "huffman-only MB/s in", "value": round(n5 / 1e6 / (ms5 / 1e3), 1), "unit": "MB/s", "ms_per_step": round(ms5, 3),
               "scaling": "strong", "higher_is_better": True,
               "workload": "huffman-only, ONE %d MiB random+zeros stream (runs of 4..256 KiB) over %d GPU(s) (BASELINE configs[4])%s"
-                          % (n5 // MIB, world, "; sharded by 65535-byte block ranges, shard outputs all-gathered over NCCL" if world > 1 else ""),
+                          % (n5 // MIB, world, "; sharded by 65535-byte block ranges, every shard packed at its bit offset into the rank's copy of "
+                                               "the stream and broadcast from there (NCCL), so that every rank ends with the whole stream" if world > 1 else ""),
               "ratio": round(n5 / total5, 3), "compressed_bytes": total5,
               "e2e": {"value": round(n5 / 1e6 / (hms5 / 1e3), 1), "unit": "MB/s", "ms_per_step": round(hms5, 3),
                       "h2d_bytes_per_step": sh_bytes, "d2h_bytes_per_step": d2h5},
               "roofline": roofline_of(ph5, (n5 + total5) / world, "huffman:%d" % (sh_bytes // MIB))}
+        if ms5_in_place is not None:
+            c5["shards_in_place"] = {"value": round(n5 / 1e6 / (ms5_in_place / 1e3), 1), "unit": "MB/s", "ms_per_step": round(ms5_in_place, 3),
+                                     "workload": "the same stream, left distributed: every rank keeps its own byte range of the stream (and the "
+                                                 "bytes it shares with its neighbours, exchanged as values); no bulk collective"}
         # parity: zlib inflates the stream back to the generated bytes (rank 0 regenerates the other ranks' ranges), and at
         # N = 1 the first 256 MiB of blocks equal the oracle's bit for bit (huffman-only blocks do not depend on each other)
         if rank == 0 and not args.skip_cpu:

@@ -173,11 +173,18 @@ def assemble_shards(final, gathered, pad, placements):
 _HEADERS = {0: b"", 1: bytes([0x1f, 0x8b, 0x08, 0, 0, 0, 0, 0, 0, 0x03]), 2: bytes([0x78, 0x9c])}  # container.zig:64,78
 
 
-def compress_simple_sharded(ctx, d_shard, lo, hi, n, mode=1, container=0, local=None):
+def compress_simple_sharded(ctx, d_shard, lo, hi, n, mode=1, container=0, local=None, out=None, gather=True):
     """One huffman-only (mode 1) or store (mode 0) stream of n bytes compressed by all ranks together: this rank holds
-    the stream's bytes [lo, hi) (its range from simple_shard_ranges) in the uint8 tensor d_shard.  Every rank ends up
-    with the whole compressed stream (all-gather of the per-shard outputs).  Returns (stream tensor, length).
-    Byte-identical with Context.compress_device on the whole stream."""
+    the stream's bytes [lo, hi) (its range from simple_shard_ranges) in the uint8 tensor d_shard.  Byte-identical with
+    Context.compress_device on the whole stream.  Returns (stream tensor, length).
+
+    With more than one rank every rank packs its shard straight into its own copy of the stream, at the bit offset the
+    exchange of the shard summaries gives it (exclusive scan with the stored-block re-alignment, block_writer.zig:283-291).
+    The bytes a shard owns alone then travel, in one grouped send/receive, into the same place of everybody's copy; the
+    bytes two shards share (a shard rarely starts on a byte boundary) are exchanged as values and OR-ed.  No staging
+    buffer, no copy after the collective.  gather=False leaves the stream distributed: this rank's copy is valid in its
+    own byte range only (returned as a third value), for callers that write the ranges out from where they are.
+    `out`: a uint8 tensor to build the stream in (at least the stream's size + 64 bytes), else one is allocated."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     dev = d_shard.device
@@ -199,27 +206,6 @@ def compress_simple_sharded(ctx, d_shard, lo, hi, n, mode=1, container=0, local=
         allm = [mine.tolist()]
     header = _HEADERS[container]
     starts, end_bit = shard_start_bits([(a[0], a[1], a[2]) for a in allm], 8 * len(header))
-    cap = (nbytes_in + nbytes_in // 8 + 1024 + 15) // 16 * 16
-    if local is None or local.numel() < cap:
-        local = torch.empty(cap, dtype=torch.uint8, device=dev)
-    if nbytes_in or is_last:
-        byte_lo, nb, _ = ctx.simple_shard_pack(starts[rank], local.data_ptr(), local.numel(), stream=sp)
-    else:
-        byte_lo, nb = starts[rank] >> 3, 0
-    place = torch.tensor([byte_lo, nb], dtype=torch.int64, device=dev)
-    if world > 1:
-        allp = [torch.zeros_like(place) for _ in range(world)]
-        dist.all_gather(allp, place)
-        placements = [tuple(t.tolist()) for t in allp]
-        pad = (max(p[1] for p in placements) + 255) // 256 * 256
-        if local.numel() < pad:
-            bigger = torch.zeros(pad, dtype=torch.uint8, device=dev)
-            bigger[:nb] = local[:nb]
-            local = bigger
-        gathered = torch.empty(world * pad, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(gathered, local[:pad])
-    else:
-        placements, pad, gathered = [(byte_lo, nb)], nb, local
     body_end = (end_bit + 7) >> 3
     footer = b""
     if container:
@@ -228,10 +214,62 @@ def compress_simple_sharded(ctx, d_shard, lo, hi, n, mode=1, container=0, local=
             total = ctx.crc32_combine(total, a[3], a[4]) if container == 1 else ctx.adler32_combine(total, a[3], a[4])
         footer = (int(total).to_bytes(4, "little") + int(n & 0xffffffff).to_bytes(4, "little")) if container == 1 \
             else int(total).to_bytes(4, "big")
-    final = torch.zeros(body_end + len(footer), dtype=torch.uint8, device=dev)
+    if world == 1:
+        cap = (nbytes_in + nbytes_in // 8 + 1024 + 15) // 16 * 16
+        if local is None or local.numel() < cap:
+            local = torch.empty(cap, dtype=torch.uint8, device=dev)
+        byte_lo, nb, _ = ctx.simple_shard_pack(starts[0], local.data_ptr(), local.numel(), stream=sp)
+        final = torch.zeros(body_end + len(footer), dtype=torch.uint8, device=dev)
+        if header:
+            final[: len(header)] = torch.frombuffer(bytearray(header), dtype=torch.uint8).to(dev)
+        assemble_shards(final, local, nb, [(byte_lo, nb)])
+        if footer:
+            final[body_end:] = torch.frombuffer(bytearray(footer), dtype=torch.uint8).to(dev)
+        return final, body_end + len(footer)
+
+    ends = starts[1:] + [end_bit]
+    size = (body_end + len(footer) + 64 + 15) // 16 * 16
+    final = out if out is not None and out.numel() >= size else torch.empty(size, dtype=torch.uint8, device=dev)
+    s_bit, e_bit = starts[rank], ends[rank]
+    if nbytes_in or is_last:
+        mine_lo = (s_bit >> 3) & ~15   # the pack's origin: 16-byte steps keep its word alignment
+        ctx.simple_shard_pack(s_bit, final.data_ptr() + mine_lo, (final.numel() - mine_lo) // 16 * 16, stream=sp)
+    # bytes shared with a neighbour: this rank's bits of them (its copy holds nothing else there yet)
+    first = final[s_bit >> 3: (s_bit >> 3) + 1] if e_bit > s_bit and s_bit & 7 else torch.zeros(1, dtype=torch.uint8, device=dev)
+    last = final[e_bit >> 3: (e_bit >> 3) + 1] if e_bit > s_bit and e_bit & 7 else torch.zeros(1, dtype=torch.uint8, device=dev)
+    edge = torch.cat([first, last]).to(torch.int64)
+    edges = [torch.zeros_like(edge) for _ in range(world)]
+    dist.all_gather(edges, edge)
+    pending = []
+    if gather:
+        # one grouped exchange: every rank sends its own bytes to every other rank's copy and receives theirs in place,
+        # all pairs at once (both directions of every NVLink / NVSwitch port busy; a broadcast per rank would take turns)
+        ops = []
+        for r in range(world):
+            a, b = (starts[r] + 7) >> 3, ends[r] >> 3   # bytes shard r owns alone
+            if b > a:
+                if r == rank:
+                    ops += [dist.P2POp(dist.isend, final[a:b], q) for q in range(world) if q != rank]
+                else:
+                    ops.append(dist.P2POp(dist.irecv, final[a:b], r))
+        if ops:
+            pending = dist.batch_isend_irecv(ops)
+    shared = {}
+    for r, ev in enumerate(t.tolist() for t in edges):
+        if ends[r] > starts[r]:
+            if starts[r] & 7:
+                shared[starts[r] >> 3] = shared.get(starts[r] >> 3, 0) | ev[0]
+            if ends[r] & 7:
+                shared[ends[r] >> 3] = shared.get(ends[r] >> 3, 0) | ev[1]
+    for w in pending:
+        w.wait()
+    if shared:
+        idx = torch.tensor(sorted(shared), dtype=torch.int64, device=dev)
+        final[idx] = torch.tensor([shared[k] for k in sorted(shared)], dtype=torch.uint8, device=dev)
     if header:
         final[: len(header)] = torch.frombuffer(bytearray(header), dtype=torch.uint8).to(dev)
-    assemble_shards(final, gathered, pad, placements)
     if footer:
-        final[body_end:] = torch.frombuffer(bytearray(footer), dtype=torch.uint8).to(dev)
-    return final, body_end + len(footer)
+        final[body_end: body_end + len(footer)] = torch.frombuffer(bytearray(footer), dtype=torch.uint8).to(dev)
+    if gather:
+        return final, body_end + len(footer)
+    return final, body_end + len(footer), ((s_bit + 7) >> 3, e_bit >> 3)

@@ -205,7 +205,11 @@ class _StubSimpleCtx:
         lo = (start_bit >> 3) & ~15
         bits = [0] * (start_bit - 8 * lo) + self.stream_bits(start_bit)
         raw = _bits_to_bytes(bits)
-        self.local[: len(raw)] = torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy())
+        # like the library: the region is zeroed a little past the shard's end (here: 12 bytes), then the bits go in,
+        # at the address the driver passes (its own copy of the stream, or a staging buffer when it runs alone)
+        import ctypes
+        assert d_out % 16 == 0 and len(raw) + 12 <= cap
+        ctypes.memmove(d_out, raw + bytes(12), len(raw) + 12)
         return lo, len(raw), start_bit + len(self.stream_bits(start_bit))
 
 
@@ -219,13 +223,17 @@ def _simple_worker(rank, world, port, q):
         lo, hi = ranges[rank]
         ctx.local = torch.zeros(1 << 18, dtype=torch.uint8)
         d_shard = torch.zeros(16, dtype=torch.uint8)
-        # stub: pack() writes into ctx.local, which is also the buffer handed to the driver
-        final, total = sharding.compress_simple_sharded(ctx, d_shard, lo, hi, 3 * 65535 + 17, mode=1, container=0, local=ctx.local)
+        final, total = sharding.compress_simple_sharded(ctx, d_shard, lo, hi, 3 * 65535 + 17, mode=1, container=0)
         # expected: the shards' bit strings one after the other, each re-aligned where it says so
         bits = []
         for r in range(world):
             bits += _StubSimpleCtx(r).stream_bits(len(bits))
-        q.put((rank, final[:total].numpy().tobytes() == _bits_to_bytes(bits), total))
+        want = _bits_to_bytes(bits)
+        ok = final[:total].numpy().tobytes() == want
+        # left distributed: this rank's copy is right in its own byte range and in the bytes shards share
+        part, total2, (a, b) = sharding.compress_simple_sharded(ctx, d_shard, lo, hi, 3 * 65535 + 17, mode=1, container=0, gather=False)
+        ok = ok and total2 == total and part[a:b].numpy().tobytes() == want[a:b]
+        q.put((rank, ok, total))
     finally:
         dist.destroy_process_group()
 
