@@ -31,6 +31,9 @@ for data in (rep, bytes(120000)):
         c = ctx.compress(data, 0, mode)
         assert zlib.decompress(c, -15) == data
 print("sparse repairs", ctx.sparse_repairs, "fallbacks", ctx.sparse_fallbacks)
+if os.environ.get("FB200_SANITIZE_QUICK"):   # the compress / decompress matrix and the repairs only
+    print("sanitize run ok (quick)")
+    sys.exit(0)
 w = io.BytesIO()
 comp = flate_b200.Compressor(1, w, 6, ctx=ctx)
 comp.write(text[:70001]); comp.flush(); comp.write(text[70001:70004]); comp.flush(); comp.write(text[70004:]); comp.finish()
