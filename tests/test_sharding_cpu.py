@@ -213,37 +213,41 @@ class _StubSimpleCtx:
         return lo, len(raw), start_bit + len(self.stream_bits(start_bit))
 
 
-def _simple_worker(rank, world, port, q):
+def _simple_worker(rank, world, port, q, n=3 * 65535 + 17):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         ctx = _StubSimpleCtx(rank)
-        ranges = sharding.simple_shard_ranges(3 * 65535 + 17, world)
+        ranges = sharding.simple_shard_ranges(n, world)
         lo, hi = ranges[rank]
-        ctx.local = torch.zeros(1 << 18, dtype=torch.uint8)
         d_shard = torch.zeros(16, dtype=torch.uint8)
-        final, total = sharding.compress_simple_sharded(ctx, d_shard, lo, hi, 3 * 65535 + 17, mode=1, container=0)
-        # expected: the shards' bit strings one after the other, each re-aligned where it says so
+        final, total = sharding.compress_simple_sharded(ctx, d_shard, lo, hi, n, mode=1, container=0)
+        # expected: the bit strings of the shards that hold anything (a rank without slices emits nothing, the last
+        # rank always emits: it owns the final block), one after the other, each re-aligned where it says so
         bits = []
         for r in range(world):
-            bits += _StubSimpleCtx(r).stream_bits(len(bits))
+            if ranges[r][1] > ranges[r][0] or r == world - 1:
+                bits += _StubSimpleCtx(r).stream_bits(len(bits))
         want = _bits_to_bytes(bits)
         ok = final[:total].numpy().tobytes() == want
         # left distributed: this rank's copy is right in its own byte range and in the bytes shards share
-        part, total2, (a, b) = sharding.compress_simple_sharded(ctx, d_shard, lo, hi, 3 * 65535 + 17, mode=1, container=0, gather=False)
+        part, total2, (a, b) = sharding.compress_simple_sharded(ctx, d_shard, lo, hi, n, mode=1, container=0, gather=False)
         ok = ok and total2 == total and part[a:b].numpy().tobytes() == want[a:b]
         q.put((rank, ok, total))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_block_range_sharded_driver(world):
+@pytest.mark.parametrize("world,n", [(2, 3 * 65535 + 17), (3, 3 * 65535 + 17), (3, 65535 + 17), (4, 100)])
+def test_block_range_sharded_driver(world, n):
+    """The driver of the block-range sharded stream over gloo with a stub context: shards of a few bytes that share
+    boundary bytes (up to three shards in one byte), ranks without any slice (n = 65535 + 17 over 3 ranks leaves the
+    middle rank empty; n = 100 over 4 ranks leaves everything to the last one)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_simple_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_simple_worker, args=(r, world, port, q, n)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
