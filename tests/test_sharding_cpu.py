@@ -192,8 +192,22 @@ class _StubSimpleCtx:
         self.has = rank % 2 == 0
         self.post = [int(b) for b in rng.integers(0, 2, 8 * (5 + rank))] if self.has else []
 
+    def plain(self, nbytes):
+        """The bytes this rank's shard stands for (only their checksum matters to the driver)."""
+        return np.random.default_rng(500 + len(self.pre)).integers(0, 256, nbytes, dtype=np.uint8).tobytes()
+
     def simple_shard_plan(self, d_in, nbytes, is_last, mode=1, container=0, stream=None):
-        return len(self.pre), int(self.has), len(self.post), 0
+        import zlib
+        sm = zlib.crc32(self.plain(nbytes)) if container == 1 else zlib.adler32(self.plain(nbytes)) if container == 2 else 0
+        return len(self.pre), int(self.has), len(self.post), sm
+
+    def crc32_combine(self, a, b, len2):
+        from flate_b200 import _lib
+        return int(_lib.load().fb200_crc32_combine(a, b, len2))
+
+    def adler32_combine(self, a, b, len2):
+        from flate_b200 import _lib
+        return int(_lib.load().fb200_adler32_combine(a, b, len2))
 
     def stream_bits(self, x):
         bits = list(self.pre)
@@ -234,6 +248,17 @@ def _simple_worker(rank, world, port, q, n=3 * 65535 + 17):
         # left distributed: this rank's copy is right in its own byte range and in the bytes shards share
         part, total2, (a, b) = sharding.compress_simple_sharded(ctx, d_shard, lo, hi, n, mode=1, container=0, gather=False)
         ok = ok and total2 == total and part[a:b].numpy().tobytes() == want[a:b]
+        # gzip and zlib: header, the same bits behind it, and a footer from the combined per-shard checksums
+        import zlib
+        plain = b"".join(_StubSimpleCtx(r).plain(ranges[r][1] - ranges[r][0]) for r in range(world))
+        for container, hdr, foot in ((1, sharding._HEADERS[1], zlib.crc32(plain).to_bytes(4, "little") + (n & 0xffffffff).to_bytes(4, "little")),
+                                    (2, sharding._HEADERS[2], zlib.adler32(plain).to_bytes(4, "big"))):
+            bits = []
+            for r in range(world):
+                if ranges[r][1] > ranges[r][0] or r == world - 1:
+                    bits += _StubSimpleCtx(r).stream_bits(8 * len(hdr) + len(bits))
+            got, tot = sharding.compress_simple_sharded(ctx, d_shard, lo, hi, n, mode=1, container=container)
+            ok = ok and got[:tot].numpy().tobytes() == hdr + _bits_to_bytes(bits) + foot
         q.put((rank, ok, total))
     finally:
         dist.destroy_process_group()
